@@ -1,0 +1,141 @@
+"""Synthetic Gaussians and cameras of the shapes named in BASELINE.json / SURVEY.md section 8d.
+
+Camera matrices follow the reference conventions: ``world_view_transform`` and
+``full_proj_transform`` are the TRANSPOSED (row-vector) 4x4 tensors built in
+scene/cameras.py:71-78 from utils/graphics_utils.py:38-74 (znear 0.01, zfar 100).
+Everything is generated on the CPU from ``torch.Generator().manual_seed(seed)``.
+"""
+import math
+from dataclasses import dataclass
+
+import torch
+
+ZNEAR, ZFAR = 0.01, 100.0
+
+
+@dataclass
+class SynthCamera:
+    image_width: int
+    image_height: int
+    FoVx: float
+    FoVy: float
+    world_view_transform: torch.Tensor   # [4,4], transposed
+    full_proj_transform: torch.Tensor    # [4,4], transposed
+    camera_center: torch.Tensor          # [3]
+    bClusterOccur = None
+
+    @property
+    def tanfovx(self):
+        return math.tan(self.FoVx * 0.5)
+
+    @property
+    def tanfovy(self):
+        return math.tan(self.FoVy * 0.5)
+
+    def to(self, device):
+        return SynthCamera(self.image_width, self.image_height, self.FoVx, self.FoVy,
+                           self.world_view_transform.to(device), self.full_proj_transform.to(device),
+                           self.camera_center.to(device))
+
+
+def projection_matrix(fovx: float, fovy: float, znear: float = ZNEAR, zfar: float = ZFAR) -> torch.Tensor:
+    """Perspective matrix with z_sign = +1 (utils/graphics_utils.py:54-74), NOT transposed."""
+    tx, ty = math.tan(fovx / 2), math.tan(fovy / 2)
+    P = torch.zeros(4, 4, dtype=torch.float64)
+    P[0, 0] = 1.0 / tx
+    P[1, 1] = 1.0 / ty
+    P[3, 2] = 1.0
+    P[2, 2] = zfar / (zfar - znear)
+    P[2, 3] = -(zfar * znear) / (zfar - znear)
+    return P
+
+
+def look_at(eye, target, W: int, H: int, fovx: float, up=(0.0, 0.0, 1.0)) -> SynthCamera:
+    """COLMAP-style camera (x right, y down, z forward) at `eye` looking at `target`."""
+    eye = torch.as_tensor(eye, dtype=torch.float64)
+    target = torch.as_tensor(target, dtype=torch.float64)
+    up = torch.as_tensor(up, dtype=torch.float64)
+    fwd = target - eye
+    fwd = fwd / fwd.norm()
+    right = torch.linalg.cross(fwd, up)
+    if right.norm() < 1e-8:
+        right = torch.linalg.cross(fwd, torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64))
+    right = right / right.norm()
+    down = torch.linalg.cross(fwd, right)
+    Rwc = torch.stack([right, down, fwd], 0)          # world -> camera rotation
+    V = torch.eye(4, dtype=torch.float64)
+    V[:3, :3] = Rwc
+    V[:3, 3] = -Rwc @ eye
+    fovy = 2.0 * math.atan(math.tan(fovx / 2) * H / W)
+    Pm = projection_matrix(fovx, fovy)
+    wvt = V.t().contiguous()
+    full = (wvt @ Pm.t()).contiguous()
+    return SynthCamera(W, H, fovx, fovy, wvt.float(), full.float(), eye.float())
+
+
+def orbit_cameras(n: int, radius: float, W: int, H: int, fovx: float, height: float = 0.0,
+                  target=(0.0, 0.0, 0.0), phase: float = 0.0):
+    cams = []
+    for i in range(n):
+        a = phase + 2 * math.pi * i / max(n, 1)
+        eye = (target[0] + radius * math.cos(a), target[1] + radius * math.sin(a), target[2] + height)
+        cams.append(look_at(eye, target, W, H, fovx))
+    return cams
+
+
+def make_gaussians(P: int, kind: str = "blender", seed: int = 0, sh_degree: int = 3, feat_dim: int = 6,
+                   scale_mult: float = 0.6):
+    """Returns a dict of ACTIVATED parameters in the layouts the rasterizer consumes
+    (what GaussianModel's getters return: scene/gaussian_model.py:122-169)."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == "blender":            # U(-1.3, 1.3)^3, scene/dataset_readers.py:346
+        xyz = (torch.rand(P, 3, generator=g) * 2 - 1) * 1.3
+        vol = 2.6 ** 3
+    elif kind == "room":             # ScanNet-like 8 x 6 x 3 m room centred at the origin
+        ext = torch.tensor([8.0, 6.0, 3.0])
+        xyz = (torch.rand(P, 3, generator=g) - 0.5) * ext
+        vol = 8.0 * 6.0 * 3.0
+    elif kind == "lerf":             # 70 % N(0, 1.5^2) core + 30 % shell out to radius 20
+        n_core = int(P * 0.7)
+        core = torch.randn(n_core, 3, generator=g) * 1.5
+        d = torch.randn(P - n_core, 3, generator=g)
+        d = d / d.norm(dim=1, keepdim=True)
+        r = 4.0 + torch.rand(P - n_core, 1, generator=g) * 16.0
+        xyz = torch.cat([core, d * r], 0)
+        vol = 4.0 / 3.0 * math.pi * 4.5 ** 3
+    else:
+        raise ValueError(kind)
+    mean_nn = (vol / P) ** (1.0 / 3.0)
+    log_s = math.log(scale_mult * mean_nn) + 0.4 * torch.randn(P, 3, generator=g)
+    scales = torch.exp(log_s)
+    if kind == "lerf":               # shell Gaussians are sparser -> proportionally larger
+        n_core = int(P * 0.7)
+        scales[n_core:] *= 6.0
+    rot = torch.randn(P, 4, generator=g)
+    rot = rot / rot.norm(dim=1, keepdim=True)
+    opacity = torch.sigmoid(2.0 * torch.randn(P, 1, generator=g))
+    M = (3 + 1) ** 2
+    shs = torch.zeros(P, M, 3)
+    shs[:, 0] = torch.randn(P, 3, generator=g) * 0.25 / 0.2821
+    shs[:, 1:] = torch.randn(P, M - 1, 3, generator=g) * 0.05
+    ins_feat = torch.rand(P, feat_dim, generator=g)
+    return dict(means3D=xyz.contiguous(), scales=scales.contiguous(), rotations=rot.contiguous(),
+                opacities=opacity.contiguous(), shs=shs.contiguous(), ins_feat=ins_feat.contiguous(),
+                sh_degree=sh_degree)
+
+
+SCENES = {
+    # name: (kind, P, W, H, fovx, camera radius, camera height)
+    "plumbing_10k_256": ("blender", 10_000, 256, 256, 0.69, 4.0, 1.0),
+    "blender_300k_800": ("blender", 300_000, 800, 800, 0.69, 4.0, 1.0),
+    "scannet_1m_1296x968": ("room", 1_000_000, 1296, 968, 2 * math.atan(1296 / (2 * 1170.0)), 2.5, 0.3),
+    "lerf_1m_1080p": ("lerf", 1_000_000, 1920, 1080, 1.0, 5.0, 1.0),
+    "lerf_3m_1080p": ("lerf", 3_000_000, 1920, 1080, 1.0, 5.0, 1.0),
+}
+
+
+def make_scene(name: str, n_views: int = 8, seed: int = 0, P: int = None):
+    kind, P0, W, H, fovx, rad, height = SCENES[name]
+    gs = make_gaussians(P or P0, kind, seed)
+    cams = orbit_cameras(n_views, rad, W, H, fovx, height)
+    return gs, cams
