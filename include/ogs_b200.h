@@ -1,0 +1,160 @@
+/*
+ * ogs_b200.h -- C ABI of libogs_b200.so, the B200 (sm_100a) hot path of OpenGaussian:
+ * the tile-based differentiable Gaussian rasterizer and the k-means codebook kernels.
+ *
+ * Every entry point: plain pointers and sizes, no torch types, returns int
+ * (0 = ok, < 0 = argument error, > 0 = cudaError_t), never throws.  ogs_last_error()
+ * returns a thread-local message for the last non-zero return.
+ * All pointers are DEVICE pointers unless the name ends in _host.  All kernels are enqueued on
+ * `stream` (a cudaStream_t passed as void*).  Arrays are contiguous, row-major, fp32 unless said.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *   ogs_raster_forward / ogs_raster_backward
+ *       the external package `ashawkey_diff_gaussian_rasterization` that
+ *       gaussian_renderer/__init__.py:15,55-70,104-163,203-225,327-345 and
+ *       utils/sam_refinement_utils.py:21,347-403,431-486 import and call (upstream pybind
+ *       symbols rasterize_gaussians / rasterize_gaussians_backward).  The C ABI additionally
+ *       composites `n_extra` per-Gaussian feature channels (OpenGaussian's ins_feat) in the same
+ *       pass, which replaces the 2x3-channel feature passes + silhouette pass of
+ *       gaussian_renderer/__init__.py:125-163.
+ *   ogs_mark_visible             upstream GaussianRasterizer.markVisible (mark_visible symbol)
+ *   ogs_raster_export_keys       debug view of the sorted (tile|depth) keys (upstream binningState)
+ *   ogs_kmeans_assign            scene/kmeans_quantize.py:38-55 (get_dist) + :181-182,:200-201,
+ *                                :223-224,:237-238 (argmin) fused with :82-87,:183-187,:202-205
+ *                                (one-hot centroid sums and counts)
+ *   ogs_kmeans_finalize          scene/kmeans_quantize.py:208-214 (centres = sums / counts, reset)
+ *   ogs_kmeans_gather_st         scene/kmeans_quantize.py:273-275 (gather centres, straight-through)
+ *   ogs_kmeans_cluster_index     scene/kmeans_quantize.py:89-144 (equalize_cluster_size index lists)
+ */
+#ifndef OGS_B200_H
+#define OGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGS_ABI_VERSION 1
+#define OGS_TILE 16
+#define OGS_MAX_CHANNELS 16 /* 3 colour channels + n_extra <= OGS_MAX_CHANNELS */
+
+/* Allocation callback (same role as upstream's resize functional): returns a device pointer to
+ * `bytes` bytes (>= 256-byte aligned) owned by the caller, alive until the matching backward
+ * has run.  `tag` names the buffer ("geom", "binning", "image"). */
+typedef void* (*ogs_alloc_fn)(void* user, size_t bytes, const char* tag);
+
+typedef struct ogs_raster_inputs {
+    int32_t P;              /* number of Gaussians */
+    int32_t sh_degree;      /* active SH degree (0..3) */
+    int32_t M;              /* SH coefficients per Gaussian in `shs` (e.g. 16), 0 if shs == NULL */
+    int32_t n_extra;        /* extra feature channels composited beside RGB (0 or e.g. 6) */
+    int32_t W, H;           /* image size in pixels */
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    int32_t prefiltered;    /* kept for API parity; must be 0 */
+    int32_t debug;          /* != 0: synchronise and check for errors after every kernel */
+    const float* bg;        /* [3 + n_extra] background (device) */
+    const float* viewmatrix;/* [16] raw floats of the transposed world->view tensor (device) */
+    const float* projmatrix;/* [16] raw floats of the transposed full projection tensor (device) */
+    const float* campos;    /* [3] (device) */
+    const float* means3D;   /* [P,3] */
+    const float* opacities; /* [P] */
+    const float* shs;       /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3] or NULL (exactly one of shs / colors_precomp) */
+    const float* scales;    /* [P,3] or NULL */
+    const float* rotations; /* [P,4] or NULL (scales+rotations, or cov3D_precomp) */
+    const float* cov3D_precomp;  /* [P,6] or NULL */
+    const float* extra;     /* [P,n_extra] or NULL when n_extra == 0 */
+} ogs_raster_inputs;
+
+typedef struct ogs_raster_outputs {
+    float* color;    /* [3 + n_extra, H, W] planar */
+    float* depth;    /* [H, W]  sum depth*alpha*T (no background, not normalised) */
+    float* alpha;    /* [H, W]  1 - T_final */
+    int32_t* radii;  /* [P] */
+} ogs_raster_outputs;
+
+/* Opaque-to-the-caller state filled by forward and consumed by backward / export. */
+typedef struct ogs_raster_state {
+    void* geom;      /* per-Gaussian records (rec0/rec1 float4, rgb, clamped, tiles_touched) */
+    void* binning;   /* point_list uint32[N] followed by ranges uint2[tiles] */
+    void* image;     /* final_T float[H*W], n_contrib uint32[H*W] */
+    int64_t num_rendered; /* N = number of (Gaussian, tile) duplicates */
+    int64_t geom_bytes, binning_bytes, image_bytes;
+} ogs_raster_state;
+
+typedef struct ogs_raster_grads_in {
+    const float* dL_dcolor;  /* [3 + n_extra, H, W] */
+    const float* dL_ddepth;  /* [H, W] or NULL */
+    const float* dL_dalpha;  /* [H, W] or NULL */
+} ogs_raster_grads_in;
+
+/* Any output pointer may be NULL: that gradient is then not produced.  If all of the geometry
+ * gradients (means3D, means2D, opacities, scales, rotations, cov3D, shs) are NULL the cheap
+ * colour-only backward is used (OpenGaussian stages 1-2, train.py:431-436). */
+typedef struct ogs_raster_grads_out {
+    float* dL_dmeans3D;   /* [P,3] */
+    float* dL_dmeans2D;   /* [P,3]  (x,y in NDC-scaled units, z = 0) */
+    float* dL_dopacities; /* [P] */
+    float* dL_dshs;       /* [P,M,3] */
+    float* dL_dcolors_precomp; /* [P,3] */
+    float* dL_dscales;    /* [P,3] */
+    float* dL_drotations; /* [P,4] */
+    float* dL_dcov3D;     /* [P,6] */
+    float* dL_dextra;     /* [P,n_extra] */
+    void* scratch;        /* [P * (3 + n_extra + 8)] floats of caller-provided workspace */
+} ogs_raster_grads_out;
+
+int ogs_abi_version(void);
+const char* ogs_last_error(void);
+
+int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* out,
+                       ogs_alloc_fn alloc, void* alloc_user, ogs_raster_state* state, void* stream);
+
+int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* state,
+                        const ogs_raster_grads_in* gin, const ogs_raster_grads_out* gout,
+                        void* stream);
+
+size_t ogs_raster_backward_scratch_floats(int32_t P, int32_t n_extra);
+
+int ogs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                     void* stream);
+
+/* Debug/export: geometry records and the sorted (tile << 32 | depth bits) keys rebuilt from the
+ * state.  Any output may be NULL.  keys/point_list: [N]; ranges: [tiles][2] uint32;
+ * xy [P,2]; depth [P]; conic_opacity [P,4]; rgb [P,3]; tiles_touched uint32 [P];
+ * final_T [H*W]; n_contrib uint32 [H*W]. */
+int ogs_raster_export(const ogs_raster_inputs* in, const ogs_raster_state* state, uint64_t* keys,
+                      uint32_t* point_list, uint32_t* ranges, float* xy, float* depth,
+                      float* conic_opacity, float* rgb, uint32_t* tiles_touched, float* final_T,
+                      uint32_t* n_contrib, void* stream);
+
+/* ---- k-means codebook ----
+ * A point is the concatenation [a (Da floats) | b (Db floats) * scale_b]  (b may be NULL, Db = 0).
+ * ids are int64 (the reference's torch.argmin dtype).  If select_ids != NULL only points with
+ * select_ids[i] == selected take part (leaf mode); others keep ids_out[i] untouched.
+ * sums [k, Da+Db] and counts [k] are ACCUMULATED into (caller zeroes them); either may be NULL
+ * to skip the centroid-sum fusion (pure reassign). */
+int ogs_kmeans_assign(int64_t N, const float* a, int32_t Da, const float* b, int32_t Db,
+                      float scale_b, const float* centers, int32_t k, const int64_t* select_ids,
+                      int64_t selected, int64_t id_offset, int64_t* ids_out, float* sums,
+                      float* counts, void* stream);
+
+/* centers_out[j, :] = sums[j, :] / (counts[j] + eps_count)  for j in [0, k). */
+int ogs_kmeans_finalize(int32_t k, int32_t D, const float* sums, const float* counts,
+                        float eps_count, float* centers_out, void* stream);
+
+/* out[i, :] = feat[i, :] - feat[i, :] + centers[ids[i], :Dout]  evaluated as the reference does
+ * (x - x + c in fp32), i.e. the forward value of the straight-through quantised feature. */
+int ogs_kmeans_gather_st(int64_t N, const float* feat, int32_t Dout, const float* centers,
+                         int32_t Dc, const int64_t* ids, float* out, void* stream);
+
+/* Per-cluster member counts: counts_out int64 [k] (zeroed by the call). */
+int ogs_kmeans_count(int64_t N, const int64_t* ids, int32_t k, int64_t* counts_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGS_B200_H */

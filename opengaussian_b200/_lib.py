@@ -1,0 +1,98 @@
+"""ctypes binding of libogs_b200.so (the C ABI declared in include/ogs_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libogs_b200.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p)
+_fp = C.c_void_p
+
+
+class RasterInputs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32), ("n_extra", C.c_int32),
+        ("W", C.c_int32), ("H", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("bg", _fp), ("viewmatrix", _fp), ("projmatrix", _fp), ("campos", _fp),
+        ("means3D", _fp), ("opacities", _fp), ("shs", _fp), ("colors_precomp", _fp),
+        ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp), ("extra", _fp),
+    ]
+
+
+class RasterOutputs(C.Structure):
+    _fields_ = [("color", _fp), ("depth", _fp), ("alpha", _fp), ("radii", _fp)]
+
+
+class RasterState(C.Structure):
+    _fields_ = [("geom", _fp), ("binning", _fp), ("image", _fp), ("num_rendered", C.c_int64),
+                ("geom_bytes", C.c_int64), ("binning_bytes", C.c_int64), ("image_bytes", C.c_int64)]
+
+
+class RasterGradsIn(C.Structure):
+    _fields_ = [("dL_dcolor", _fp), ("dL_ddepth", _fp), ("dL_dalpha", _fp)]
+
+
+class RasterGradsOut(C.Structure):
+    _fields_ = [("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dopacities", _fp), ("dL_dshs", _fp),
+                ("dL_dcolors_precomp", _fp), ("dL_dscales", _fp), ("dL_drotations", _fp),
+                ("dL_dcov3D", _fp), ("dL_dextra", _fp), ("scratch", _fp)]
+
+
+EXPORTS = {
+    "ogs_abi_version": (C.c_int, []),
+    "ogs_last_error": (C.c_char_p, []),
+    "ogs_raster_forward": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterOutputs), ALLOC_FN, C.c_void_p,
+                                     C.POINTER(RasterState), C.c_void_p]),
+    "ogs_raster_backward": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterState), C.POINTER(RasterGradsIn),
+                                      C.POINTER(RasterGradsOut), C.c_void_p]),
+    "ogs_raster_backward_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "ogs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_raster_export": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterState)] + [_fp] * 10 + [C.c_void_p]),
+    "ogs_kmeans_assign": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, C.c_int32, C.c_float, _fp, C.c_int32, _fp,
+                                    C.c_int64, C.c_int64, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_kmeans_finalize": (C.c_int, [C.c_int32, C.c_int32, _fp, _fp, C.c_float, _fp, C.c_void_p]),
+    "ogs_kmeans_gather_st": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_void_p]),
+    "ogs_kmeans_count": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, C.c_void_p]),
+}
+
+_LIB = None
+
+
+class OgsError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise OgsError(f"{LIB_PATH} not found: run `python -m opengaussian_b200.build` "
+                           "(the sm_100a CUDA extension is mandatory; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.ogs_abi_version() != 1:
+            raise OgsError("libogs_b200.so ABI version mismatch")
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().ogs_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise Exception(msg)          # same exception type/message as the reference Python layer
+        raise OgsError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) tensor or None."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,118 @@
+// binning.cu -- builds the per-tile, depth-ordered Gaussian lists.
+//
+// Replaces upstream InclusiveSum + duplicateWithKeys + 64-bit RadixSort + identifyTileRanges of the
+// external rasterizer.  The upstream order is: stable ascending sort
+// of (tile << 32 | depth bits) with ties kept in Gaussian-index order.  The SAME order is produced
+// here with ~6x less sort traffic (SURVEY.md section 7 "Sort cost"):
+//   1. stable sort of the P Gaussians by depth bits (32-bit keys, P items; culled -> 0xFFFFFFFF),
+//   2. inclusive scan of tiles_touched in that order,
+//   3. emit one (tile id uint16, Gaussian idx) pair per touched tile, row-major inside the rect,
+//   4. stable sort of the N pairs by tile id only (<= 13 bits),
+//   5. tile ranges from the sorted tile ids.
+// Inside one tile every entry belongs to a distinct Gaussian, so (depth, index) order inside a tile
+// after step 4 is exactly the upstream order: point_list and ranges are bit-identical; the 64-bit
+// keys are rebuilt on demand by ogs_raster_export for parity tests.
+//
+// Compiled with --fmad=false (the tile-rect arithmetic must match preprocess.cu / the oracle).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ogs {
+
+struct TilesOfSorted {
+    const uint32_t* tiles;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& g) const { return tiles[g]; }
+};
+
+size_t depth_sort_temp_bytes(int P) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, P, 0, 32);
+    cub::TransformInputIterator<uint32_t, TilesOfSorted, const uint32_t*> it(nullptr, TilesOfSorted{nullptr});
+    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, P);
+    return a > b ? a : b;
+}
+
+size_t tile_sort_temp_bytes(int64_t N) {
+    size_t a = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint16_t*)nullptr, (uint16_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)N, 0, 16);
+    return a;
+}
+
+int depth_sort_and_scan(int P, const GeomPtrs& g, BinScratch& sc, cudaStream_t s, int debug) {
+    size_t tb = sc.cub_temp_bytes;
+    OGS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_temp, tb, sc.dkeys_in, sc.dkeys_out, sc.dvals_in,
+                                             sc.dvals_out, P, 0, 32, s));
+    cub::TransformInputIterator<uint32_t, TilesOfSorted, const uint32_t*> it(sc.dvals_out, TilesOfSorted{g.tiles});
+    tb = sc.cub_temp_bytes;
+    OGS_CUDA(cub::DeviceScan::InclusiveSum(sc.cub_temp, tb, it, sc.offsets, P, s));
+    OGS_KERNEL_CHECK("depth_sort_and_scan", debug, s);
+    return 0;
+}
+
+__device__ __forceinline__ int imin_(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int imax_(int a, int b) { return a > b ? a : b; }
+
+__global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, const uint32_t* __restrict__ order,
+                                                   const uint32_t* __restrict__ offsets,
+                                                   const float4* __restrict__ rec0, const float4* __restrict__ rec1,
+                                                   uint16_t* __restrict__ tkeys, uint32_t* __restrict__ tvals) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    const uint32_t g = order[i];
+    const float4 b = rec1[g];
+    const int radius = __float_as_int(b.w);
+    if (radius <= 0) return;
+    const float4 a = rec0[g];
+    const float r = (float)radius;
+    const int x0 = imin_(gx, imax_(0, (int)((a.x - r) / 16.0f)));
+    const int y0 = imin_(gy, imax_(0, (int)((a.y - r) / 16.0f)));
+    const int x1 = imin_(gx, imax_(0, (int)((a.x + r + 15.0f) / 16.0f)));
+    const int y1 = imin_(gy, imax_(0, (int)((a.y + r + 15.0f) / 16.0f)));
+    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+            tkeys[off] = (uint16_t)(y * gx + x);
+            tvals[off] = g;
+            off++;
+        }
+}
+
+__global__ void __launch_bounds__(256) ranges_kernel(int64_t N, const uint16_t* __restrict__ tk,
+                                                     uint2* __restrict__ ranges) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t t = tk[i];
+    if (i == 0) ranges[t].x = 0;
+    else {
+        const uint32_t pt = tk[i - 1];
+        if (t != pt) { ranges[pt].y = (uint32_t)i; ranges[t].x = (uint32_t)i; }
+    }
+    if (i == N - 1) ranges[t].y = (uint32_t)N;
+}
+
+int emit_sort_ranges(int P, int W, int H, int64_t N, const GeomPtrs& g, BinScratch& sc, uint16_t* tkeys_in,
+                     uint32_t* tvals_in, uint16_t* tkeys_out, uint32_t* point_list, uint2* ranges,
+                     cudaStream_t s, int debug) {
+    const int gx = (W + 15) / 16, gy = (H + 15) / 16;
+    const int tiles = gx * gy;
+    OGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
+    if (N == 0) return 0;
+    emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, gx, gy, sc.dvals_out, sc.offsets, g.rec0, g.rec1, tkeys_in,
+                                                tvals_in);
+    OGS_KERNEL_CHECK("emit_kernel", debug, s);
+    int bits = 0;
+    while ((1 << bits) < tiles) bits++;
+    if (bits == 0) bits = 1;
+    size_t tb = sc.cub_temp_bytes;
+    OGS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_temp, tb, tkeys_in, tkeys_out, tvals_in, point_list, (int)N, 0,
+                                             bits, s));
+    OGS_KERNEL_CHECK("tile_sort", debug, s);
+    ranges_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(N, tkeys_out, ranges);
+    OGS_KERNEL_CHECK("ranges_kernel", debug, s);
+    return 0;
+}
+
+}  // namespace ogs

@@ -1,0 +1,331 @@
+// capi.cu -- the extern "C" boundary of libogs_b200.so (declared in include/ogs_b200.h).
+// Orchestrates the kernel families; owns no long-lived memory: per-call state lives in buffers
+// obtained through the caller's allocation callback (same role as upstream's resize functionals),
+// transient sort scratch comes from the stream-ordered CUDA memory pool.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ogs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e > 0 ? (int)e : 999;
+}
+
+static int ensure_pool(void) {
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    OGS_CUDA(cudaGetDevice(&dev));
+    if (done_dev == dev) return 0;
+    cudaMemPool_t pool;
+    OGS_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX;
+    OGS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    done_dev = dev;
+    return 0;
+}
+
+static uint32_t* pinned_scalar(void) {
+    static thread_local uint32_t* p = nullptr;
+    if (!p) {
+        if (cudaMallocHost((void**)&p, 64) != cudaSuccess) p = nullptr;
+    }
+    return p;
+}
+
+__global__ void export_keys_kernel(int tiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                   const float4* __restrict__ rec1, uint64_t* __restrict__ keys) {
+    const int t = blockIdx.x;
+    if (t >= tiles) return;
+    const uint2 r = ranges[t];
+    for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x) {
+        const uint32_t g = point_list[i];
+        keys[i] = ((uint64_t)(uint32_t)t << 32) | (uint64_t)__float_as_uint(rec1[g].z);
+    }
+}
+
+__global__ void export_geom_kernel(int P, GeomPtrs g, bool has_rgb, float* xy, float* depth, float* conic_opacity,
+                                   float* rgb, uint32_t* tiles) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float4 a = g.rec0[i], b = g.rec1[i];
+    if (xy) { xy[2 * i] = a.x; xy[2 * i + 1] = a.y; }
+    if (depth) depth[i] = b.z;
+    if (conic_opacity) {
+        conic_opacity[4 * i] = a.z; conic_opacity[4 * i + 1] = a.w; conic_opacity[4 * i + 2] = b.x;
+        conic_opacity[4 * i + 3] = b.y;
+    }
+    if (rgb && has_rgb) { rgb[3 * i] = g.rgb[3 * i]; rgb[3 * i + 1] = g.rgb[3 * i + 1]; rgb[3 * i + 2] = g.rgb[3 * i + 2]; }
+    if (tiles) tiles[i] = g.tiles[i];
+}
+
+static int validate_inputs(const ogs_raster_inputs* in) {
+    if (!in) { set_error("inputs is NULL"); return -1; }
+    if (in->P < 0 || in->W <= 0 || in->H <= 0) { set_error("bad sizes P=%d W=%d H=%d", in->P, in->W, in->H); return -1; }
+    if ((in->shs != nullptr) == (in->colors_precomp != nullptr) && in->P > 0) {
+        set_error("Please provide excatly one of either SHs or precomputed colors!");
+        return -2;
+    }
+    const bool sr = in->scales != nullptr && in->rotations != nullptr;
+    if (in->P > 0 && (sr == (in->cov3D_precomp != nullptr) || ((in->scales != nullptr) != (in->rotations != nullptr)))) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        return -2;
+    }
+    if (in->n_extra < 0 || 3 + in->n_extra > OGS_MAX_CHANNELS) { set_error("n_extra=%d out of range", in->n_extra); return -1; }
+    if (in->n_extra > 0 && !in->extra && in->P > 0) { set_error("n_extra > 0 but extra is NULL"); return -1; }
+    if (in->shs && (in->sh_degree < 0 || in->sh_degree > 3 || (in->sh_degree + 1) * (in->sh_degree + 1) > in->M)) {
+        set_error("sh_degree=%d incompatible with M=%d", in->sh_degree, in->M);
+        return -1;
+    }
+    if (in->prefiltered) { set_error("prefiltered=True is not supported"); return -1; }
+    const int gx = (in->W + 15) / 16, gy = (in->H + 15) / 16;
+    if ((int64_t)gx * gy > 65535) { set_error("image too large: %d tiles (max 65535)", gx * gy); return -1; }
+    if (!in->bg || !in->viewmatrix || !in->projmatrix || !in->campos) { set_error("bg/viewmatrix/projmatrix/campos must be set"); return -1; }
+    return 0;
+}
+
+}  // namespace ogs
+
+using namespace ogs;
+
+extern "C" {
+
+int ogs_abi_version(void) { return OGS_ABI_VERSION; }
+const char* ogs_last_error(void) { return g_err; }
+
+size_t ogs_raster_backward_scratch_floats(int32_t P, int32_t n_extra) {
+    return (size_t)(P > 0 ? P : 1) * (size_t)(3 + n_extra + 7);
+}
+
+int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* out, ogs_alloc_fn alloc,
+                       void* alloc_user, ogs_raster_state* st, void* stream_) {
+    int rc = validate_inputs(in);
+    if (rc) return rc;
+    if (!out || !out->color || !out->depth || !out->alpha || !out->radii || !alloc || !st) {
+        set_error("outputs/alloc/state must be set");
+        return -1;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    if ((rc = ensure_pool())) return rc;
+    const int P = in->P, W = in->W, H = in->H, C = 3 + in->n_extra;
+    const int gx = (W + 15) / 16, gy = (H + 15) / 16, tiles = gx * gy;
+    const bool has_sh = in->shs != nullptr;
+
+    const GeomLayout gl = GeomLayout::make(P, has_sh);
+    const ImgLayout il = ImgLayout::make(W, H);
+    memset(st, 0, sizeof *st);
+    st->geom = alloc(alloc_user, gl.total, "geom");
+    st->image = alloc(alloc_user, il.total, "image");
+    st->geom_bytes = (int64_t)gl.total;
+    st->image_bytes = (int64_t)il.total;
+    if (!st->geom || !st->image) { set_error("allocation callback returned NULL"); return -6; }
+    const GeomPtrs g = GeomPtrs::from(st->geom, gl);
+    float* final_T = (float*)((char*)st->image + il.final_T);
+    uint32_t* n_contrib = (uint32_t*)((char*)st->image + il.n_contrib);
+
+    int64_t N = 0;
+    char* scratch1 = nullptr;
+    BinScratch sc;
+    memset(&sc, 0, sizeof sc);
+    if (P > 0) {
+        const size_t pw = align_up((size_t)P * 4, 256);
+        sc.cub_temp_bytes = align_up(depth_sort_temp_bytes(P), 256);
+        OGS_CUDA(cudaMallocAsync((void**)&scratch1, pw * 5 + sc.cub_temp_bytes, s));
+        sc.dkeys_in = (uint32_t*)(scratch1);
+        sc.dvals_in = (uint32_t*)(scratch1 + pw);
+        sc.dkeys_out = (uint32_t*)(scratch1 + 2 * pw);
+        sc.dvals_out = (uint32_t*)(scratch1 + 3 * pw);
+        sc.offsets = (uint32_t*)(scratch1 + 4 * pw);
+        sc.cub_temp = scratch1 + 5 * pw;
+
+        PreprocessArgs pa;
+        pa.P = P; pa.D = in->sh_degree; pa.M = in->M; pa.W = W; pa.H = H;
+        pa.means3D = in->means3D; pa.scales = in->scales; pa.rotations = in->rotations;
+        pa.cov3D_precomp = in->cov3D_precomp; pa.opacities = in->opacities; pa.shs = in->shs;
+        pa.scale_modifier = in->scale_modifier; pa.tanfovx = in->tanfovx; pa.tanfovy = in->tanfovy;
+        pa.view = in->viewmatrix; pa.proj = in->projmatrix; pa.campos = in->campos;
+        pa.radii = out->radii; pa.g = g; pa.depth_keys = sc.dkeys_in; pa.depth_vals = sc.dvals_in;
+        if ((rc = launch_preprocess_forward(pa, s))) { cudaFreeAsync(scratch1, s); return rc; }
+        OGS_KERNEL_CHECK("preprocess_forward", in->debug, s);
+        if ((rc = depth_sort_and_scan(P, g, sc, s, in->debug))) { cudaFreeAsync(scratch1, s); return rc; }
+        uint32_t* h = pinned_scalar();
+        if (!h) { cudaFreeAsync(scratch1, s); set_error("cudaMallocHost failed"); return 2; }
+        OGS_CUDA(cudaMemcpyAsync(h, sc.offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s));
+        OGS_CUDA(cudaStreamSynchronize(s));
+        N = (int64_t)*h;
+    }
+    st->num_rendered = N;
+    const BinLayout bl = BinLayout::make(N, tiles);
+    st->binning = alloc(alloc_user, bl.total, "binning");
+    st->binning_bytes = (int64_t)bl.total;
+    if (!st->binning) { if (scratch1) cudaFreeAsync(scratch1, s); set_error("allocation callback returned NULL"); return -6; }
+    uint32_t* point_list = (uint32_t*)((char*)st->binning + bl.point_list);
+    uint2* ranges = (uint2*)((char*)st->binning + bl.ranges);
+
+    char* scratch2 = nullptr;
+    if (N > 0) {
+        const size_t k2 = align_up((size_t)N * 2, 256), v4 = align_up((size_t)N * 4, 256);
+        const size_t tb = align_up(tile_sort_temp_bytes(N), 256);
+        OGS_CUDA(cudaMallocAsync((void**)&scratch2, 2 * k2 + v4 + tb, s));
+        sc.cub_temp = scratch2 + 2 * k2 + v4;
+        sc.cub_temp_bytes = tb;
+        rc = emit_sort_ranges(P, W, H, N, g, sc, (uint16_t*)scratch2, (uint32_t*)(scratch2 + 2 * k2),
+                              (uint16_t*)(scratch2 + k2), point_list, ranges, s, in->debug);
+    } else {
+        cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "memset ranges");
+    }
+    if (scratch2) cudaFreeAsync(scratch2, s);
+    if (scratch1) cudaFreeAsync(scratch1, s);
+    if (rc) return rc;
+
+    BlendFwdArgs ba;
+    ba.W = W; ba.H = H; ba.C = C;
+    ba.ranges = ranges; ba.point_list = point_list; ba.rec0 = g.rec0; ba.rec1 = g.rec1;
+    ba.base = has_sh ? g.rgb : in->colors_precomp;
+    ba.extra = in->extra; ba.bg = in->bg;
+    ba.out_color = out->color; ba.out_depth = out->depth; ba.out_alpha = out->alpha;
+    ba.final_T = final_T; ba.n_contrib = n_contrib;
+    if ((rc = launch_blend_forward(ba, s))) return rc;
+    OGS_KERNEL_CHECK("blend_forward", in->debug, s);
+    return 0;
+}
+
+int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st, const ogs_raster_grads_in* gin,
+                        const ogs_raster_grads_out* go, void* stream_) {
+    int rc = validate_inputs(in);
+    if (rc) return rc;
+    if (!st || !gin || !go || !gin->dL_dcolor || !go->scratch) { set_error("state/grads/scratch must be set"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int P = in->P, W = in->W, H = in->H, C = 3 + in->n_extra;
+    if (P == 0) return 0;
+    const int gx = (W + 15) / 16, gy = (H + 15) / 16, tiles = gx * gy;
+    const bool has_sh = in->shs != nullptr;
+    const GeomLayout gl = GeomLayout::make(P, has_sh);
+    const ImgLayout il = ImgLayout::make(W, H);
+    const BinLayout bl = BinLayout::make(st->num_rendered, tiles);
+    const GeomPtrs g = GeomPtrs::from(st->geom, gl);
+
+    const int geom = (go->dL_dmeans3D || go->dL_dmeans2D || go->dL_dopacities || go->dL_dshs || go->dL_dscales ||
+                      go->dL_drotations || go->dL_dcov3D) ? 1 : 0;
+    BlendBwdArgs ba;
+    ba.P = P; ba.W = W; ba.H = H; ba.C = C;
+    ba.ranges = (const uint2*)((char*)st->binning + bl.ranges);
+    ba.point_list = (const uint32_t*)((char*)st->binning + bl.point_list);
+    ba.rec0 = g.rec0; ba.rec1 = g.rec1;
+    ba.base = has_sh ? g.rgb : in->colors_precomp;
+    ba.extra = in->extra; ba.bg = in->bg;
+    ba.final_T = (const float*)((char*)st->image + il.final_T);
+    ba.n_contrib = (const uint32_t*)((char*)st->image + il.n_contrib);
+    ba.dL_dcolor = gin->dL_dcolor; ba.dL_ddepth = gin->dL_ddepth; ba.dL_dalpha = gin->dL_dalpha;
+    ba.geom = geom;
+    ba.acc = (float*)go->scratch;
+    ba.stride = blend_bwd_stride(C, geom);
+    if ((rc = launch_blend_backward(ba, s))) return rc;
+    OGS_KERNEL_CHECK("blend_backward", in->debug, s);
+
+    PreprocessBwdArgs pa;
+    pa.P = P; pa.D = in->sh_degree; pa.M = in->M; pa.C = C; pa.W = W; pa.H = H;
+    pa.means3D = in->means3D; pa.scales = in->scales; pa.rotations = in->rotations;
+    pa.cov3D_precomp = in->cov3D_precomp; pa.shs = in->shs;
+    pa.scale_modifier = in->scale_modifier; pa.tanfovx = in->tanfovx; pa.tanfovy = in->tanfovy;
+    pa.view = in->viewmatrix; pa.proj = in->projmatrix; pa.campos = in->campos;
+    pa.g = g; pa.acc = ba.acc; pa.stride = ba.stride; pa.geom = geom;
+    pa.dL_dmeans3D = go->dL_dmeans3D; pa.dL_dmeans2D = go->dL_dmeans2D; pa.dL_dopacities = go->dL_dopacities;
+    pa.dL_dshs = go->dL_dshs; pa.dL_dcolors_precomp = go->dL_dcolors_precomp; pa.dL_dscales = go->dL_dscales;
+    pa.dL_drotations = go->dL_drotations; pa.dL_dcov3D = go->dL_dcov3D; pa.dL_dextra = go->dL_dextra;
+    if ((rc = launch_preprocess_backward(pa, s))) return rc;
+    OGS_KERNEL_CHECK("preprocess_backward", in->debug, s);
+    return 0;
+}
+
+int ogs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream_) {
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("mark_visible: bad arguments"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = launch_mark_visible(P, means3D, viewmatrix, present, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("mark_visible", 0, s);
+    return 0;
+}
+
+int ogs_raster_export(const ogs_raster_inputs* in, const ogs_raster_state* st, uint64_t* keys, uint32_t* point_list,
+                      uint32_t* ranges, float* xy, float* depth, float* conic_opacity, float* rgb,
+                      uint32_t* tiles_touched, float* final_T, uint32_t* n_contrib, void* stream_) {
+    if (!in || !st) { set_error("export: NULL inputs/state"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int P = in->P, W = in->W, H = in->H;
+    const int gx = (W + 15) / 16, gy = (H + 15) / 16, tiles = gx * gy;
+    const bool has_sh = in->shs != nullptr;
+    const GeomLayout gl = GeomLayout::make(P, has_sh);
+    const ImgLayout il = ImgLayout::make(W, H);
+    const BinLayout bl = BinLayout::make(st->num_rendered, tiles);
+    const GeomPtrs g = GeomPtrs::from(st->geom, gl);
+    const uint32_t* pl = (const uint32_t*)((char*)st->binning + bl.point_list);
+    const uint2* rg = (const uint2*)((char*)st->binning + bl.ranges);
+    const int64_t N = st->num_rendered;
+    if (keys && N > 0) export_keys_kernel<<<tiles, 128, 0, s>>>(tiles, rg, pl, g.rec1, keys);
+    if (point_list && N > 0) OGS_CUDA(cudaMemcpyAsync(point_list, pl, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
+    if (ranges) OGS_CUDA(cudaMemcpyAsync(ranges, rg, (size_t)tiles * 8, cudaMemcpyDeviceToDevice, s));
+    if (P > 0 && (xy || depth || conic_opacity || rgb || tiles_touched))
+        export_geom_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g, has_sh, xy, depth, conic_opacity, rgb, tiles_touched);
+    if (final_T) OGS_CUDA(cudaMemcpyAsync(final_T, (char*)st->image + il.final_T, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, s));
+    if (n_contrib) OGS_CUDA(cudaMemcpyAsync(n_contrib, (char*)st->image + il.n_contrib, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, s));
+    OGS_KERNEL_CHECK("export", 0, s);
+    return 0;
+}
+
+int ogs_kmeans_assign(int64_t N, const float* a, int32_t Da, const float* b, int32_t Db, float scale_b,
+                      const float* centers, int32_t k, const int64_t* select_ids, int64_t selected,
+                      int64_t id_offset, int64_t* ids_out, float* sums, float* counts, void* stream_) {
+    if (N < 0 || Da < 0 || Db < 0 || Da + Db < 1 || k < 1 || !centers || (N > 0 && (!a || !ids_out)) || (Db > 0 && !b)) {
+        set_error("kmeans_assign: bad arguments");
+        return -1;
+    }
+    if (N == 0) return 0;
+    int rc = ensure_pool();
+    if (rc) return rc;
+    return launch_kmeans_assign(N, a, Da, b, Db, scale_b, centers, k, select_ids, selected, id_offset, ids_out, sums,
+                                counts, (cudaStream_t)stream_);
+}
+
+int ogs_kmeans_finalize(int32_t k, int32_t D, const float* sums, const float* counts, float eps_count,
+                        float* centers_out, void* stream_) {
+    if (k < 0 || D < 1 || !sums || !counts || !centers_out) { set_error("kmeans_finalize: bad arguments"); return -1; }
+    int rc = launch_kmeans_finalize(k, D, sums, counts, eps_count, centers_out, (cudaStream_t)stream_);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("kmeans_finalize", 0, (cudaStream_t)stream_);
+    return 0;
+}
+
+int ogs_kmeans_gather_st(int64_t N, const float* feat, int32_t Dout, const float* centers, int32_t Dc,
+                         const int64_t* ids, float* out, void* stream_) {
+    if (N < 0 || Dout < 1 || Dc < Dout || (N > 0 && (!feat || !centers || !ids || !out))) {
+        set_error("kmeans_gather_st: bad arguments");
+        return -1;
+    }
+    int rc = launch_kmeans_gather_st(N, feat, Dout, centers, Dc, ids, out, (cudaStream_t)stream_);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("kmeans_gather_st", 0, (cudaStream_t)stream_);
+    return 0;
+}
+
+int ogs_kmeans_count(int64_t N, const int64_t* ids, int32_t k, int64_t* counts_out, void* stream_) {
+    if (N < 0 || k < 0 || !counts_out || (N > 0 && !ids)) { set_error("kmeans_count: bad arguments"); return -1; }
+    int rc = launch_kmeans_count(N, ids, k, counts_out, (cudaStream_t)stream_);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("kmeans_count", 0, (cudaStream_t)stream_);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// common.cuh -- shared declarations of libogs_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ogs_b200.h"
+
+#define OGS_BLOCK 256              // threads per tile CTA (16x16 pixels)
+#define OGS_NUM_SMS 148
+
+namespace ogs {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);   // records + returns (int)e
+
+#define OGS_CUDA(call)                                                \
+    do {                                                              \
+        cudaError_t _e = (call);                                      \
+        if (_e != cudaSuccess) return ogs::cuda_fail(_e, #call);      \
+    } while (0)
+
+#define OGS_KERNEL_CHECK(name, dbg, stream)                           \
+    do {                                                              \
+        cudaError_t _e = cudaGetLastError();                          \
+        if (_e == cudaSuccess && (dbg)) _e = cudaStreamSynchronize(stream); \
+        if (_e != cudaSuccess) return ogs::cuda_fail(_e, name);       \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- geometry state layout (one caller-owned block, see ogs_raster_state::geom) ----
+struct GeomLayout {
+    size_t rec0, rec1, rgb, clamped, tiles, total;
+    __host__ static GeomLayout make(int P, bool has_sh) {
+        GeomLayout g;
+        size_t o = 0;
+        size_t n = (size_t)(P > 0 ? P : 1);
+        g.rec0 = o; o = align_up(o + n * 16, 256);
+        g.rec1 = o; o = align_up(o + n * 16, 256);
+        g.rgb = o; if (has_sh) o = align_up(o + n * 12, 256);
+        g.clamped = o; if (has_sh) o = align_up(o + n, 256);
+        g.tiles = o; o = align_up(o + n * 4, 256);
+        g.total = o;
+        return g;
+    }
+};
+
+struct GeomPtrs {
+    float4* rec0;      // x, y, conic.a, conic.b
+    float4* rec1;      // conic.c, opacity, depth, radius (int bits)
+    float* rgb;        // [P,3] SH colours (only with shs)
+    uint8_t* clamped;  // bit c set: channel c was clamped at 0
+    uint32_t* tiles;   // tiles_touched
+    __host__ static GeomPtrs from(void* base, const GeomLayout& l) {
+        char* b = (char*)base;
+        GeomPtrs p;
+        p.rec0 = (float4*)(b + l.rec0);
+        p.rec1 = (float4*)(b + l.rec1);
+        p.rgb = (float*)(b + l.rgb);
+        p.clamped = (uint8_t*)(b + l.clamped);
+        p.tiles = (uint32_t*)(b + l.tiles);
+        return p;
+    }
+};
+
+struct BinLayout {
+    size_t point_list, ranges, total;
+    __host__ static BinLayout make(int64_t N, int tiles) {
+        BinLayout b;
+        size_t o = 0;
+        b.point_list = o; o = align_up(o + (size_t)(N > 0 ? N : 1) * 4, 256);
+        b.ranges = o; o = align_up(o + (size_t)tiles * 8, 256);
+        b.total = o;
+        return b;
+    }
+};
+
+struct ImgLayout {
+    size_t final_T, n_contrib, total;
+    __host__ static ImgLayout make(int W, int H) {
+        ImgLayout l;
+        size_t o = 0, n = (size_t)W * H;
+        l.final_T = o; o = align_up(o + n * 4, 256);
+        l.n_contrib = o; o = align_up(o + n * 4, 256);
+        l.total = o;
+        return l;
+    }
+};
+
+// ---- kernels launchers (defined in the per-family .cu files) ----
+struct PreprocessArgs {
+    int P, D, M, W, H;
+    const float *means3D, *scales, *rotations, *cov3D_precomp, *opacities, *shs;
+    float scale_modifier, tanfovx, tanfovy;
+    const float *view, *proj, *campos;
+    int32_t* radii;
+    GeomPtrs g;
+    uint32_t* depth_keys;   // [P] depth bits, 0xFFFFFFFF when culled
+    uint32_t* depth_vals;   // [P] identity
+};
+int launch_preprocess_forward(const PreprocessArgs& a, cudaStream_t s);
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
+
+// binning (binning.cu)
+struct BinScratch {
+    uint32_t *dkeys_in, *dvals_in, *dkeys_out, *dvals_out;  // [P]
+    uint32_t* offsets;                                      // [P] inclusive scan in depth order
+    void* cub_temp; size_t cub_temp_bytes;
+};
+size_t binning_temp_bytes(int P, int64_t N_cap);
+int depth_sort_and_scan(int P, const GeomPtrs& g, BinScratch& sc, cudaStream_t s, int debug);
+int emit_sort_ranges(int P, int W, int H, int64_t N, const GeomPtrs& g, BinScratch& sc,
+                     uint16_t* tkeys_in, uint32_t* tvals_in, uint16_t* tkeys_out,
+                     uint32_t* point_list, uint2* ranges, cudaStream_t s, int debug);
+size_t tile_sort_temp_bytes(int64_t N);
+size_t depth_sort_temp_bytes(int P);
+
+// blend (blend_fwd.cu / blend_bwd.cu)
+struct BlendFwdArgs {
+    int W, H, C;                // C = 3 + n_extra
+    const uint2* ranges; const uint32_t* point_list;
+    const float4 *rec0, *rec1;
+    const float* base;          // [P,3] rgb (SH) or colors_precomp
+    const float* extra;         // [P,C-3] or NULL
+    const float* bg;            // [C]
+    float *out_color, *out_depth, *out_alpha, *final_T; uint32_t* n_contrib;
+};
+int launch_blend_forward(const BlendFwdArgs& a, cudaStream_t s);
+
+struct BlendBwdArgs {
+    int P, W, H, C;
+    const uint2* ranges; const uint32_t* point_list;
+    const float4 *rec0, *rec1;
+    const float* base; const float* extra; const float* bg;
+    const float* final_T; const uint32_t* n_contrib;
+    const float *dL_dcolor, *dL_ddepth, *dL_dalpha;
+    int geom;                   // 1: all gradients, 0: colour/feature gradients only
+    float* acc;                 // [P][stride] accumulators (zeroed by the launcher)
+    int stride;                 // floats per Gaussian in acc
+};
+// acc layout per Gaussian: [0..C) dL_dcolors, then (geom) C+0 dL_ddepth, C+1 dmean2D.x, C+2 dmean2D.y,
+// C+3 dconic.a, C+4 dconic.b(half), C+5 dconic.c, C+6 dopacity
+int blend_bwd_stride(int C, int geom);
+int launch_blend_backward(const BlendBwdArgs& a, cudaStream_t s);
+
+struct PreprocessBwdArgs {
+    int P, D, M, C, W, H;
+    const float *means3D, *scales, *rotations, *cov3D_precomp, *shs;
+    float scale_modifier, tanfovx, tanfovy;
+    const float *view, *proj, *campos;
+    GeomPtrs g;
+    const float* acc; int stride; int geom;
+    float *dL_dmeans3D, *dL_dmeans2D, *dL_dopacities, *dL_dshs, *dL_dcolors_precomp, *dL_dscales,
+        *dL_drotations, *dL_dcov3D, *dL_dextra;
+};
+int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s);
+
+// kmeans (kmeans.cu)
+int launch_kmeans_assign(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b,
+                         const float* centers, int k, const int64_t* select_ids, int64_t selected, int64_t id_offset,
+                         int64_t* ids_out, float* sums, float* counts, cudaStream_t s);
+int launch_kmeans_finalize(int k, int D, const float* sums, const float* counts, float eps, float* out, cudaStream_t s);
+int launch_kmeans_gather_st(int64_t N, const float* feat, int Dout, const float* centers, int Dc, const int64_t* ids,
+                            float* out, cudaStream_t s);
+int launch_kmeans_count(int64_t N, const int64_t* ids, int k, int64_t* counts, cudaStream_t s);
+
+}  // namespace ogs

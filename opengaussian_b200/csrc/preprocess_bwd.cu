@@ -1,0 +1,282 @@
+// preprocess_bwd.cu -- per-Gaussian chain rule from the blend accumulators to the inputs.
+//
+// Replaces upstream computeCov2DCUDA + preprocessCUDA<3> backward of the external rasterizer
+// (SURVEY.md section 2b / 8a8): conic -> cov2D -> (cov3D, mean); mean2D -> mean3D through the
+// projective division; depth -> mean3D; SH backward incl. direction normalisation and the clamp
+// mask; cov3D -> (scale, quaternion).  Same formulas as oracle/raster_oracle.c
+// (ogs_oracle_preprocess_backward), evaluated in fp32; cov3D is recomputed instead of being
+// stored by the forward (saves 48 B/Gaussian of HBM traffic).
+// HBM-bound: reads (C+7)*4 B accumulators + ~236 B parameters, writes the gradient rows.
+#include "common.cuh"
+
+namespace ogs {
+
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+__constant__ float b_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                 0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                 -0.5900435899266435f};
+
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.P) return;
+    const int C = a.C;
+    const float* acc = a.acc + (size_t)i * a.stride;
+    const float4 r1 = a.g.rec1[i];
+    const int radius = __float_as_int(r1.w);
+    const bool vis = radius > 0;
+
+    // colour / feature gradients pass straight through
+    if (a.dL_dcolors_precomp) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) a.dL_dcolors_precomp[3 * (size_t)i + c] = vis ? acc[c] : 0.f;
+    }
+    if (a.dL_dextra) {
+        for (int c = 3; c < C; c++) a.dL_dextra[(size_t)(C - 3) * i + (c - 3)] = vis ? acc[c] : 0.f;
+    }
+    if (!a.geom) return;
+
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float dscale[3] = {0.f, 0.f, 0.f};
+    float drot[4] = {0.f, 0.f, 0.f, 0.f};
+    float dc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dm2x = 0.f, dm2y = 0.f, dop = 0.f;
+    const int M = a.M;
+
+    if (vis) {
+        const float* v = a.view;
+        const float* proj = a.proj;
+        const float m0 = a.means3D[3 * (size_t)i], m1 = a.means3D[3 * (size_t)i + 1], m2 = a.means3D[3 * (size_t)i + 2];
+        const float dL_ddepth = acc[C + 0];
+        dm2x = acc[C + 1];
+        dm2y = acc[C + 2];
+        const float dLA = acc[C + 3], dLBh = acc[C + 4], dLC = acc[C + 5];
+        dop = acc[C + 6];
+
+        // cov3D (recomputed)
+        float c6[6];
+        float R[3][3];
+        float s[3] = {0.f, 0.f, 0.f};
+        float qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c6[k] = a.cov3D_precomp[6 * (size_t)i + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            qr = q.x; qx = q.y; qy = q.z; qz = q.w;
+            const float r = qr, x = qx, y = qy, z = qz;
+            R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
+            R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
+            R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+#pragma unroll
+            for (int k = 0; k < 3; k++) s[k] = a.scale_modifier * a.scales[3 * (size_t)i + k];
+            float L[3][3];
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+                for (int jj = 0; jj < 3; jj++) L[ii][jj] = s[jj] * R[ii][jj];
+            c6[0] = L[0][0] * L[0][0] + L[0][1] * L[0][1] + L[0][2] * L[0][2];
+            c6[1] = L[0][0] * L[1][0] + L[0][1] * L[1][1] + L[0][2] * L[1][2];
+            c6[2] = L[0][0] * L[2][0] + L[0][1] * L[2][1] + L[0][2] * L[2][2];
+            c6[3] = L[1][0] * L[1][0] + L[1][1] * L[1][1] + L[1][2] * L[1][2];
+            c6[4] = L[1][0] * L[2][0] + L[1][1] * L[2][1] + L[1][2] * L[2][2];
+            c6[5] = L[2][0] * L[2][0] + L[2][1] * L[2][1] + L[2][2] * L[2][2];
+        }
+
+        // ---- cov2D backward ----
+        const float fx = (float)a.W / (2.0f * a.tanfovx);
+        const float fy = (float)a.H / (2.0f * a.tanfovy);
+        float t0 = v[0] * m0 + v[4] * m1 + v[8] * m2 + v[12];
+        float t1 = v[1] * m0 + v[5] * m1 + v[9] * m2 + v[13];
+        const float t2 = v[2] * m0 + v[6] * m1 + v[10] * m2 + v[14];
+        const float limx = 1.3f * a.tanfovx, limy = 1.3f * a.tanfovy;
+        const float txtz = t0 / t2, tytz = t1 / t2;
+        t0 = fminf(limx, fmaxf(-limx, txtz)) * t2;
+        t1 = fminf(limy, fmaxf(-limy, tytz)) * t2;
+        const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+        const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+        const float J00 = fx / t2, J02 = -(fx * t0) / (t2 * t2);
+        const float J11 = fy / t2, J12 = -(fy * t1) / (t2 * t2);
+        float T0[3], T1[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            T0[k] = v[4 * k + 0] * J00 + v[4 * k + 2] * J02;
+            T1[k] = v[4 * k + 1] * J11 + v[4 * k + 2] * J12;
+        }
+        const float Vm[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+        float VT0[3], VT1[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            VT0[k] = Vm[k][0] * T0[0] + Vm[k][1] * T0[1] + Vm[k][2] * T0[2];
+            VT1[k] = Vm[k][0] * T1[0] + Vm[k][1] * T1[1] + Vm[k][2] * T1[2];
+        }
+        const float ca = T0[0] * VT0[0] + T0[1] * VT0[1] + T0[2] * VT0[2] + 0.3f;
+        const float cb = T0[0] * VT1[0] + T0[1] * VT1[1] + T0[2] * VT1[2];
+        const float cc = T1[0] * VT1[0] + T1[1] * VT1[1] + T1[2] * VT1[2] + 0.3f;
+        const float denom = ca * cc - cb * cb;
+        const float d2inv = 1.0f / (denom * denom + 0.0000001f);
+        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+        if (d2inv != 0.f) {
+            dL_da = d2inv * (-cc * cc * dLA + 2.f * cb * cc * dLBh + (denom - ca * cc) * dLC);
+            dL_dc = d2inv * (-ca * ca * dLC + 2.f * ca * cb * dLBh + (denom - ca * cc) * dLA);
+            dL_db = d2inv * 2.f * (cb * cc * dLA - (denom + 2.f * cb * cb) * dLBh + ca * cb * dLC);
+            dc6[0] = T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc;
+            dc6[3] = T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc;
+            dc6[5] = T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc;
+            dc6[1] = 2.f * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2.f * T1[0] * T1[1] * dL_dc;
+            dc6[2] = 2.f * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2.f * T1[0] * T1[2] * dL_dc;
+            dc6[4] = 2.f * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2.f * T1[1] * T1[2] * dL_dc;
+        }
+        float dT0[3], dT1[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dT0[k] = 2.f * VT0[k] * dL_da + VT1[k] * dL_db;
+            dT1[k] = 2.f * VT1[k] * dL_dc + VT0[k] * dL_db;
+        }
+        float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dJ00 += v[4 * k + 0] * dT0[k]; dJ02 += v[4 * k + 2] * dT0[k];
+            dJ11 += v[4 * k + 1] * dT1[k]; dJ12 += v[4 * k + 2] * dT1[k];
+        }
+        const float tz = 1.0f / t2, tz2 = tz * tz, tz3 = tz2 * tz;
+        const float dtx = x_grad_mul * -fx * tz2 * dJ02;
+        const float dty = y_grad_mul * -fy * tz2 * dJ12;
+        const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2.f * fx * t0) * tz3 * dJ02 + (2.f * fy * t1) * tz3 * dJ12;
+        dmean[0] = v[0] * dtx + v[1] * dty + v[2] * dtz;
+        dmean[1] = v[4] * dtx + v[5] * dty + v[6] * dtz;
+        dmean[2] = v[8] * dtx + v[9] * dty + v[10] * dtz;
+
+        // ---- mean2D (NDC-scaled) -> mean3D ----
+        const float mh0 = proj[0] * m0 + proj[4] * m1 + proj[8] * m2 + proj[12];
+        const float mh1 = proj[1] * m0 + proj[5] * m1 + proj[9] * m2 + proj[13];
+        const float mh3 = proj[3] * m0 + proj[7] * m1 + proj[11] * m2 + proj[15];
+        const float m_w = 1.0f / (mh3 + 0.0000001f);
+        const float mul1 = mh0 * m_w * m_w, mul2 = mh1 * m_w * m_w;
+        dmean[0] += (proj[0] * m_w - proj[3] * mul1) * dm2x + (proj[1] * m_w - proj[3] * mul2) * dm2y;
+        dmean[1] += (proj[4] * m_w - proj[7] * mul1) * dm2x + (proj[5] * m_w - proj[7] * mul2) * dm2y;
+        dmean[2] += (proj[8] * m_w - proj[11] * mul1) * dm2x + (proj[9] * m_w - proj[11] * mul2) * dm2y;
+        // ---- depth = p_view.z ----
+        dmean[0] += v[2] * dL_ddepth;
+        dmean[1] += v[6] * dL_ddepth;
+        dmean[2] += v[10] * dL_ddepth;
+
+        // ---- SH backward ----
+        if (a.shs) {
+            const float* sh = a.shs + (size_t)i * M * 3;
+            float* dsh = a.dL_dshs ? a.dL_dshs + (size_t)i * M * 3 : nullptr;
+            const float d0 = m0 - a.campos[0], d1 = m1 - a.campos[1], d2 = m2 - a.campos[2];
+            const float len = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+            const float x = d0 / len, y = d1 / len, z = d2 / len;
+            const uint8_t cl = a.g.clamped[i];
+            float dRGB[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) dRGB[ch] = ((cl >> ch) & 1) ? 0.f : acc[ch];
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            const int deg = a.D;
+            auto term = [&](int k, float basis, float bx, float by, float bz) {
+                float sx = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    if (dsh) dsh[k * 3 + ch] = basis * dRGB[ch];
+                    sx += sh[k * 3 + ch] * dRGB[ch];
+                }
+                ddx += bx * sx; ddy += by * sx; ddz += bz * sx;
+            };
+            term(0, SH_C0, 0.f, 0.f, 0.f);
+            if (deg > 0) {
+                term(1, -SH_C1 * y, 0.f, -SH_C1, 0.f);
+                term(2, SH_C1 * z, 0.f, 0.f, SH_C1);
+                term(3, -SH_C1 * x, -SH_C1, 0.f, 0.f);
+                if (deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    term(4, b_SH_C2[0] * xy, b_SH_C2[0] * y, b_SH_C2[0] * x, 0.f);
+                    term(5, b_SH_C2[1] * yz, 0.f, b_SH_C2[1] * z, b_SH_C2[1] * y);
+                    term(6, b_SH_C2[2] * (2.f * zz - xx - yy), b_SH_C2[2] * -2.f * x, b_SH_C2[2] * -2.f * y, b_SH_C2[2] * 4.f * z);
+                    term(7, b_SH_C2[3] * xz, b_SH_C2[3] * z, 0.f, b_SH_C2[3] * x);
+                    term(8, b_SH_C2[4] * (xx - yy), b_SH_C2[4] * 2.f * x, b_SH_C2[4] * -2.f * y, 0.f);
+                    if (deg > 2) {
+                        term(9, b_SH_C3[0] * y * (3.f * xx - yy), b_SH_C3[0] * 6.f * xy, b_SH_C3[0] * (3.f * xx - 3.f * yy), 0.f);
+                        term(10, b_SH_C3[1] * xy * z, b_SH_C3[1] * yz, b_SH_C3[1] * xz, b_SH_C3[1] * xy);
+                        term(11, b_SH_C3[2] * y * (4.f * zz - xx - yy), b_SH_C3[2] * -2.f * xy, b_SH_C3[2] * (4.f * zz - xx - 3.f * yy), b_SH_C3[2] * 8.f * yz);
+                        term(12, b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy), b_SH_C3[3] * -6.f * xz, b_SH_C3[3] * -6.f * yz, b_SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy));
+                        term(13, b_SH_C3[4] * x * (4.f * zz - xx - yy), b_SH_C3[4] * (4.f * zz - 3.f * xx - yy), b_SH_C3[4] * -2.f * xy, b_SH_C3[4] * 8.f * xz);
+                        term(14, b_SH_C3[5] * z * (xx - yy), b_SH_C3[5] * 2.f * xz, b_SH_C3[5] * -2.f * yz, b_SH_C3[5] * (xx - yy));
+                        term(15, b_SH_C3[6] * x * (xx - 3.f * yy), b_SH_C3[6] * (3.f * xx - 3.f * yy), b_SH_C3[6] * -6.f * xy, 0.f);
+                    }
+                }
+            }
+            if (dsh) {
+                const int ncoef = (deg + 1) * (deg + 1);
+                for (int k = ncoef * 3; k < M * 3; k++) dsh[k] = 0.f;
+            }
+            const float sum2 = len * len, invsum32 = 1.0f / (sum2 * len);
+            dmean[0] += ((sum2 - d0 * d0) * ddx - d1 * d0 * ddy - d2 * d0 * ddz) * invsum32;
+            dmean[1] += (-d0 * d1 * ddx + (sum2 - d1 * d1) * ddy - d2 * d1 * ddz) * invsum32;
+            dmean[2] += (-d0 * d2 * ddx - d1 * d2 * ddy + (sum2 - d2 * d2) * ddz) * invsum32;
+        }
+
+        // ---- cov3D -> scale, quaternion ----
+        if (!a.cov3D_precomp) {
+            const float r = qr, x = qx, y = qy, z = qz;
+            const float Gs[3][3] = {{dc6[0], 0.5f * dc6[1], 0.5f * dc6[2]}, {0.5f * dc6[1], dc6[3], 0.5f * dc6[4]}, {0.5f * dc6[2], 0.5f * dc6[4], dc6[5]}};
+            float dLm[3][3], dR[3][3];
+#pragma unroll
+            for (int aa = 0; aa < 3; aa++)
+#pragma unroll
+                for (int bb = 0; bb < 3; bb++) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) t += Gs[aa][k] * R[k][bb] * s[bb];
+                    dLm[aa][bb] = 2.f * t;
+                }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                float ds = 0.f;
+#pragma unroll
+                for (int aa = 0; aa < 3; aa++) { ds += R[aa][j] * dLm[aa][j]; dR[aa][j] = dLm[aa][j] * s[j]; }
+                dscale[j] = ds * a.scale_modifier;
+            }
+            drot[0] = 2.f * (-z * dR[0][1] + y * dR[0][2] + z * dR[1][0] - x * dR[1][2] - y * dR[2][0] + x * dR[2][1]);
+            drot[1] = 2.f * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] - 2.f * x * dR[1][1] - r * dR[1][2] + z * dR[2][0] + r * dR[2][1] - 2.f * x * dR[2][2]);
+            drot[2] = 2.f * (-2.f * y * dR[0][0] + x * dR[0][1] + r * dR[0][2] + x * dR[1][0] + z * dR[1][2] - r * dR[2][0] + z * dR[2][1] - 2.f * y * dR[2][2]);
+            drot[3] = 2.f * (-2.f * z * dR[0][0] - r * dR[0][1] + x * dR[0][2] + r * dR[1][0] - 2.f * z * dR[1][1] + y * dR[1][2] + x * dR[2][0] + y * dR[2][1]);
+        }
+    } else if (a.shs && a.dL_dshs) {
+        float* dsh = a.dL_dshs + (size_t)i * M * 3;
+        for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
+    }
+
+    if (a.dL_dmeans3D) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) a.dL_dmeans3D[3 * (size_t)i + k] = dmean[k];
+    }
+    if (a.dL_dmeans2D) {
+        a.dL_dmeans2D[3 * (size_t)i + 0] = dm2x;
+        a.dL_dmeans2D[3 * (size_t)i + 1] = dm2y;
+        a.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
+    }
+    if (a.dL_dopacities) a.dL_dopacities[i] = dop;
+    if (a.dL_dscales) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) a.dL_dscales[3 * (size_t)i + k] = dscale[k];
+    }
+    if (a.dL_drotations) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) a.dL_drotations[4 * (size_t)i + k] = drot[k];
+    }
+    if (a.dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)i + k] = dc6[k];
+    }
+}
+
+int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return 0;
+    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    return 0;
+}
+
+}  // namespace ogs

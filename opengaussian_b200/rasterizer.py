@@ -1,0 +1,244 @@
+"""Drop-in for the rasterizer package OpenGaussian imports as
+``ashawkey_diff_gaussian_rasterization`` (gaussian_renderer/__init__.py:15,55-70,104-112;
+utils/sam_refinement_utils.py:21,347-403): ``GaussianRasterizationSettings``,
+``GaussianRasterizer`` and the autograd function behind them.
+
+Same names, argument meaning, return tuple ``(color [3,H,W], radii [P] int32, depth [1,H,W],
+alpha [1,H,W])`` and error messages as the upstream Python layer.  The compute is
+libogs_b200.so (hand-written sm_100a CUDA behind the C ABI of include/ogs_b200.h); torch only
+owns device memory and the stream.  Extension over upstream: ``extra_feats=[P,F]`` composites F
+more per-Gaussian channels (OpenGaussian's ``ins_feat``) in the SAME pass and appends a fifth
+return value ``feats [F,H,W]`` -- this is what lets ``render()`` replace its 4 passes by one.
+"""
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_SUPPORTED_C = (3, 4, 6, 9, 12, 16)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _none_if_empty(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor) and t.numel() == 0:
+        return None
+    return t
+
+
+class _Alloc:
+    """Allocation callback handed to the C ABI; keeps the torch buffers alive for backward."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+        def cb(_user, nbytes, tag):
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+            self.bufs[tag.decode()] = t
+            return t.data_ptr()
+
+        self.fn = _lib.ALLOC_FN(cb)
+
+
+def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities, shs, colors_precomp, scales,
+                 rotations, cov3D_precomp, extra, n_extra) -> _lib.RasterInputs:
+    ri = _lib.RasterInputs()
+    ri.P = means3D.shape[0]
+    ri.sh_degree = int(rs.sh_degree)
+    ri.M = 0 if shs is None else int(shs.shape[1])
+    ri.n_extra = n_extra
+    ri.W = int(rs.image_width)
+    ri.H = int(rs.image_height)
+    ri.tanfovx = float(rs.tanfovx)
+    ri.tanfovy = float(rs.tanfovy)
+    ri.scale_modifier = float(rs.scale_modifier)
+    ri.prefiltered = int(bool(rs.prefiltered))
+    ri.debug = int(bool(rs.debug))
+    ri.bg = _lib.ptr(bg_full)
+    ri.viewmatrix = _lib.ptr(rs.viewmatrix)
+    ri.projmatrix = _lib.ptr(rs.projmatrix)
+    ri.campos = _lib.ptr(rs.campos)
+    ri.means3D = _lib.ptr(means3D)
+    ri.opacities = _lib.ptr(opacities)
+    ri.shs = _lib.ptr(shs)
+    ri.colors_precomp = _lib.ptr(colors_precomp)
+    ri.scales = _lib.ptr(scales)
+    ri.rotations = _lib.ptr(rotations)
+    ri.cov3D_precomp = _lib.ptr(cov3D_precomp)
+    ri.extra = _lib.ptr(extra)
+    return ri
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra,
+                raster_settings):
+        L = _lib.lib()
+        rs = raster_settings
+        dev = means3D.device
+        if dev.type != "cuda":
+            raise _lib.OgsError("GaussianRasterizer needs CUDA tensors (there is no CPU fallback)")
+        means3D = _f32c(means3D)
+        sh = _f32c(sh)
+        colors_precomp = _f32c(colors_precomp)
+        opacities = _f32c(opacities)
+        scales = _f32c(scales)
+        rotations = _f32c(rotations)
+        cov3Ds_precomp = _f32c(cov3Ds_precomp)
+        extra = _f32c(extra)
+        P = means3D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        n_extra_user = 0 if extra is None else int(extra.shape[1])
+        n_extra = n_extra_user
+        if n_extra_user:
+            c_tot = next((c for c in _SUPPORTED_C if c >= 3 + n_extra_user), None)
+            if c_tot is None:
+                raise _lib.OgsError(f"extra_feats: at most {_SUPPORTED_C[-1] - 3} channels are supported")
+            if c_tot != 3 + n_extra_user:   # pad with zero channels up to a compiled width
+                extra = torch.cat([extra, extra.new_zeros(P, c_tot - 3 - n_extra_user)], 1).contiguous()
+                n_extra = c_tot - 3
+        bg = _f32c(rs.bg).reshape(-1)
+        bg_full = bg if n_extra == 0 else torch.cat([bg, bg.new_zeros(n_extra)])
+        rs = rs._replace(viewmatrix=_f32c(rs.viewmatrix), projmatrix=_f32c(rs.projmatrix), campos=_f32c(rs.campos))
+
+        color_all = torch.empty(3 + n_extra, H, W, dtype=torch.float32, device=dev)
+        depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+        alpha = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+        radii = torch.empty(P, dtype=torch.int32, device=dev)
+
+        ri = _fill_inputs(rs, bg_full, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
+                          extra, n_extra)
+        ro = _lib.RasterOutputs(_lib.ptr(color_all), _lib.ptr(depth), _lib.ptr(alpha), _lib.ptr(radii))
+        st = _lib.RasterState()
+        alloc = _Alloc(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, None, C.byref(st), C.c_void_p(stream))
+        _lib.check(rc, "ogs_raster_forward")
+
+        ctx.rs = rs
+        ctx.bg_full = bg_full
+        ctx.state = st
+        ctx.bufs = alloc.bufs            # keeps geom/binning/image buffers alive
+        ctx.n_extra = n_extra
+        ctx.n_extra_user = n_extra_user
+        ctx.num_rendered = int(st.num_rendered)
+        ctx.save_for_backward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra)
+        ctx.mark_non_differentiable(radii)
+        if n_extra != n_extra_user:
+            color_all = color_all[:3 + n_extra_user]
+        return color_all, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color_all, _grad_radii, grad_depth, grad_alpha):
+        L = _lib.lib()
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra = ctx.saved_tensors
+        rs = ctx.rs
+        dev = means3D.device
+        P = means3D.shape[0]
+        n_extra = ctx.n_extra
+        H, W = int(rs.image_height), int(rs.image_width)
+        need = ctx.needs_input_grad   # means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3D, extra
+
+        gc = _f32c(grad_color_all)
+        if gc.shape[0] != 3 + n_extra:
+            gc = torch.cat([gc, gc.new_zeros(3 + n_extra - gc.shape[0], H, W)], 0)
+        gd = _f32c(grad_depth) if grad_depth is not None else None
+        ga = _f32c(grad_alpha) if grad_alpha is not None else None
+
+        def out(flag, *shape):
+            return torch.empty(*shape, dtype=torch.float32, device=dev) if flag else None
+
+        g_means3D = out(need[0], P, 3)
+        g_means2D = out(need[1], P, 3)
+        g_sh = out(need[2] and sh is not None, *(sh.shape if sh is not None else (0,)))
+        g_colors = out(need[3] and colors_precomp is not None, P, 3)
+        g_opac = out(need[4], *opacities.shape)
+        g_scales = out(need[5] and scales is not None, P, 3)
+        g_rot = out(need[6] and rotations is not None, P, 4)
+        g_cov = out(need[7] and cov3Ds_precomp is not None, P, 6)
+        g_extra = out(need[8] and extra is not None, P, max(n_extra, 1))
+        scratch = torch.empty(L.ogs_raster_backward_scratch_floats(P, n_extra), dtype=torch.float32, device=dev)
+
+        ri = _fill_inputs(rs, ctx.bg_full, means3D, opacities, sh, colors_precomp, scales, rotations,
+                          cov3Ds_precomp, extra, n_extra)
+        gi = _lib.RasterGradsIn(_lib.ptr(gc), _lib.ptr(gd), _lib.ptr(ga))
+        go = _lib.RasterGradsOut(_lib.ptr(g_means3D), _lib.ptr(g_means2D), _lib.ptr(g_opac), _lib.ptr(g_sh),
+                                 _lib.ptr(g_colors), _lib.ptr(g_scales), _lib.ptr(g_rot), _lib.ptr(g_cov),
+                                 _lib.ptr(g_extra), _lib.ptr(scratch))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = L.ogs_raster_backward(C.byref(ri), C.byref(ctx.state), C.byref(gi), C.byref(go), C.c_void_p(stream))
+        _lib.check(rc, "ogs_raster_backward")
+        if g_extra is not None and n_extra != ctx.n_extra_user:
+            g_extra = g_extra[:, :ctx.n_extra_user].contiguous()
+        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, g_extra, None
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings, extra_feats=None):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, extra_feats, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """Near-plane frustum test (upstream markVisible): bool [P]."""
+        L = _lib.lib()
+        with torch.no_grad():
+            pos = _f32c(positions)
+            view = _f32c(self.raster_settings.viewmatrix)
+            out = torch.empty(pos.shape[0], dtype=torch.uint8, device=pos.device)
+            stream = torch.cuda.current_stream(pos.device).cuda_stream
+            with torch.cuda.device(pos.device):
+                rc = L.ogs_mark_visible(pos.shape[0], _lib.ptr(pos), _lib.ptr(view), _lib.ptr(out), C.c_void_p(stream))
+            _lib.check(rc, "ogs_mark_visible")
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, extra_feats=None):
+        rs = self.raster_settings
+        if means3D.shape[0] > 0:     # upstream passes torch.Tensor([]) for "not given"
+            shs, colors_precomp = _none_if_empty(shs), _none_if_empty(colors_precomp)
+            scales, rotations, cov3D_precomp = _none_if_empty(scales), _none_if_empty(rotations), _none_if_empty(cov3D_precomp)
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        color_all, radii, depth, alpha = rasterize_gaussians(
+            means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs, extra_feats)
+        if extra_feats is None:
+            return color_all, radii, depth, alpha
+        return color_all[:3], radii, depth, alpha, color_all[3:]

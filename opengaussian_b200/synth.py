@@ -125,17 +125,21 @@ def make_gaussians(P: int, kind: str = "blender", seed: int = 0, sh_degree: int 
 
 
 SCENES = {
-    # name: (kind, P, W, H, fovx, camera radius, camera height)
-    "plumbing_10k_256": ("blender", 10_000, 256, 256, 0.69, 4.0, 1.0),
-    "blender_300k_800": ("blender", 300_000, 800, 800, 0.69, 4.0, 1.0),
-    "scannet_1m_1296x968": ("room", 1_000_000, 1296, 968, 2 * math.atan(1296 / (2 * 1170.0)), 2.5, 0.3),
-    "lerf_1m_1080p": ("lerf", 1_000_000, 1920, 1080, 1.0, 5.0, 1.0),
-    "lerf_3m_1080p": ("lerf", 3_000_000, 1920, 1080, 1.0, 5.0, 1.0),
+    # name: (kind, P, W, H, fovx, camera radius, camera height, scale_mult)
+    # scale_mult (sigma as a fraction of the mean nearest-neighbour distance) is tuned so that the
+    # realised duplicates/visible-Gaussian ratio is what trained 3DGS scenes show (7-17 tiles per
+    # Gaussian): N ~ 2.1 M (blender 300k), 5.9 M (scannet 1M), 8.2 M (lerf 1M @1080p = SURVEY 8d's
+    # worked example).
+    "plumbing_10k_256": ("blender", 10_000, 256, 256, 0.69, 4.0, 1.0, 0.6),
+    "blender_300k_800": ("blender", 300_000, 800, 800, 0.69, 4.0, 1.0, 0.3),
+    "scannet_1m_1296x968": ("room", 1_000_000, 1296, 968, 2 * math.atan(1296 / (2 * 1170.0)), 2.5, 0.3, 0.3),
+    "lerf_1m_1080p": ("lerf", 1_000_000, 1920, 1080, 1.0, 5.0, 1.0, 0.2),
+    "lerf_3m_1080p": ("lerf", 3_000_000, 1920, 1080, 1.0, 5.0, 1.0, 0.2),
 }
 
 
 def make_scene(name: str, n_views: int = 8, seed: int = 0, P: int = None):
-    kind, P0, W, H, fovx, rad, height = SCENES[name]
-    gs = make_gaussians(P or P0, kind, seed)
+    kind, P0, W, H, fovx, rad, height, scale_mult = SCENES[name]
+    gs = make_gaussians(P or P0, kind, seed, scale_mult=scale_mult)
     cams = orbit_cameras(n_views, rad, W, H, fovx, height)
     return gs, cams

@@ -1,0 +1,272 @@
+"""GPU parity: libogs_b200.so (through the Python drop-in / C ABI) vs the CPU oracle.
+
+Bars (BASELINE.json north_star): radii, tiles_touched, depth bits, sorted keys, point list and
+tile ranges BIT-EXACT; images/features within 1e-5 absolute (pixels whose skip/stop decision sits
+within the oracle's relative margin of a threshold are excluded and counted); gradients within
+1e-3 relative (to the tensor's max magnitude; atomic/reduction order differs).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import np_inputs, small_scene, to_oracle_cam
+from oracle import raster as orc
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-5
+GRAD_RTOL = 1e-3
+
+
+def _settings(cam, bg, sh_degree=3, scale_modifier=1.0, dev="cuda"):
+    from opengaussian_b200.rasterizer import GaussianRasterizationSettings
+    return GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.as_tensor(bg, dtype=torch.float32, device=dev), scale_modifier=scale_modifier,
+        viewmatrix=cam.world_view_transform.to(dev), projmatrix=cam.full_proj_transform.to(dev),
+        sh_degree=sh_degree, campos=cam.camera_center.to(dev), prefiltered=False, debug=True)
+
+
+def _cuda(gs):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in gs.items()}
+
+
+def _cov3d(gs):
+    """[P,6] covariance from scales/rotations (utils/general_utils.py:64-110 order xx,xy,xz,yy,yz,zz)."""
+    q = gs["rotations"].double()
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+    L = R * gs["scales"].double()[:, None, :]
+    S = L @ L.transpose(1, 2)
+    return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1).float().contiguous()
+
+
+CASES = [
+    # name, P, W, H, kwargs
+    ("sh_rgb", 400, 64, 48, dict(mode="sh")),
+    ("sh_fused_feat", 500, 80, 64, dict(mode="sh", extra=True)),
+    ("precomp", 300, 50, 37, dict(mode="precomp")),                 # W, H not multiples of 16
+    ("precomp_fused", 300, 33, 70, dict(mode="precomp", extra=True)),
+    ("cov3d", 300, 64, 64, dict(mode="sh", cov=True)),
+    ("sh_deg1_mod", 300, 64, 48, dict(mode="sh", sh_degree=1, scale_modifier=0.7)),
+    ("dense_overlap", 3000, 96, 96, dict(mode="sh", extra=True, scale_mult=4.0)),   # long lists: T<1e-4 stops
+    ("inside_scene", 1500, 64, 64, dict(mode="sh", radius=0.5)),   # camera inside the cloud: near culls
+]
+
+
+def _run_case(P, W, H, mode="sh", extra=False, cov=False, sh_degree=3, scale_modifier=1.0, scale_mult=2.5,
+              radius=3.5, seed=0):
+    from opengaussian_b200 import debug
+    gs, cam = small_scene(P=P, W=W, H=H, seed=seed, scale_mult=scale_mult, radius=radius)
+    bg = np.array([0.1, 0.25, 0.4], np.float32)
+    g = np_inputs(gs)
+    ocam = to_oracle_cam(cam, sh_degree=sh_degree, scale_modifier=scale_modifier)
+    colors = torch.rand(P, 3, generator=torch.Generator().manual_seed(5))
+    cov6 = _cov3d(gs) if cov else None
+    okw = dict(shs=g["shs"]) if mode == "sh" else dict(colors_precomp=colors.numpy())
+    if cov:
+        okw.update(cov3D_precomp=cov6.numpy())
+    else:
+        okw.update(scales=g["scales"], rotations=g["rotations"])
+    st = orc.forward(ocam, g["means3D"], g["opacities"], extra=g["ins_feat"] if extra else None, bg=bg, **okw)
+
+    c = _cuda(gs)
+    rs = _settings(cam, bg, sh_degree, scale_modifier)
+    kw = dict(shs=c["shs"]) if mode == "sh" else dict(colors_precomp=colors.cuda())
+    if cov:
+        kw.update(cov3D_precomp=cov6.cuda())
+    else:
+        kw.update(scales=c["scales"], rotations=c["rotations"])
+    out = debug.forward_with_state(rs, c["means3D"], c["opacities"], extra=c["ins_feat"] if extra else None, **kw)
+    torch.cuda.synchronize()
+    return gs, cam, st, out, rs, kw, colors, cov6, bg
+
+
+@pytest.mark.parametrize("name,P,W,H,kw", CASES, ids=[c[0] for c in CASES])
+def test_forward_parity(name, P, W, H, kw):
+    gs, cam, st, out, *_ = _run_case(P, W, H, **kw)
+    # ---- integer artefacts: bit-exact ----
+    assert np.array_equal(out["radii"].cpu().numpy(), st.radii)
+    assert np.array_equal(out["tiles_touched"].cpu().numpy().view(np.uint32), st.tiles_touched)
+    vis = st.radii > 0
+    assert np.array_equal(out["xy"].cpu().numpy().view(np.uint32)[vis], st.xy.view(np.uint32)[vis])
+    assert np.array_equal(out["geom_depth"].cpu().numpy().view(np.uint32)[vis], st.depth.view(np.uint32)[vis])
+    assert np.array_equal(out["conic_opacity"].cpu().numpy().view(np.uint32)[vis], st.conic_opacity.view(np.uint32)[vis])
+    if kw.get("mode") == "sh":
+        assert np.array_equal(out["rgb"].cpu().numpy().view(np.uint32)[vis], st.rgb.view(np.uint32)[vis])
+    assert out["N"] == st.N
+    assert np.array_equal(out["keys"].cpu().numpy().view(np.uint64), st.keys)
+    assert np.array_equal(out["point_list"].cpu().numpy().view(np.uint32), st.point_list)
+    assert np.array_equal(out["ranges"].cpu().numpy().view(np.uint32), st.ranges)
+    # ---- images ----
+    ok = st.flags == 0
+    assert ok.mean() > 0.9
+    color = out["color"].cpu().numpy()
+    assert np.abs(color - st.color)[:, ok].max() <= IMG_TOL
+    assert np.abs(out["depth"].cpu().numpy() - st.out_depth)[ok].max() <= IMG_TOL * max(1.0, st.out_depth.max())
+    assert np.abs(out["alpha"].cpu().numpy() - st.out_alpha)[ok].max() <= IMG_TOL
+    assert np.abs(out["final_T"].cpu().numpy() - st.final_T)[ok].max() <= IMG_TOL
+    assert np.array_equal(out["n_contrib"].cpu().numpy().view(np.uint32)[ok], st.n_contrib[ok])
+    # flagged pixels may differ by one borderline contribution but must stay sane
+    assert np.abs(color - st.color).max() < 0.05
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-20)
+
+
+GRAD_CASES = [c for c in CASES if c[0] in ("sh_rgb", "sh_fused_feat", "precomp_fused", "cov3d", "sh_deg1_mod",
+                                             "dense_overlap", "inside_scene")]
+
+
+@pytest.mark.parametrize("name,P,W,H,kw", GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
+def test_backward_parity(name, P, W, H, kw):
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    gs, cam, st, out, rs, rkw, colors, cov6, bg = _run_case(P, W, H, **kw)
+    extra = kw.get("extra", False)
+    Cn = 9 if extra else 3
+    rng = np.random.default_rng(3)
+    gc = rng.standard_normal((Cn, H, W)).astype(np.float32)
+    gd = rng.standard_normal((H, W)).astype(np.float32)
+    ga = rng.standard_normal((H, W)).astype(np.float32)
+    # Pixels whose forward decision was borderline could take a different branch: zero their loss.
+    m = (st.flags == 0).astype(np.float32)
+    gc *= m
+    gd *= m
+    ga *= m
+    ref = orc.backward(st, gc, gd, ga)
+
+    c = _cuda(gs)
+    leaves = {}
+
+    def leaf(t):
+        t = t.detach().clone().cuda().requires_grad_(True)
+        return t
+
+    leaves["means3D"] = leaf(gs["means3D"])
+    leaves["means2D"] = torch.zeros(P, 3, device="cuda", requires_grad=True)
+    leaves["opacities"] = leaf(gs["opacities"])
+    args = dict(means3D=leaves["means3D"], means2D=leaves["means2D"], opacities=leaves["opacities"])
+    if kw.get("mode") == "sh":
+        leaves["shs"] = leaf(gs["shs"])
+        args["shs"] = leaves["shs"]
+    else:
+        leaves["colors_precomp"] = leaf(colors)
+        args["colors_precomp"] = leaves["colors_precomp"]
+    if kw.get("cov"):
+        leaves["cov3D_precomp"] = leaf(cov6)
+        args["cov3D_precomp"] = leaves["cov3D_precomp"]
+    else:
+        leaves["scales"] = leaf(gs["scales"])
+        leaves["rotations"] = leaf(gs["rotations"])
+        args["scales"] = leaves["scales"]
+        args["rotations"] = leaves["rotations"]
+    if extra:
+        leaves["extra"] = leaf(gs["ins_feat"])
+        args["extra_feats"] = leaves["extra"]
+    res = GaussianRasterizer(rs)(**args)
+    color, radii, depth, alpha = res[:4]
+    loss = (color * torch.as_tensor(gc[:3]).cuda()).sum() + (depth[0] * torch.as_tensor(gd).cuda()).sum() \
+        + (alpha[0] * torch.as_tensor(ga).cuda()).sum()
+    if extra:
+        loss = loss + (res[4] * torch.as_tensor(gc[3:]).cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    for k, t in leaves.items():
+        want = ref[k]
+        got = t.grad.cpu().numpy().reshape(np.asarray(want).shape)
+        assert np.isfinite(got).all(), k
+        assert _rel(got, want) <= GRAD_RTOL, (k, _rel(got, want))
+
+
+def test_feature_only_backward_matches_full():
+    """Colour-only fast path (geometry detached, OpenGaussian stages 1-2) == full path's dL/dextra."""
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    P, W, H = 800, 96, 80
+    gs, cam, st, out, rs, rkw, colors, cov6, bg = _run_case(P, W, H, mode="sh", extra=True)
+    c = _cuda(gs)
+    gcol = torch.randn(3, H, W, device="cuda")
+    gfeat = torch.randn(6, H, W, device="cuda")
+    grads = []
+    for full in (False, True):
+        extra = c["ins_feat"].clone().requires_grad_(True)
+        m3 = c["means3D"].clone().requires_grad_(full)
+        r = GaussianRasterizer(rs)(means3D=m3, means2D=torch.zeros_like(m3), opacities=c["opacities"], shs=c["shs"],
+                                   scales=c["scales"], rotations=c["rotations"], extra_feats=extra)
+        ((r[0] * gcol).sum() + (r[4] * gfeat).sum()).backward()
+        grads.append(extra.grad.clone())
+    ref = orc.backward(st, torch.cat([gcol, gfeat]).cpu().numpy())
+    assert _rel(grads[0].cpu().numpy(), ref["extra"]) <= GRAD_RTOL
+    assert _rel(grads[0].cpu().numpy(), grads[1].cpu().numpy()) <= 1e-4
+
+
+def test_empty_and_culled():
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    gs, cam = small_scene(P=64, W=40, H=24)
+    bg = np.array([0.3, 0.6, 0.9], np.float32)
+    rs = _settings(cam, bg)
+    c = _cuda(gs)
+    # everything behind the camera
+    far = c["means3D"] * 0 + cam.camera_center.cuda() - 5.0 * (0 - cam.camera_center.cuda())
+    color, radii, depth, alpha = GaussianRasterizer(rs)(means3D=far, means2D=torch.zeros_like(far),
+                                                        opacities=c["opacities"], shs=c["shs"], scales=c["scales"],
+                                                        rotations=c["rotations"])
+    assert int(radii.abs().sum()) == 0
+    assert torch.allclose(color, torch.as_tensor(bg).cuda()[:, None, None].expand_as(color))
+    assert float(alpha.abs().max()) == 0.0 and float(depth.abs().max()) == 0.0
+    # P == 0
+    e = torch.zeros(0, 3, device="cuda")
+    color, radii, depth, alpha = GaussianRasterizer(rs)(
+        means3D=e, means2D=e, opacities=torch.zeros(0, 1, device="cuda"), colors_precomp=e,
+        scales=e, rotations=torch.zeros(0, 4, device="cuda"))
+    assert radii.numel() == 0 and torch.allclose(color[:, 0, 0].cpu(), torch.as_tensor(bg))
+
+
+def test_argument_errors():
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    gs, cam = small_scene(P=16, W=32, H=32)
+    rs = _settings(cam, [0, 0, 0])
+    c = _cuda(gs)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        GaussianRasterizer(rs)(means3D=c["means3D"], means2D=c["means3D"], opacities=c["opacities"],
+                               scales=c["scales"], rotations=c["rotations"])
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        GaussianRasterizer(rs)(means3D=c["means3D"], means2D=c["means3D"], opacities=c["opacities"], shs=c["shs"])
+
+
+def test_mark_visible():
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    gs, cam = small_scene(P=5000, W=32, H=32, radius=0.8)
+    rs = _settings(cam, [0, 0, 0])
+    got = GaussianRasterizer(rs).markVisible(gs["means3D"].cuda()).cpu().numpy()
+    want = orc.mark_visible(gs["means3D"].numpy(), cam.world_view_transform.numpy())
+    assert np.array_equal(got, want) and 0 < want.sum() < want.size
+
+
+def test_medium_scene_properties():
+    """Larger scene (oracle still seconds): exact binning + image parity + structural invariants."""
+    from opengaussian_b200 import debug, synth
+    gs, cams = synth.make_scene("plumbing_10k_256", n_views=3)
+    cam = cams[1]
+    bg = np.zeros(3, np.float32)
+    g = np_inputs(gs)
+    st = orc.forward(to_oracle_cam(cam), g["means3D"], g["opacities"], g["scales"], g["rotations"], shs=g["shs"],
+                     extra=g["ins_feat"], bg=bg)
+    c = _cuda(gs)
+    out = debug.forward_with_state(_settings(cam, bg), c["means3D"], c["opacities"], shs=c["shs"], scales=c["scales"],
+                                   rotations=c["rotations"], extra=c["ins_feat"])
+    assert out["N"] == st.N
+    assert np.array_equal(out["keys"].cpu().numpy().view(np.uint64), st.keys)
+    assert np.array_equal(out["point_list"].cpu().numpy().view(np.uint32), st.point_list)
+    assert np.array_equal(out["ranges"].cpu().numpy().view(np.uint32), st.ranges)
+    keys = out["keys"].cpu().numpy().view(np.uint64)
+    assert np.all(keys[1:] >= keys[:-1])                     # sortedness
+    ok = st.flags == 0
+    assert np.abs(out["color"].cpu().numpy() - st.color)[:, ok].max() <= IMG_TOL
+    a = out["alpha"].cpu().numpy()
+    assert a.min() >= 0.0 and a.max() <= 1.0
+    assert np.allclose(a, 1.0 - out["final_T"].cpu().numpy(), atol=1e-7)
