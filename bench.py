@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the OpenGaussian hot path on B200.
+
+Metric (BASELINE.json): fwd+bwd frames/sec @ 1 M Gaussians, 1920x1080, SH degree 3, gradients
+w.r.t. all rasterizer inputs ("frame" = one GaussianRasterizer forward +
+backward).  One process per GPU; every rank renders its own camera views against a full replica of
+the Gaussians (views split across ranks, weak scaling) and the parameter gradients are summed
+with NCCL all-reduce when N > 1.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes
+through the public Python API with the per-step inputs (camera + the loss-gradient images that
+stand in for the ground-truth image) copied from pinned host memory and the loss scalar read
+back, inside the timed region.  `--impl reference` times the CPU restatement of the reference
+path (oracle/, OpenMP over all host threads) on the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd frames/sec @1M Gaussians 1080p"
+UNIT = "frames/s"
+WORKLOAD = "lerf_1m_1080p"
+N_VIEWS = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kmeans", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.sm = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.ok = False
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap"}
+            self.ok = True
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        except Exception:
+            self.ok = False
+
+    def result(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# --------------------------------------------------------------------------------------------
+def algorithmic_bytes(P, P_vis, N, H, W, C, deg, tile_bits):
+    """SURVEY.md section 8d per-frame algorithmic HBM bytes, split per kernel family."""
+    b_in = 12 + 12 + 16 + 4 + 4 * 3 * (deg + 1) ** 2
+    HW = H * W
+    d = {}
+    d["preprocess_fwd"] = P * b_in + P_vis * 48
+    d["depth_sort_scan"] = P * 16 * 4 + P * 8
+    d["emit"] = N * 6 + P * 40
+    d["tile_sort"] = N * 12 * ((tile_bits + 7) // 8)
+    d["tile_ranges"] = N * 2
+    d["blend_fwd"] = N * (4 + 28 + 4 * C + 4) + HW * 4 * (C + 2) + HW * 8
+    d["blend_bwd"] = HW * 4 * (C + 2) + HW * 8 + N * (4 + 28 + 4 * C + 4) + P_vis * 4 * (C + 7) * 2
+    d["preprocess_bwd"] = P_vis * (40 + b_in) + P * b_in
+    return d
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from opengaussian_b200 import _lib, synth
+    from opengaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()   # fails loudly if the CUDA library is missing
+
+    kind, P0, W, H, fovx, rad, height, scale_mult = synth.SCENES[a.workload]
+    gs = synth.make_gaussians(P0, kind, 0, scale_mult=scale_mult)
+    cams = [c.to(dev) for c in synth.orbit_cameras(N_VIEWS * world, rad, W, H, fovx, height)][rank::world]
+    P = P0
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+    params = {k: gs[k].to(dev).requires_grad_(True) for k in names}
+    means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
+    bg = torch.zeros(3, device=dev)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    G_host = [torch.randn(5, H, W, generator=gen).pin_memory() for _ in range(2)]
+    G = G_host[0].to(dev)
+    settings = [GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, c.world_view_transform,
+                                              c.full_proj_transform, 3, c.camera_center, False, False) for c in cams]
+    grads = [params[k] for k in names] + [means2D]
+
+    def zero_grads():
+        for t in grads:
+            t.grad = None
+
+    def frame(i, Gd):
+        rast = GaussianRasterizer(settings[i % len(settings)])
+        color, radii, depth, alpha = rast(means2D=means2D, **params)
+        torch.autograd.backward((color, depth, alpha), (Gd[0:3], Gd[3:4], Gd[4:5]))
+        if world > 1:
+            for t in grads[:-1]:
+                dist.all_reduce(t.grad)
+        return color, radii
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload statistics (untimed) ----
+    with torch.no_grad():
+        from opengaussian_b200 import debug
+        st = debug.forward_with_state(settings[0], params["means3D"].detach(), params["opacities"].detach(),
+                                      shs=params["shs"].detach(), scales=params["scales"].detach(),
+                                      rotations=params["rotations"].detach(), export=True)
+        N_r = int(st["N"])
+        P_vis = int((st["radii"] > 0).sum())
+        mean_contrib = float(st["n_contrib"].float().mean())
+        del st
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    tile_bits = max(1, (tiles - 1).bit_length())
+
+    # ---- device-resident timing ----
+    for i in range(a.warmup):
+        zero_grads()
+        frame(i, G)
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        zero_grads()
+        frame(a.warmup + i, G)
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    barrier()
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms)
+    sampler.join(timeout=2)
+    value = world * a.steps / (ms / 1000.0)
+
+    # ---- end-to-end timing: host inputs (pinned) -> H2D -> fwd+bwd -> loss scalar D2H ----
+    cam_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
+                           c.camera_center.reshape(-1)]).cpu().pin_memory() for c in cams]
+    copy_stream = torch.cuda.Stream(dev)
+    G_dev = [torch.empty(5, H, W, device=dev) for _ in range(2)]
+    cam_dev = [torch.empty(35, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(i):   # async H2D of step i's inputs on the copy stream (double buffered)
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            G_dev[s].copy_(G_host[s], non_blocking=True)
+            cam_dev[s].copy_(cam_host[i % len(cam_host)], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_step(i, nxt):
+        s = i % 2
+        torch.cuda.current_stream().wait_event(ready[s])
+        if nxt:
+            stage(i + 1)
+        c = cams[i % len(cams)]
+        cd = cam_dev[s]
+        rs = GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, cd[0:16].view(4, 4), cd[16:32].view(4, 4),
+                                           3, cd[32:35], False, False)
+        zero_grads()
+        color, radii, depth, alpha = GaussianRasterizer(rs)(means2D=means2D, **params)
+        Gd = G_dev[s]
+        loss = (color * Gd[0:3]).sum() + (depth * Gd[3:4]).sum() + (alpha * Gd[4:5]).sum()
+        loss.backward()
+        if world > 1:
+            for t in grads[:-1]:
+                dist.all_reduce(t.grad)
+        consumed[s].record()
+        return float(loss.item())    # D2H read of the step's result
+
+    for s in range(2):
+        consumed[s].record()
+    stage(0)
+    for i in range(3):
+        e2e_step(i, True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(3, 3 + a.steps):
+        e2e_step(i, i + 1 < 3 + a.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    wall_e2e = (time.perf_counter() - t0) * 1000.0
+    barrier()
+    t_ms = torch.tensor([max(ms_e2e, wall_e2e)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * a.steps / (float(t_ms) / 1000.0)
+    h2d = 5 * H * W * 4 + 35 * 4
+    d2h = 4
+
+    # ---- k-means secondary metric (rank-local shard of 5 M points; allreduce of [k, D+1]) ----
+    km = None
+    if not a.no_kmeans:
+        from opengaussian_b200.kmeans_quantize import kmeans_assign
+        Nk = 5_000_000 // world
+        g2 = torch.Generator(device=dev).manual_seed(7 + rank)
+        fa = torch.rand(Nk, 6, device=dev, generator=g2)
+        fb = (torch.rand(Nk, 3, device=dev, generator=g2) - 0.5) * 8
+        cen = torch.cat([fa[:64], fb[:64]], 1).contiguous()
+        if world > 1:
+            dist.broadcast(cen, 0)
+        ids = torch.empty(Nk, dtype=torch.int64, device=dev)
+
+        s9 = torch.zeros(64, 9, device=dev)
+        c1 = torch.zeros(64, device=dev)
+
+        def km_pass():
+            s9.zero_()
+            c1.zero_()
+            kmeans_assign(fa, fb, 1.0, cen, ids_out=ids, sums=s9, counts=c1)
+            if world > 1:
+                dist.all_reduce(s9)
+                dist.all_reduce(c1)
+
+        for _ in range(3):
+            km_pass()
+        barrier()
+        e0.record()
+        for _ in range(20):
+            km_pass()
+        e1.record()
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / 20
+        t_ms = torch.tensor([kms], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        kms = float(t_ms)
+        km = {"metric": "kmeans assign+centroid-sum pass, k=64 D=9", "points": Nk * world, "ms_per_pass": kms,
+              "gpts_per_s": Nk * world / kms / 1e6, "hbm_frac": (Nk * 44 / (kms / 1e3) / 1e9) / load_peaks()[0]}
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = load_peaks()
+    alg = algorithmic_bytes(P, P_vis, N_r, H, W, 3, 3, tile_bits)
+    fam_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
+    dom = max((k for k in fam_ms if k in alg), key=lambda k: prof[k][0])
+    ach = alg[dom] / (fam_ms[dom] / 1e3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                "ms_per_launch": fam_ms[dom],
+                "note": "blend kernels are FP32-ALU/MUFU bound (SURVEY 8d); HBM fraction reported as the contract asks"}
+    breakdown = {k: {"ms_per_launch": fam_ms[k], "launches": prof[k][1],
+                     "hbm_frac": (alg[k] / (fam_ms[k] / 1e3) / 1e9 / peak) if k in alg else None} for k in fam_ms}
+    own = ("preprocess_fwd", "emit", "tile_ranges", "blend_fwd", "blend_bwd", "preprocess_bwd")
+    gpu_launches = sum(prof[k][1] for k in own if k in prof)
+    frame_bytes = sum(alg.values())
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": a.workload, "gaussians": P, "image": [W, H], "sh_degree": 3, "views_per_rank": len(cams),
+                   "gradients": "all inputs (means3D, means2D, opacities, shs, scales, rotations)",
+                   "parallelism": f"view-parallel x{world}" + (" + NCCL grad allreduce" if world > 1 else ""),
+                   "l2": "inputs larger than L2 (236 MB parameters + 8 rotating views per rank)",
+                   "num_rendered": N_r, "visible": P_vis, "mean_tile_list": N_r / tiles, "mean_n_contrib": mean_contrib},
+        "clocks": sampler.result(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": gpu_launches,
+        "roofline": roofline,
+        "frame_hbm": {"algorithmic_bytes": frame_bytes, "frac_of_peak": frame_bytes / (ms / a.steps / 1e3) / 1e9 / peak},
+        "breakdown": breakdown,
+    }
+    if km:
+        out["kmeans"] = km
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_frame_baseline(a.workload, steps=1, warmup=0)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_frame_baseline(workload, steps, warmup):
+    """Times the CPU oracle (the restated reference path, OpenMP) on full frames of the workload."""
+    from opengaussian_b200 import synth
+    from oracle import lib
+    from oracle import raster as orc
+    import numpy as np
+    kind, P0, W, H, fovx, rad, height, scale_mult = synth.SCENES[workload]
+    gs = synth.make_gaussians(P0, kind, 0, scale_mult=scale_mult)
+    cams = synth.orbit_cameras(N_VIEWS, rad, W, H, fovx, height)
+    g = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in gs.items()}
+    cores = int(lib().ogs_oracle_set_threads(0))
+    rng = np.random.default_rng(0)
+    gc = rng.standard_normal((3, H, W)).astype(np.float32)
+    gd = rng.standard_normal((H, W)).astype(np.float32)
+    ga = rng.standard_normal((H, W)).astype(np.float32)
+
+    def frame(i):
+        c = cams[i % len(cams)]
+        oc = orc.Camera(W=W, H=H, tanfovx=c.tanfovx, tanfovy=c.tanfovy, view=c.world_view_transform.numpy().reshape(-1),
+                        proj=c.full_proj_transform.numpy().reshape(-1), campos=c.camera_center.numpy())
+        st = orc.forward(oc, g["means3D"], g["opacities"], g["scales"], g["rotations"], shs=g["shs"])
+        orc.backward(st, gc, gd, ga)
+
+    for i in range(warmup):
+        frame(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        frame(warmup + i)
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} full fwd+bwd frame(s) of {workload} through oracle/raster_oracle.c (C, OpenMP)",
+            "seconds": dt}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, a.steps)
+    warm = max(0, a.warmup)
+    # bounded: a full CPU frame costs seconds; keep the whole run within a few minutes
+    t0 = time.perf_counter()
+    probe = cpu_frame_baseline(a.workload, steps=1, warmup=0)
+    per = probe["seconds"]
+    budget = 150.0
+    if per * (steps + warm) > budget:
+        warm = min(warm, 1)
+        steps_run = max(1, int((budget - per * warm) / per))
+    else:
+        steps_run = steps
+    base = cpu_frame_baseline(a.workload, steps=steps_run, warmup=warm)
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
+           "steps": steps_run, "warmup": warm, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": a.workload, "gaussians": 1_000_000 if a.workload == WORKLOAD else None,
+                      "note": "CPU restatement of the reference rasterizer path (the upstream CUDA source is absent "
+                              "from the reference tree); each step is one full fwd+bwd frame; steps capped to keep "
+                              "the run within minutes" if steps_run != steps else
+                              "CPU restatement of the reference rasterizer path; each step is one full fwd+bwd frame"},
+           "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

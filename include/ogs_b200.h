@@ -104,11 +104,19 @@ typedef struct ogs_raster_grads_out {
     float* dL_drotations; /* [P,4] */
     float* dL_dcov3D;     /* [P,6] */
     float* dL_dextra;     /* [P,n_extra] */
-    void* scratch;        /* [P * (3 + n_extra + 8)] floats of caller-provided workspace */
+    void* scratch;        /* ogs_raster_backward_scratch_floats(P, n_extra) floats of caller workspace */
 } ogs_raster_grads_out;
 
 int ogs_abi_version(void);
 const char* ogs_last_error(void);
+
+/* Optional device timing of the kernel families (CUDA events recorded on the launching stream).
+ * Families: 0 preprocess_fwd, 1 depth_sort_scan, 2 emit, 3 tile_sort, 4 tile_ranges, 5 blend_fwd,
+ * 6 blend_bwd, 7 preprocess_bwd, 8 kmeans_assign.  ogs_profile_read synchronises the recorded
+ * events, writes the summed milliseconds and launch counts of the first n families and resets. */
+#define OGS_PROFILE_FAMILIES 9
+void ogs_profile_enable(int on);
+int ogs_profile_read(float* ms_out_host, int32_t* launches_out_host, int32_t n);
 
 int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* out,
                        ogs_alloc_fn alloc, void* alloc_user, ogs_raster_state* state, void* stream);

@@ -46,6 +46,8 @@ class RasterGradsOut(C.Structure):
 EXPORTS = {
     "ogs_abi_version": (C.c_int, []),
     "ogs_last_error": (C.c_char_p, []),
+    "ogs_profile_enable": (None, [C.c_int]),
+    "ogs_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "ogs_raster_forward": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterOutputs), ALLOC_FN, C.c_void_p,
                                      C.POINTER(RasterState), C.c_void_p]),
     "ogs_raster_backward": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterState), C.POINTER(RasterGradsIn),
@@ -91,6 +93,23 @@ def check(rc: int, what: str):
         if rc == -2:
             raise Exception(msg)          # same exception type/message as the reference Python layer
         raise OgsError(f"{what} failed (rc={rc}): {msg}")
+
+
+PROFILE_FAMILIES = ("preprocess_fwd", "depth_sort_scan", "emit", "tile_sort", "tile_ranges", "blend_fwd",
+                    "blend_bwd", "preprocess_bwd", "kmeans_assign")
+
+
+def profile_enable(on: bool):
+    lib().ogs_profile_enable(int(on))
+
+
+def profile_read():
+    """{family: (total_ms, launches)} since the last read (synchronises the recorded events)."""
+    n = len(PROFILE_FAMILIES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int32 * n)()
+    check(lib().ogs_profile_read(ms, cnt, n), "ogs_profile_read")
+    return {PROFILE_FAMILIES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
 def ptr(t):

@@ -100,16 +100,21 @@ int emit_sort_ranges(int P, int W, int H, int64_t N, const GeomPtrs& g, BinScrat
     const int tiles = gx * gy;
     OGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
     if (N == 0) return 0;
+    prof_begin(PF_EMIT, s);
     emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, gx, gy, sc.dvals_out, sc.offsets, g.rec0, g.rec1, tkeys_in,
                                                 tvals_in);
+    prof_end(PF_EMIT, s);
     OGS_KERNEL_CHECK("emit_kernel", debug, s);
     int bits = 0;
     while ((1 << bits) < tiles) bits++;
     if (bits == 0) bits = 1;
     size_t tb = sc.cub_temp_bytes;
+    prof_begin(PF_TILE_SORT, s);
     OGS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_temp, tb, tkeys_in, tkeys_out, tvals_in, point_list, (int)N, 0,
                                              bits, s));
+    prof_end(PF_TILE_SORT, s);
     OGS_KERNEL_CHECK("tile_sort", debug, s);
+    ProfScope ps(PF_RANGES, s);
     ranges_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(N, tkeys_out, ranges);
     OGS_KERNEL_CHECK("ranges_kernel", debug, s);
     return 0;

@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace ogs {
@@ -21,6 +23,33 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return (int)e > 0 ? (int)e : 999;
+}
+
+// ---- profiling: event pairs per family, drained by ogs_profile_read ----
+struct ProfPair { cudaEvent_t a, b; int fam; };
+static bool g_prof_on = false;
+static std::vector<ProfPair> g_prof_pairs;
+static std::vector<cudaEvent_t> g_prof_free;
+static cudaEvent_t g_prof_open[PF_COUNT];
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_free.empty()) { cudaEvent_t e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int family, cudaStream_t s) {
+    if (!g_prof_on) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, s);
+    g_prof_open[family] = e;
+}
+void prof_end(int family, cudaStream_t s) {
+    if (!g_prof_on || !g_prof_open[family]) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, s);
+    g_prof_pairs.push_back({g_prof_open[family], e, family});
+    g_prof_open[family] = nullptr;
 }
 
 static int ensure_pool(void) {
@@ -102,6 +131,29 @@ using namespace ogs;
 extern "C" {
 
 int ogs_abi_version(void) { return OGS_ABI_VERSION; }
+
+void ogs_profile_enable(int on) { g_prof_on = on != 0; }
+
+int ogs_profile_read(float* ms_out, int32_t* launches_out, int32_t n) {
+    float ms[PF_COUNT] = {0};
+    int cnt[PF_COUNT] = {0};
+    for (auto& p : g_prof_pairs) {
+        cudaError_t e = cudaEventSynchronize(p.b);
+        float t = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, p.a, p.b);
+        if (e != cudaSuccess) return cuda_fail(e, "profile_read");
+        ms[p.fam] += t;
+        cnt[p.fam]++;
+        g_prof_free.push_back(p.a);
+        g_prof_free.push_back(p.b);
+    }
+    g_prof_pairs.clear();
+    for (int i = 0; i < n && i < PF_COUNT; i++) {
+        if (ms_out) ms_out[i] = ms[i];
+        if (launches_out) launches_out[i] = cnt[i];
+    }
+    return 0;
+}
 const char* ogs_last_error(void) { return g_err; }
 
 size_t ogs_raster_backward_scratch_floats(int32_t P, int32_t n_extra) {
@@ -156,9 +208,15 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         pa.scale_modifier = in->scale_modifier; pa.tanfovx = in->tanfovx; pa.tanfovy = in->tanfovy;
         pa.view = in->viewmatrix; pa.proj = in->projmatrix; pa.campos = in->campos;
         pa.radii = out->radii; pa.g = g; pa.depth_keys = sc.dkeys_in; pa.depth_vals = sc.dvals_in;
-        if ((rc = launch_preprocess_forward(pa, s))) { cudaFreeAsync(scratch1, s); return rc; }
+        prof_begin(PF_PREPROCESS_FWD, s);
+        rc = launch_preprocess_forward(pa, s);
+        prof_end(PF_PREPROCESS_FWD, s);
+        if (rc) { cudaFreeAsync(scratch1, s); return rc; }
         OGS_KERNEL_CHECK("preprocess_forward", in->debug, s);
-        if ((rc = depth_sort_and_scan(P, g, sc, s, in->debug))) { cudaFreeAsync(scratch1, s); return rc; }
+        prof_begin(PF_DEPTH_SORT_SCAN, s);
+        rc = depth_sort_and_scan(P, g, sc, s, in->debug);
+        prof_end(PF_DEPTH_SORT_SCAN, s);
+        if (rc) { cudaFreeAsync(scratch1, s); return rc; }
         uint32_t* h = pinned_scalar();
         if (!h) { cudaFreeAsync(scratch1, s); set_error("cudaMallocHost failed"); return 2; }
         OGS_CUDA(cudaMemcpyAsync(h, sc.offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s));
@@ -197,7 +255,10 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     ba.extra = in->extra; ba.bg = in->bg;
     ba.out_color = out->color; ba.out_depth = out->depth; ba.out_alpha = out->alpha;
     ba.final_T = final_T; ba.n_contrib = n_contrib;
-    if ((rc = launch_blend_forward(ba, s))) return rc;
+    prof_begin(PF_BLEND_FWD, s);
+    rc = launch_blend_forward(ba, s);
+    prof_end(PF_BLEND_FWD, s);
+    if (rc) return rc;
     OGS_KERNEL_CHECK("blend_forward", in->debug, s);
     return 0;
 }
@@ -232,7 +293,10 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
     ba.geom = geom;
     ba.acc = (float*)go->scratch;
     ba.stride = blend_bwd_stride(C, geom);
-    if ((rc = launch_blend_backward(ba, s))) return rc;
+    prof_begin(PF_BLEND_BWD, s);
+    rc = launch_blend_backward(ba, s);
+    prof_end(PF_BLEND_BWD, s);
+    if (rc) return rc;
     OGS_KERNEL_CHECK("blend_backward", in->debug, s);
 
     PreprocessBwdArgs pa;
@@ -245,7 +309,10 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
     pa.dL_dmeans3D = go->dL_dmeans3D; pa.dL_dmeans2D = go->dL_dmeans2D; pa.dL_dopacities = go->dL_dopacities;
     pa.dL_dshs = go->dL_dshs; pa.dL_dcolors_precomp = go->dL_dcolors_precomp; pa.dL_dscales = go->dL_dscales;
     pa.dL_drotations = go->dL_drotations; pa.dL_dcov3D = go->dL_dcov3D; pa.dL_dextra = go->dL_dextra;
-    if ((rc = launch_preprocess_backward(pa, s))) return rc;
+    prof_begin(PF_PREPROCESS_BWD, s);
+    rc = launch_preprocess_backward(pa, s);
+    prof_end(PF_PREPROCESS_BWD, s);
+    if (rc) return rc;
     OGS_KERNEL_CHECK("preprocess_backward", in->debug, s);
     return 0;
 }
@@ -295,6 +362,7 @@ int ogs_kmeans_assign(int64_t N, const float* a, int32_t Da, const float* b, int
     if (N == 0) return 0;
     int rc = ensure_pool();
     if (rc) return rc;
+    ProfScope ps(PF_KMEANS_ASSIGN, (cudaStream_t)stream_);
     return launch_kmeans_assign(N, a, Da, b, Db, scale_b, centers, k, select_ids, selected, id_offset, ids_out, sums,
                                 counts, (cudaStream_t)stream_);
 }

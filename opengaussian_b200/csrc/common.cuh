@@ -27,6 +27,17 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns (int)e
         if (_e != cudaSuccess) return ogs::cuda_fail(_e, name);       \
     } while (0)
 
+// ---- optional per-family device timing (CUDA events on the launching stream) ----
+enum ProfFamily { PF_PREPROCESS_FWD = 0, PF_DEPTH_SORT_SCAN, PF_EMIT, PF_TILE_SORT, PF_RANGES, PF_BLEND_FWD,
+                  PF_BLEND_BWD, PF_PREPROCESS_BWD, PF_KMEANS_ASSIGN, PF_COUNT };
+void prof_begin(int family, cudaStream_t s);
+void prof_end(int family, cudaStream_t s);
+struct ProfScope {
+    int f; cudaStream_t s;
+    ProfScope(int family, cudaStream_t st) : f(family), s(st) { prof_begin(f, s); }
+    ~ProfScope() { prof_end(f, s); }
+};
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- geometry state layout (one caller-owned block, see ogs_raster_state::geom) ----

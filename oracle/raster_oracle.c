@@ -38,6 +38,23 @@
 #include <string.h>
 
 #define OGS_TILE 16
+/* The pixel loops are OpenMP-parallel when built with -fopenmp (bench.py's CPU baselines use all
+ * host threads); per-Gaussian gradient sums then use atomic double adds. */
+#ifdef _OPENMP
+#include <omp.h>
+#define OGS_ATOMIC _Pragma("omp atomic")
+#else
+#define OGS_ATOMIC
+#endif
+int ogs_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 static const float SH_C0 = 0.28209479177387814f;
 static const float SH_C1 = 0.4886025119029199f;
@@ -171,6 +188,7 @@ int ogs_oracle_preprocess(int P, int sh_degree, int M, const float* means3D, con
     const float fx = (float)W / (2.0f * tanfovx);
     const float fy = (float)H / (2.0f * tanfovy);
     const int gx = (W + OGS_TILE - 1) / OGS_TILE, gy = (H + OGS_TILE - 1) / OGS_TILE;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < P; i++) {
         radii[i] = 0;
         tiles_touched[i] = 0;
@@ -307,7 +325,10 @@ int ogs_oracle_blend_forward(int W, int H, int C, const uint32_t* ranges, const 
                              float* out_depth, float* out_alpha, float* final_T,
                              uint32_t* n_contrib, uint8_t* flags) {
     const int gx = (W + OGS_TILE - 1) / OGS_TILE;
+#pragma omp parallel
+    {
     float* acc = (float*)malloc(sizeof(float) * (size_t)C);
+#pragma omp for schedule(dynamic, 4)
     for (int py = 0; py < H; py++)
         for (int px = 0; px < W; px++) {
             int tile = (py / OGS_TILE) * gx + (px / OGS_TILE);
@@ -346,6 +367,7 @@ int ogs_oracle_blend_forward(int W, int H, int C, const uint32_t* ranges, const 
             if (flags) flags[pix] = flag;
         }
     free(acc);
+    }
     return 0;
 }
 
@@ -368,10 +390,13 @@ int ogs_oracle_blend_backward(int P, int W, int H, int C, const uint32_t* ranges
     memset(dL_dopacity, 0, sizeof(double) * (size_t)P);
     memset(dL_dcolors, 0, sizeof(double) * (size_t)C * P);
     memset(dL_ddepth, 0, sizeof(double) * (size_t)P);
+    const double ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
+#pragma omp parallel
+    {
     double* accum_rec = (double*)malloc(sizeof(double) * C);
     double* last_color = (double*)malloc(sizeof(double) * C);
     double* g = (double*)malloc(sizeof(double) * C);
-    const double ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
+#pragma omp for schedule(dynamic, 4)
     for (int py = 0; py < H; py++)
         for (int px = 0; px < W; px++) {
             size_t pix = (size_t)py * W + px;
@@ -403,12 +428,14 @@ int ogs_oracle_blend_backward(int P, int W, int H, int C, const uint32_t* ranges
                     accum_rec[c] = last_alpha * last_color[c] + (1.0 - last_alpha) * accum_rec[c];
                     last_color[c] = col;
                     dL_dalpha += (col - accum_rec[c]) * g[c];
+                    OGS_ATOMIC
                     dL_dcolors[(size_t)gi * C + c] += w * g[c];
                 }
                 double cd = depth[gi];
                 accum_depth = last_alpha * last_depth + (1.0 - last_alpha) * accum_depth;
                 last_depth = cd;
                 dL_dalpha += (cd - accum_depth) * gd;
+                OGS_ATOMIC
                 dL_ddepth[gi] += w * gd;
                 accum_alpha = last_alpha * 1.0 + (1.0 - last_alpha) * accum_alpha;
                 dL_dalpha += (1.0 - accum_alpha) * ga;
@@ -420,15 +447,22 @@ int ogs_oracle_blend_backward(int P, int W, int H, int C, const uint32_t* ranges
                 const double gdx = G * dx, gdy = G * dy;
                 const double dG_ddelx = -gdx * co[0] - gdy * co[1];
                 const double dG_ddely = -gdy * co[2] - gdx * co[1];
+                OGS_ATOMIC
                 dL_dmean2D[2 * gi + 0] += dL_dG * dG_ddelx * ddelx_dx;
+                OGS_ATOMIC
                 dL_dmean2D[2 * gi + 1] += dL_dG * dG_ddely * ddely_dy;
+                OGS_ATOMIC
                 dL_dconic[3 * gi + 0] += -0.5 * gdx * dx * dL_dG;
+                OGS_ATOMIC
                 dL_dconic[3 * gi + 1] += -0.5 * gdx * dy * dL_dG;
+                OGS_ATOMIC
                 dL_dconic[3 * gi + 2] += -0.5 * gdy * dy * dL_dG;
+                OGS_ATOMIC
                 dL_dopacity[gi] += G * dL_dalpha;
             }
         }
     free(accum_rec); free(last_color); free(g);
+    }
     return 0;
 }
 
@@ -459,6 +493,7 @@ int ogs_oracle_preprocess_backward(int P, int sh_degree, int M, int C, const flo
     memset(dL_dcov3D, 0, sizeof(double) * 6 * (size_t)P);
     if (dL_dshs) memset(dL_dshs, 0, sizeof(double) * 3 * (size_t)M * P);
     const float* v = view;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < P; i++) {
         if (!(radii[i] > 0)) continue;
         const float* m = means3D + 3 * i;

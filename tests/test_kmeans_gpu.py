@@ -1,0 +1,156 @@
+"""GPU parity of the k-means codebook kernels (through the Quantize_kMeans drop-in / C ABI).
+
+* one assign pass: ids BIT-EXACT vs the C oracle (same fmaf chain, lowest-index ties);
+  fused centroid sums/counts: counts exact, sums within fp32 reordering (1e-5 relative);
+* full cluster_assign (root + leaf) vs the golden vectors produced by the reference file itself:
+  ids equal away from near-ties (<= 2e-3 mismatches), centres within 2e-3;
+* properties at BASELINE size (5 M points): every id is the argmin under a recomputed fp64
+  distance up to fp32 slack; counts sum to N; idempotence of the reassign.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kmeans as okm
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "kmeans_golden.npz")
+
+
+def _golden_inputs(name):
+    spec = importlib.util.spec_from_file_location("mkg", os.path.join(os.path.dirname(GOLD), "make_kmeans_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.inputs(name), m.CASES[name]
+
+
+class _G:
+    pass
+
+
+@pytest.mark.parametrize("N,Da,Db,k", [(1, 6, 3, 64), (31, 6, 0, 10), (10_000, 6, 3, 64), (123_457, 6, 3, 64),
+                                       (50_000, 6, 0, 7), (4096, 3, 0, 1), (70_000, 9, 0, 200)])
+def test_assign_bit_exact_and_fused_sums(N, Da, Db, k):
+    from opengaussian_b200.kmeans_quantize import kmeans_assign
+    rs = np.random.RandomState(N % 97)
+    a = rs.rand(N, Da).astype(np.float32)
+    b = (rs.rand(N, Db).astype(np.float32) * 4 - 2) if Db else None
+    centers = rs.rand(k, Da + Db).astype(np.float32)
+    if k > 2:
+        centers[2] = centers[1]                       # duplicate centre: ties must go to the lower index
+    scale_b = 0.37
+    want = okm.assign(a, b, scale_b, centers)
+    sums = torch.zeros(k, Da + Db, device="cuda")
+    cnt = torch.zeros(k, device="cuda")
+    ids = kmeans_assign(torch.from_numpy(a).cuda(), None if b is None else torch.from_numpy(b).cuda(), scale_b,
+                        torch.from_numpy(centers).cuda(), sums=sums, counts=cnt)
+    assert ids.dtype == torch.int64
+    assert np.array_equal(ids.cpu().numpy(), want)
+    wsum, wcnt = okm.accumulate(a, b, scale_b, k, want)
+    assert np.array_equal(cnt.cpu().numpy(), wcnt)
+    assert np.allclose(sums.cpu().numpy(), wsum, rtol=1e-5, atol=1e-4 * max(1.0, np.abs(wsum).max() * 1e-2))
+
+
+def test_assign_select_and_offset():
+    from opengaussian_b200.kmeans_quantize import kmeans_assign
+    rs = np.random.RandomState(5)
+    N = 30_000
+    a = rs.rand(N, 6).astype(np.float32)
+    sel = rs.randint(0, 8, size=N).astype(np.int64)
+    centers = rs.rand(5, 6).astype(np.float32)
+    out0 = np.full(N, 640, np.int64)
+    want = okm.assign(a, None, 1.0, centers, sel, 3, 30, out0.copy())
+    ids = torch.from_numpy(out0.copy()).cuda()
+    sums = torch.zeros(5, 6, device="cuda")
+    cnt = torch.zeros(5, device="cuda")
+    kmeans_assign(torch.from_numpy(a).cuda(), None, 1.0, torch.from_numpy(centers).cuda(),
+                  torch.from_numpy(sel).cuda(), 3, 30, ids, sums, cnt)
+    assert np.array_equal(ids.cpu().numpy(), want)
+    assert int(cnt.sum()) == int((sel == 3).sum())
+
+
+def test_quantize_kmeans_vs_reference_golden():
+    from opengaussian_b200.kmeans_quantize import Quantize_kMeans
+    gold = np.load(GOLD)
+    for name in ("root_25k", "root_20k_exact_chunks"):
+        (ins_feat, xyz), (N, k1, k2, iters, pw) = _golden_inputs(name)
+        g = _G()
+        g._ins_feat = torch.from_numpy(ins_feat).cuda().requires_grad_(True)
+        g._xyz = torch.from_numpy(xyz).cuda()
+        q = Quantize_kMeans(num_clusters=k1, num_leaf_clusters=k2, num_iters=iters, dim=9)
+        q.centers = torch.from_numpy(np.concatenate([ins_feat, xyz * np.float32(pw)], 1)[:k1]).cuda()
+        q.forward(g, 1, assign=True, mode="root", pos_weight=pw)
+        ref_ids = gold[f"{name}/cls_ids"].astype(np.int64)
+        assert q.cls_ids.dtype == torch.int64 and q.centers.dtype == torch.float32
+        assert (q.cls_ids.cpu().numpy() != ref_ids).mean() <= 2e-3
+        assert np.allclose(q.centers.cpu().numpy(), gold[f"{name}/centers"], rtol=2e-3, atol=2e-3)
+        fq = g._ins_feat_q.detach().cpu().numpy()[:512]
+        assert (np.abs(fq - gold[f"{name}/ins_feat_q"]).max(1) > 1e-3).mean() <= 0.01
+        # straight-through: gradient of _ins_feat_q flows unchanged into _ins_feat
+        g._ins_feat_q.sum().backward()
+        assert torch.equal(g._ins_feat.grad, torch.ones_like(g._ins_feat))
+        # the CUDA path and the CPU oracle mirror agree closely
+        oc, oi = okm.cluster_assign_root(ins_feat, xyz, pw, np.concatenate([ins_feat, xyz * np.float32(pw)], 1)[:k1], iters)
+        assert (q.cls_ids.cpu().numpy() != oi).mean() <= 1e-4
+        assert np.allclose(q.centers.cpu().numpy(), oc, rtol=1e-4, atol=1e-5)
+        if name == "root_25k":
+            q.cls_ids = torch.from_numpy(ref_ids).cuda()
+            q.leaf_centers = torch.from_numpy(ins_feat[:k1 * k2 + 1].copy()).cuda()
+            q.leaf_cls_ids = torch.ones(N, device="cuda").to(torch.int64) * k1 * k2
+            sub = torch.full((k1,), k2, dtype=torch.int64)
+            sub[7] = 4
+            q.iLeafSubNum = sub
+            for sel in (3, 7):
+                q.forward(g, 1, assign=True, mode="leaf", selected_leaf=sel)
+            ref_leaf = gold[f"{name}/leaf_cls_ids"].astype(np.int64)
+            got = q.leaf_cls_ids.cpu().numpy()
+            assert (got != ref_leaf).mean() <= 2e-3
+            assert np.array_equal(got == k1 * k2, ref_leaf == k1 * k2)
+            lc = q.leaf_centers.cpu().numpy()
+            assert np.allclose(lc, gold[f"{name}/leaf_centers"], rtol=2e-3, atol=2e-3)
+            assert np.all(lc[7 * k2 + 4:8 * k2] == 0.0)
+            # lazily built equalize_cluster_size products keep the reference's shapes
+            assert q.cluster_ids.numel() == (k1 * k2 + 1) * int(q.max_cnt)
+            assert q.cluster_len.shape == (k1 * k2 + 1, 1)
+
+
+def test_non_assign_forward_is_noop_on_centres():
+    from opengaussian_b200.kmeans_quantize import Quantize_kMeans
+    (ins_feat, xyz), (N, k1, k2, iters, pw) = _golden_inputs("root_20k_exact_chunks")
+    g = _G()
+    g._ins_feat = torch.from_numpy(ins_feat).cuda().requires_grad_(True)
+    g._xyz = torch.from_numpy(xyz).cuda()
+    q = Quantize_kMeans(num_clusters=k1, num_leaf_clusters=k2, num_iters=2, dim=9)
+    q.forward(g, 1, assign=True, mode="root", pos_weight=pw)      # random init path (torch.randperm)
+    c0, i0 = q.centers.clone(), q.nn_index.clone()
+    q.forward(g, 2, assign=False, mode="root", pos_weight=pw)
+    assert torch.equal(q.centers, c0) and torch.equal(q.nn_index, i0)
+    assert torch.allclose(g._ins_feat_q, c0[i0][:, :6])
+
+
+def test_full_size_properties():
+    """BASELINE config 5 size (5 M points, coarse k=64, D=9): size-independent properties."""
+    from opengaussian_b200.kmeans_quantize import kmeans_assign
+    N, k = 5_000_000, 64
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.rand(N, 6, device="cuda", generator=gen)
+    b = (torch.rand(N, 3, device="cuda", generator=gen) - 0.5) * 8
+    centers = torch.cat([a[:k], b[:k] * 0.5], 1).contiguous()
+    sums = torch.zeros(k, 9, device="cuda")
+    cnt = torch.zeros(k, device="cuda")
+    ids = kmeans_assign(a, b, 0.5, centers, sums=sums, counts=cnt)
+    assert int(cnt.sum()) == N and int(ids.min()) >= 0 and int(ids.max()) < k
+    assert torch.equal(torch.bincount(ids, minlength=k).float(), cnt)
+    x = torch.cat([a, b * 0.5], 1)
+    idx = torch.randint(0, N, (200_000,), device="cuda", generator=gen)
+    d = torch.cdist(x[idx].double(), centers.double())
+    best = d.min(1).values
+    mine = d.gather(1, ids[idx, None])[:, 0]
+    assert float((mine - best).max()) <= 1e-5            # chosen centre is the (fp32-slack) nearest
+    assert torch.allclose(sums.double(), torch.zeros(k, 9, device="cuda", dtype=torch.float64).index_add_(0, ids, x.double()),
+                          rtol=1e-4, atol=1e-1)
+    # idempotence: same centres -> same ids
+    assert torch.equal(kmeans_assign(a, b, 0.5, centers), ids)

@@ -1,0 +1,147 @@
+"""CPU tests (no GPU): the oracles against (i) the golden vectors produced by the reference
+k-means file itself, (ii) an independent fp64 autograd restatement, (iii) structural properties."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import np_inputs, small_scene, to_oracle_cam
+from oracle import kmeans as okm
+from oracle import raster as orc
+from oracle import raster_torch as rt
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "kmeans_golden.npz")
+
+
+def _golden_inputs(name):
+    spec = importlib.util.spec_from_file_location("mkg", os.path.join(os.path.dirname(GOLD), "make_kmeans_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.inputs(name), m.CASES[name]
+
+
+@pytest.mark.parametrize("name", ["root_25k", "root_20k_exact_chunks"])
+def test_kmeans_oracle_vs_reference_golden_root(name):
+    gold = np.load(GOLD)
+    (ins_feat, xyz), (N, k1, k2, iters, pw) = _golden_inputs(name)
+    c0 = np.concatenate([ins_feat, xyz * np.float32(pw)], 1)[:k1]
+    centers, ids = okm.cluster_assign_root(ins_feat, xyz, pw, c0, iters)
+    ref_ids = gold[f"{name}/cls_ids"].astype(np.int64)
+    mism = (ids != ref_ids).mean()
+    # the reference's cdist uses the cancellation-prone matmul form with an unspecified BLAS order:
+    # agreement is required away from near-ties only ("k-means bit-exact ids")
+    assert mism <= 2e-3, mism
+    assert np.allclose(centers, gold[f"{name}/centers"], rtol=2e-3, atol=2e-3)
+    q = centers[ids[:512]][:, :6]
+    assert np.abs(q - gold[f"{name}/ins_feat_q"]).max() < 0.25   # a few near-tie points may switch centre
+    assert (np.abs(q - gold[f"{name}/ins_feat_q"]).max(1) > 1e-3).mean() <= 0.01
+
+
+def test_kmeans_oracle_vs_reference_golden_leaf():
+    gold = np.load(GOLD)
+    name = "root_25k"
+    (ins_feat, xyz), (N, k1, k2, iters, pw) = _golden_inputs(name)
+    cls_ids = gold[f"{name}/cls_ids"].astype(np.int64)          # coarse ids as the reference produced them
+    leaf_centers = ins_feat[:k1 * k2 + 1].copy()
+    leaf_ids = np.full(N, k1 * k2, np.int64)
+    for sel, n_sub in ((3, k2), (7, 4)):
+        leaf_centers, leaf_ids = okm.cluster_assign_leaf(ins_feat, cls_ids, leaf_centers, leaf_ids, sel, n_sub, k2, iters)
+    ref_ids = gold[f"{name}/leaf_cls_ids"].astype(np.int64)
+    assert (leaf_ids != ref_ids).mean() <= 2e-3
+    assert np.array_equal(leaf_ids == k1 * k2, ref_ids == k1 * k2)      # sentinel for untouched points
+    assert np.allclose(leaf_centers, gold[f"{name}/leaf_centers"], rtol=2e-3, atol=2e-3)
+    # rows >= iLeafSubNum of a rewritten block are zero (0 / eps), rows of untouched blocks keep their init
+    assert np.all(leaf_centers[7 * k2 + 4:8 * k2] == 0.0)
+    assert np.array_equal(leaf_centers[0:k2], ins_feat[0:k2])
+
+
+def test_kmeans_assign_tie_and_select():
+    a = np.array([[0.0, 0.0], [1.0, 1.0], [0.5, 0.5]], np.float32)
+    c = np.array([[1.0, 1.0], [0.0, 0.0], [1.0, 1.0]], np.float32)
+    ids = okm.assign(a, None, 1.0, c)
+    assert ids.tolist() == [1, 0, 0]          # exact tie at [0.5,0.5] -> lowest index; duplicate centre -> first
+    sel = np.array([5, 6, 5], np.int64)
+    out = np.full(3, -7, np.int64)
+    okm.assign(a, None, 1.0, c, sel, 5, 100, out)
+    assert out.tolist() == [101, -7, 100]
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-20)
+
+
+@pytest.mark.parametrize("mode", ["sh", "cov_precomp_colors"])
+def test_raster_oracle_backward_vs_fp64_autograd(mode):
+    P, W, H = 150, 48, 32
+    gs, cam = small_scene(P=P, W=W, H=H, seed=1)
+    ocam = to_oracle_cam(cam)
+    g = np_inputs(gs)
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    rng = np.random.default_rng(0)
+    colors = rng.random((P, 3)).astype(np.float32)
+    if mode == "sh":
+        st = orc.forward(ocam, g["means3D"], g["opacities"], g["scales"], g["rotations"], shs=g["shs"],
+                         extra=g["ins_feat"], bg=bg)
+    else:
+        st0 = orc.forward(ocam, g["means3D"], g["opacities"], g["scales"], g["rotations"], shs=g["shs"], bg=bg)
+        st = orc.forward(ocam, g["means3D"], g["opacities"], cov3D_precomp=st0.cov3D * 0 + _cov(g), colors_precomp=colors,
+                         extra=g["ins_feat"], bg=bg)
+    gc = rng.standard_normal((9, H, W)).astype(np.float32)
+    gd = rng.standard_normal((H, W)).astype(np.float32)
+    ga = rng.standard_normal((H, W)).astype(np.float32)
+    gr = orc.backward(st, gc, gd, ga)
+
+    T = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=True)  # noqa: E731
+    m3, op, ex = T(g["means3D"]), T(g["opacities"]), T(g["ins_feat"])
+    m2 = torch.zeros(P, 3, dtype=torch.float64, requires_grad=True)
+    kw, leaves = {}, dict(means3D=m3, means2D=m2, opacities=op, extra=ex)
+    if mode == "sh":
+        leaves.update(scales=T(g["scales"]), rotations=T(g["rotations"]), shs=T(g["shs"]))
+        kw = dict(scales=leaves["scales"], rotations=leaves["rotations"], shs=leaves["shs"])
+    else:
+        leaves.update(cov3D_precomp=T(_cov(g)), colors_precomp=T(colors))
+        kw = dict(cov3D_precomp=leaves["cov3D_precomp"], colors_precomp=leaves["colors_precomp"])
+    c, d, a = rt.render(ocam, st.radii, st.point_list, st.ranges, m3, m2, op, extra=ex, bg=bg.astype(np.float64), **kw)
+    assert np.abs(c.detach().numpy() - st.color).max() < 5e-6
+    assert np.abs(a.detach().numpy() - st.out_alpha).max() < 5e-6
+    L = (c * torch.tensor(gc, dtype=torch.float64)).sum() + (d * torch.tensor(gd, dtype=torch.float64)).sum() + \
+        (a * torch.tensor(ga, dtype=torch.float64)).sum()
+    L.backward()
+    for k, t in leaves.items():
+        assert _rel(gr[k], t.grad.numpy().reshape(np.asarray(gr[k]).shape)) < 2e-5, k
+
+
+def _cov(g):
+    q = g["rotations"].astype(np.float64)
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                  2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                  2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+    L = R * g["scales"].astype(np.float64)[:, None, :]
+    S = L @ L.transpose(0, 2, 1)
+    return np.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1).astype(np.float32)
+
+
+def test_raster_oracle_structure():
+    gs, cam = small_scene(P=2000, W=100, H=70, seed=2, scale_mult=3.0)
+    g = np_inputs(gs)
+    st = orc.forward(to_oracle_cam(cam), g["means3D"], g["opacities"], g["scales"], g["rotations"], shs=g["shs"])
+    assert st.N == int(st.tiles_touched.sum()) == len(st.keys)
+    assert np.all(st.keys[1:] >= st.keys[:-1])
+    tiles = (st.keys >> np.uint64(32)).astype(np.int64)
+    for t in np.unique(tiles)[:50]:
+        lo, hi = st.ranges[t]
+        assert np.all(tiles[lo:hi] == t) and (lo == 0 or tiles[lo - 1] != t) and (hi == st.N or tiles[hi] != t)
+    # depth order inside a tile, ties broken by Gaussian index (stable sort of emission order)
+    lo, hi = st.ranges[np.bincount(tiles).argmax()]
+    d = st.depth[st.point_list[lo:hi]]
+    assert np.all(np.diff(d) >= 0)
+    assert st.out_alpha.min() >= 0 and st.out_alpha.max() <= 1 + 1e-6
+    assert np.allclose(st.out_alpha, 1 - st.final_T, atol=2e-6)
+    # empty scene -> background
+    st0 = orc.forward(to_oracle_cam(cam), g["means3D"][:0], g["opacities"][:0], g["scales"][:0], g["rotations"][:0],
+                      shs=g["shs"][:0], bg=np.array([0.2, 0.4, 0.6], np.float32))
+    assert st0.N == 0 and np.allclose(st0.color[1], 0.4)
