@@ -55,29 +55,75 @@ int depth_sort_and_scan(int P, const GeomPtrs& g, BinScratch& sc, cudaStream_t s
 __device__ __forceinline__ int imin_(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int imax_(int a, int b) { return a > b ? a : b; }
 
-__global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, const uint32_t* __restrict__ order,
+// Entry-balanced emit: CTA b writes output entries [b*EMIT_CHUNK, (b+1)*EMIT_CHUNK).  The
+// depth-sorted Gaussians that own those entries are found by a binary search over the inclusive
+// offsets, staged 256 at a time (start offset + rect) in shared memory, and the span is written
+// entry-parallel (owner = 8-step binary search in shared memory).  Every store is coalesced and
+// every CTA does the same amount of work, however skewed the per-Gaussian tile counts are (the
+// nearest Gaussians -- first in depth order -- cover thousands of tiles each).
+#define EMIT_CHUNK 2048
+__global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, uint32_t N, const uint32_t* __restrict__ order,
                                                    const uint32_t* __restrict__ offsets,
                                                    const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                                                    uint16_t* __restrict__ tkeys, uint32_t* __restrict__ tvals) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= P) return;
-    const uint32_t g = order[i];
-    const float4 b = rec1[g];
-    const int radius = __float_as_int(b.w);
-    if (radius <= 0) return;
-    const float4 a = rec0[g];
-    const float r = (float)radius;
-    const int x0 = imin_(gx, imax_(0, (int)((a.x - r) / 16.0f)));
-    const int y0 = imin_(gy, imax_(0, (int)((a.y - r) / 16.0f)));
-    const int x1 = imin_(gx, imax_(0, (int)((a.x + r + 15.0f) / 16.0f)));
-    const int y1 = imin_(gy, imax_(0, (int)((a.y + r + 15.0f) / 16.0f)));
-    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            tkeys[off] = (uint16_t)(y * gx + x);
-            tvals[off] = g;
-            off++;
+    __shared__ uint32_t s_start[256];
+    __shared__ uint32_t s_g[256];
+    __shared__ uint32_t s_rect[256];   // x0 | y0 << 16
+    __shared__ uint32_t s_w[256];      // rect width in tiles
+    __shared__ uint32_t s_round_end;
+    const int t = threadIdx.x;
+    const uint32_t chunk_lo = blockIdx.x * (uint32_t)EMIT_CHUNK;
+    const uint32_t chunk_hi = min(N, chunk_lo + (uint32_t)EMIT_CHUNK);
+    // first sorted slot whose inclusive offset exceeds chunk_lo (it owns entry chunk_lo)
+    int lo = 0, hi = P;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) > chunk_lo) hi = mid; else lo = mid + 1;
+    }
+    for (int round_start = lo; round_start < P; round_start += 256) {
+        const int slot = round_start + t;
+        uint32_t start = 0xFFFFFFFFu, g = 0, rect = 0, rw = 1;
+        if (slot < P) {
+            start = (slot == 0) ? 0u : __ldg(offsets + slot - 1);
+            if (start < chunk_hi) {
+                g = order[slot];
+                const float4 b = rec1[g];
+                const int radius = __float_as_int(b.w);
+                if (radius > 0) {
+                    const float4 a = rec0[g];
+                    const float r = (float)radius;
+                    const int x0 = imin_(gx, imax_(0, (int)((a.x - r) / 16.0f)));
+                    const int y0 = imin_(gy, imax_(0, (int)((a.y - r) / 16.0f)));
+                    const int x1 = imin_(gx, imax_(0, (int)((a.x + r + 15.0f) / 16.0f)));
+                    rect = (uint32_t)x0 | ((uint32_t)y0 << 16);
+                    rw = (uint32_t)(x1 - x0);
+                }
+            }
         }
+        const int last_slot = min(P, round_start + 256) - 1;
+        if (slot == last_slot) s_round_end = min(chunk_hi, __ldg(offsets + slot));
+        s_start[t] = start;
+        s_g[t] = g;
+        s_rect[t] = rect;
+        s_w[t] = rw;
+        __syncthreads();
+        const uint32_t e_lo = max(chunk_lo, s_start[0]);
+        const uint32_t e_hi = s_round_end;
+        for (uint32_t e = e_lo + t; e < e_hi; e += 256) {
+            int j = 0;   // last j with s_start[j] <= e
+#pragma unroll
+            for (int step = 128; step >= 1; step >>= 1)
+                if (s_start[j + step] <= e) j += step;
+            const uint32_t rc = s_rect[j];
+            const uint32_t local = e - s_start[j];
+            const uint32_t w = s_w[j];
+            const uint32_t dy = local / w, dx = local - dy * w;
+            tkeys[e] = (uint16_t)(((rc >> 16) + dy) * gx + (rc & 0xFFFFu) + dx);
+            tvals[e] = s_g[j];
+        }
+        __syncthreads();
+        if (e_hi >= chunk_hi) break;
+    }
 }
 
 __global__ void __launch_bounds__(256) ranges_kernel(int64_t N, const uint16_t* __restrict__ tk,
@@ -101,8 +147,8 @@ int emit_sort_ranges(int P, int W, int H, int64_t N, const GeomPtrs& g, BinScrat
     OGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
     if (N == 0) return 0;
     prof_begin(PF_EMIT, s);
-    emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, gx, gy, sc.dvals_out, sc.offsets, g.rec0, g.rec1, tkeys_in,
-                                                tvals_in);
+    emit_kernel<<<(unsigned)((N + EMIT_CHUNK - 1) / EMIT_CHUNK), 256, 0, s>>>(P, gx, gy, (uint32_t)N, sc.dvals_out,
+                                                                              sc.offsets, g.rec0, g.rec1, tkeys_in, tvals_in);
     prof_end(PF_EMIT, s);
     OGS_KERNEL_CHECK("emit_kernel", debug, s);
     int bits = 0;

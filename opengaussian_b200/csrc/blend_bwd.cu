@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     }
     float S = 0.f, last_dot = 0.f, last_alpha = 0.f;
     const float half_w = 0.5f * (float)a.W, half_h = 0.5f * (float)a.H;
+    const float bx0 = (float)(blockIdx.x * 16 + (warp & 1) * 8), by0 = (float)(blockIdx.y * 16 + (warp >> 1) * 4);
 
     // block / warp maxima of the last contributor
     if (threadIdx.x == 0) s_max_last = 0;
@@ -120,7 +121,17 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
         __syncthreads();
         // ---- traverse back to front ----
         if (start < wmax) {
-            for (int j = min(n, wmax - start) - 1; j >= 0; j--) {
+          const int nw = min(n, wmax - start);
+          for (int grp = ((nw - 1) >> 5) << 5; grp >= 0; grp -= 32) {
+            // warp-level culling (see blend_fwd.cu): lane l tests entry grp+l against the warp's 8x4 block
+            const int idx = grp + lane;
+            bool hit = false;
+            if (idx < nw) hit = ogs_rect_hit(s_r0[idx], s_r1[idx], bx0, by0, bx0 + 7.0f, by0 + 3.0f);
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int bit = 31 - __clz(mask);
+                mask &= ~(1u << bit);
+                const int j = grp + bit;
                 const int pos = start + j;
                 const float4 r0 = s_r0[j];
                 const float4 r1 = s_r1[j];
@@ -165,6 +176,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
                 const int k = lane >> SHIFT;
                 if ((lane & ((1 << SHIFT) - 1)) == 0 && k < V) my_acc[j * V + k] += v[0];
             }
+          }
         }
         __syncthreads();
         // ---- flush: sum the 8 warp rows, one red per value per (tile, Gaussian) ----

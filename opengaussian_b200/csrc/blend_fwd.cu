@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     float acc[C];
 #pragma unroll
     for (int c = 0; c < C; c++) acc[c] = 0.f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
+    const float bx0 = (float)(blockIdx.x * 16 + (warp & 1) * 8), by0 = (float)(blockIdx.y * 16 + (warp >> 1) * 4);
 
     for (int r = 0; r < rounds; r++, todo -= BATCH) {
         if (__syncthreads_count(done) == OGS_BLOCK) break;
@@ -59,24 +60,31 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
         __syncthreads();
         const int n = todo < BATCH ? todo : BATCH;
         if (!__all_sync(0xffffffffu, done)) {
-            for (int j = 0; j < n; j++) {
-                contributor++;
-                const float4 r0 = s_r0[j];
-                const float4 r1 = s_r1[j];
-                const float dx = r0.x - pxf, dy = r0.y - pyf;
-                const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
-                float alpha = fminf(0.99f, r1.y * __expf(power));
-                const bool ok = !done && power <= 0.0f && alpha >= (1.0f / 255.0f);
-                if (!__any_sync(0xffffffffu, ok)) continue;
-                if (!ok) continue;
-                const float test_T = T * (1.0f - alpha);
-                if (test_T < 0.0001f) { done = true; continue; }
-                const float w = alpha * T;
+            for (int grp = 0; grp < n; grp += 32) {
+                // warp-level culling: lane l tests entry grp+l against this warp's 8x4 pixel block
+                const int idx = grp + lane;
+                bool hit = false;
+                if (idx < n) hit = ogs_rect_hit(s_r0[idx], s_r1[idx], bx0, by0, bx0 + 7.0f, by0 + 3.0f);
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int j = grp + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float4 r0 = s_r0[j];
+                    const float4 r1 = s_r1[j];
+                    const float dx = r0.x - pxf, dy = r0.y - pyf;
+                    const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
+                    const float alpha = fminf(0.99f, r1.y * __expf(power));
+                    if (done || power > 0.0f || alpha < (1.0f / 255.0f)) continue;
+                    const float test_T = T * (1.0f - alpha);
+                    if (test_T < 0.0001f) { done = true; continue; }
+                    const float w = alpha * T;
 #pragma unroll
-                for (int c = 0; c < C; c++) acc[c] = fmaf(s_col[j * C + c], w, acc[c]);
-                D = fmaf(r1.z, w, D);
-                T = test_T;
-                last = contributor;
+                    for (int c = 0; c < C; c++) acc[c] = fmaf(s_col[j * C + c], w, acc[c]);
+                    D = fmaf(r1.z, w, D);
+                    T = test_T;
+                    last = (uint32_t)(r * BATCH + j + 1);
+                }
+                if (__all_sync(0xffffffffu, done)) break;
             }
         }
     }

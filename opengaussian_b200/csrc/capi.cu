@@ -132,7 +132,15 @@ extern "C" {
 
 int ogs_abi_version(void) { return OGS_ABI_VERSION; }
 
-void ogs_profile_enable(int on) { g_prof_on = on != 0; }
+void ogs_profile_enable(int on) {
+    g_prof_on = on != 0;
+    if (g_prof_on && g_prof_free.size() < 2048) {   // pre-create so that recording costs no driver allocation
+        for (int i = 0; i < 2048; i++) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) == cudaSuccess) g_prof_free.push_back(e);
+        }
+    }
+}
 
 int ogs_profile_read(float* ms_out, int32_t* launches_out, int32_t n) {
     float ms[PF_COUNT] = {0};
@@ -164,7 +172,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
                        void* alloc_user, ogs_raster_state* st, void* stream_) {
     int rc = validate_inputs(in);
     if (rc) return rc;
-    if (!out || !out->color || !out->depth || !out->alpha || !out->radii || !alloc || !st) {
+    if (!out || !out->color || !out->depth || !out->alpha || (!out->radii && in->P > 0) || !alloc || !st) {
         set_error("outputs/alloc/state must be set");
         return -1;
     }

@@ -167,6 +167,42 @@ struct PreprocessBwdArgs {
 };
 int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s);
 
+#ifdef __CUDACC__
+// Conservative test "can Gaussian (r0 = x,y,A,B ; r1 = C,opacity,..) reach alpha >= 1/255 anywhere in
+// the pixel rectangle [x0,x1] x [y0,y1]?".  alpha >= 1/255 needs q(d) = A dx^2 + 2 B dx dy + C dy^2
+// <= 2 ln(255 opacity); q is convex, so its minimum over the rectangle is 0 if the centre is inside,
+// else the smallest of the four clamped 1-D edge minima.  A small margin keeps the test conservative
+// under fp32 rounding: an entry is dropped only if it would have been skipped by every pixel.
+__device__ __forceinline__ bool ogs_rect_hit(const float4 r0, const float4 r1, float x0, float y0, float x1, float y1) {
+    const float A = r0.z, B = r0.w, C = r1.x;
+    const float o255 = 255.0f * r1.y;
+    if (!(o255 >= 1.0f)) return false;
+    if (!(A > 0.f && C > 0.f)) return true;
+    const float tau2 = 2.0f * __logf(o255);
+    const float dxl = r0.x - x1, dxh = r0.x - x0, dyl = r0.y - y1, dyh = r0.y - y0;
+    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;
+    const float nbc = -B / C, nba = -B / A;
+    float q = 3.0e38f;
+    {
+        const float c = dxl, d = fminf(dyh, fmaxf(dyl, nbc * c));
+        q = fminf(q, A * c * c + 2.f * B * c * d + C * d * d);
+    }
+    {
+        const float c = dxh, d = fminf(dyh, fmaxf(dyl, nbc * c));
+        q = fminf(q, A * c * c + 2.f * B * c * d + C * d * d);
+    }
+    {
+        const float c = dyl, d = fminf(dxh, fmaxf(dxl, nba * c));
+        q = fminf(q, A * d * d + 2.f * B * d * c + C * c * c);
+    }
+    {
+        const float c = dyh, d = fminf(dxh, fmaxf(dxl, nba * c));
+        q = fminf(q, A * d * d + 2.f * B * d * c + C * c * c);
+    }
+    return q <= tau2 * 1.001f + 1e-3f;
+}
+#endif
+
 // kmeans (kmeans.cu)
 int launch_kmeans_assign(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b,
                          const float* centers, int k, const int64_t* select_ids, int64_t selected, int64_t id_offset,

@@ -19,14 +19,56 @@ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
                                  0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                  -0.5900435899266435f};
 
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a) {
+// STAGE_SH: the block's SH slab (visible rows only) is loaded with coalesced 16-byte loads into a
+// padded shared-memory layout, each thread overwrites its row in place with dL/dsh, and the slab
+// is written back coalesced -- instead of 48 strided 4-byte accesses per thread in each direction.
+template <bool STAGE_SH>
+__device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, int i, float* s_row, bool vis);
+
+template <bool STAGE_SH>
+__global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(PreprocessBwdArgs a) {
+    extern __shared__ float s_sh[];
+    __shared__ uint8_t s_vis[256];
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.P) return;
+    const bool active = i < a.P;
+    bool vis = false;
+    if (active) vis = __float_as_int(a.g.rec1[i].w) > 0;
+    const int per = a.M * 3;
+    if (STAGE_SH) {
+        s_vis[threadIdx.x] = vis;
+        __syncthreads();
+        const size_t base = (size_t)blockIdx.x * 256 * per;
+        const float4* src = reinterpret_cast<const float4*>(a.shs + base);
+        for (int e = threadIdx.x; e < 64 * per; e += 256) {     // 256 * per / 4 float4 (per % 4 == 0)
+            const int f = e * 4;
+            const int gi = f / per, k = f - gi * per;
+            if (s_vis[gi]) {
+                const float4 v = __ldg(src + e);
+                float* d = s_sh + gi * (per + 1) + k;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+        __syncthreads();
+    }
+    if (active) preprocess_bwd_body<STAGE_SH>(a, i, STAGE_SH ? s_sh + threadIdx.x * (per + 1) : nullptr, vis);
+    if (STAGE_SH && a.dL_dshs) {
+        __syncthreads();
+        const size_t base = (size_t)blockIdx.x * 256 * per;
+        float4* dst = reinterpret_cast<float4*>(a.dL_dshs + base);
+        const int rows = min(256, a.P - blockIdx.x * 256);
+        for (int e = threadIdx.x; e < rows * per / 4; e += 256) {
+            const int f = e * 4;
+            const int gi = f / per, k = f - gi * per;
+            const float* d = s_sh + gi * (per + 1) + k;
+            dst[e] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    }
+}
+
+template <bool STAGE_SH>
+__device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, int i, float* s_row, bool vis) {
     const int C = a.C;
     const float* acc = a.acc + (size_t)i * a.stride;
-    const float4 r1 = a.g.rec1[i];
-    const int radius = __float_as_int(r1.w);
-    const bool vis = radius > 0;
 
     // colour / feature gradients pass straight through
     if (a.dL_dcolors_precomp) {
@@ -165,8 +207,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 
         // ---- SH backward ----
         if (a.shs) {
-            const float* sh = a.shs + (size_t)i * M * 3;
-            float* dsh = a.dL_dshs ? a.dL_dshs + (size_t)i * M * 3 : nullptr;
+            const float* sh = STAGE_SH ? s_row : a.shs + (size_t)i * M * 3;
+            float* dsh = STAGE_SH ? s_row : (a.dL_dshs ? a.dL_dshs + (size_t)i * M * 3 : nullptr);
             const float d0 = m0 - a.campos[0], d1 = m1 - a.campos[1], d2 = m2 - a.campos[2];
             const float len = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
             const float x = d0 / len, y = d1 / len, z = d2 / len;
@@ -180,8 +222,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                 float sx = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
+                    sx += sh[k * 3 + ch] * dRGB[ch];        // read before the in-place overwrite
                     if (dsh) dsh[k * 3 + ch] = basis * dRGB[ch];
-                    sx += sh[k * 3 + ch] * dRGB[ch];
                 }
                 ddx += bx * sx; ddy += by * sx; ddz += bz * sx;
             };
@@ -244,8 +286,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
             drot[2] = 2.f * (-2.f * y * dR[0][0] + x * dR[0][1] + r * dR[0][2] + x * dR[1][0] + z * dR[1][2] - r * dR[2][0] + z * dR[2][1] - 2.f * y * dR[2][2]);
             drot[3] = 2.f * (-2.f * z * dR[0][0] - r * dR[0][1] + x * dR[0][2] + r * dR[1][0] - 2.f * z * dR[1][1] + y * dR[1][2] + x * dR[2][0] + y * dR[2][1]);
         }
-    } else if (a.shs && a.dL_dshs) {
-        float* dsh = a.dL_dshs + (size_t)i * M * 3;
+    } else if (a.shs && (STAGE_SH || a.dL_dshs)) {
+        float* dsh = STAGE_SH ? s_row : a.dL_dshs + (size_t)i * M * 3;
         for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
     }
 
@@ -275,7 +317,18 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 
 int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
     if (a.P <= 0) return 0;
-    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    const int per = a.M * 3;
+    const size_t smem = (size_t)256 * (per + 1) * sizeof(float);
+    if (a.geom && a.shs && (per % 4) == 0 && smem <= 100 * 1024) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attr_done = true;
+        }
+        preprocess_bwd_kernel<true><<<(a.P + 255) / 256, 256, smem, s>>>(a);
+    } else {
+        preprocess_bwd_kernel<false><<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    }
     return 0;
 }
 

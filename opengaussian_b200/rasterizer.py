@@ -53,18 +53,28 @@ def _none_if_empty(t):
 
 
 class _Alloc:
-    """Allocation callback handed to the C ABI; keeps the torch buffers alive for backward."""
+    """Allocation callback handed to the C ABI.  ONE process-wide ctypes thunk is created; each
+    forward installs a fresh dict that receives the torch buffers (kept alive by the autograd ctx).
+    No per-call ctypes objects and no reference cycles: buffers are released by refcount as soon as
+    the graph dies (a cycle here would park ~100 MB per frame until the cyclic GC runs and force
+    the caching allocator into cudaMalloc on every step)."""
+    _current = None
+    _device = None
+
+    @staticmethod
+    def _cb(_user, nbytes, tag):
+        t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_Alloc._device)
+        _Alloc._current[tag.decode()] = t
+        return t.data_ptr()
 
     def __init__(self, device):
-        self.device = device
         self.bufs = {}
+        _Alloc._current = self.bufs
+        _Alloc._device = device
+        self.fn = _ALLOC_THUNK
 
-        def cb(_user, nbytes, tag):
-            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
-            self.bufs[tag.decode()] = t
-            return t.data_ptr()
 
-        self.fn = _lib.ALLOC_FN(cb)
+_ALLOC_THUNK = _lib.ALLOC_FN(_Alloc._cb)
 
 
 def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities, shs, colors_precomp, scales,

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--P", type=int, default=None)
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--feat_only", type=int, default=0)
+    ap.add_argument("--sync", type=int, default=1)
     a = ap.parse_args()
     gs, cams = synth.make_scene(a.scene, n_views=4, P=a.P)
     dev = "cuda"
@@ -42,21 +43,35 @@ def main():
         rast = GaussianRasterizer(rs)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         tf = tb = 0.0
+        hf = hb = 0.0
+        t_all0 = None
         for it in range(a.iters + 3):
             for t in list(leaves.values()) + [m2] + ([extra] if extra is not None else []):
                 t.grad = None
+            if it == 3:
+                torch.cuda.synchronize(); t_all0 = time.perf_counter()
             ev[0].record()
+            h0 = time.perf_counter()
             out = rast(means2D=m2, extra_feats=extra, **leaves)
+            h1 = time.perf_counter()
             loss = (out[0] * gc).sum() + (out[2] * gd).sum() + (out[3] * ga).sum()
             if a.fused:
                 loss = loss + (out[4] * gf).sum()
             ev[1].record()
+            h2 = time.perf_counter()
             loss.backward()
+            h3 = time.perf_counter()
             ev[2].record()
-            torch.cuda.synchronize()
+            if a.sync:
+                torch.cuda.synchronize()
             if it >= 3:
+                hf += h1 - h0; hb += h3 - h2
+            if it >= 3 and a.sync:
                 tf += ev[0].elapsed_time(ev[1])
                 tb += ev[1].elapsed_time(ev[2])
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t_all0) / a.iters * 1e3
+        print(f"  host: fwd call {hf / a.iters * 1e3:.3f} ms, bwd call {hb / a.iters * 1e3:.3f} ms, wall/step {wall:.3f} ms")
         N = out[0].grad_fn.num_rendered if hasattr(out[0].grad_fn, "num_rendered") else -1
         vis = int((out[1] > 0).sum())
         print(f"view {vi}: P={P} vis={vis} N={N} {W}x{H} fwd {tf / a.iters:.3f} ms  bwd {tb / a.iters:.3f} ms  "
