@@ -8,10 +8,15 @@
 //  * the "colour behind" recursion is carried as ONE scalar per pixel: with d_i = <c_i, g> (dot of
 //    the Gaussian's channel vector incl. depth and 1 with the pixel's incoming gradients),
 //    S <- a_prev d_prev + (1 - a_prev) S and dL/dalpha = (d_i - S) T -- C-independent state;
-//  * per (warp, Gaussian) the 32 pixels' contributions are summed with a recursive-halving
+//  * 128 threads per 16x16 tile, warp = 8x8 pixel block, TWO pixels per lane: the two pixels'
+//    contributions are added in registers first, so the cross-lane reduction, the shared-memory
+//    reads and the culling test are amortised over 64 pixels;
+//  * per (warp, Gaussian) the lanes' contributions are summed with a recursive-halving
 //    (transpose) reduction: V values cost ~V + 5 shuffles instead of 5 V;
+//  * warp-level culling (ogs_rect_hit): lane l tests Gaussian l of a 32-group against the warp's
+//    block; only ballot survivors are evaluated;
 //  * each warp accumulates into its own shared-memory rows (no shared atomics); once per batch of
-//    64 Gaussians the 8 warp rows are summed and ONE red.global.add per value per (tile, Gaussian)
+//    64 Gaussians the 4 warp rows are summed and ONE red.global.add per value per (tile, Gaussian)
 //    is issued, skipping zeros;
 //  * GEOM=false specialisation (OpenGaussian stages 1-2 detach geometry, train.py:431-436): only
 //    w = alpha T and dL/dc are evaluated.
@@ -19,7 +24,9 @@
 
 namespace ogs {
 
-#define BB 64   // Gaussians per backward batch
+#define BB 64            // Gaussians per backward batch
+#define BWD_THREADS 128
+#define BWD_WARPS 4
 
 template <int CUR, int M>
 struct HalvingReduce {
@@ -49,12 +56,53 @@ constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v / 2); }
 
 int blend_bwd_stride(int C, int geom) { return geom ? C + 7 : C; }
 
+template <int C>
+struct PixelState {
+    float T, T_final, S, last_dot, last_alpha, gd, ga, bg_dot, pyf;
+    float g[C];
+    int last;
+};
+
+template <int C, bool GEOM, int VP>
+__device__ __forceinline__ void pixel_contrib(PixelState<C>& p, bool ok, float alpha, float G, float dx, float dy,
+                                              const float4& r0, const float4& r1, const float* __restrict__ col,
+                                              float half_w, float half_h, float (&v)[VP]) {
+    if (!ok) return;
+    const float inv = __fdividef(1.0f, 1.0f - alpha);
+    p.T = p.T * inv;
+    const float w = alpha * p.T;
+#pragma unroll
+    for (int c = 0; c < C; c++) v[c] = fmaf(w, p.g[c], v[c]);
+    if (GEOM) {
+        float dot = fmaf(r1.z, p.gd, p.ga);
+#pragma unroll
+        for (int c = 0; c < C; c++) dot = fmaf(col[c], p.g[c], dot);
+        p.S = fmaf(p.last_alpha, p.last_dot, (1.0f - p.last_alpha) * p.S);
+        p.last_dot = dot;
+        p.last_alpha = alpha;
+        float dL_dalpha = (dot - p.S) * p.T;
+        dL_dalpha = fmaf(-p.T_final * inv, p.bg_dot, dL_dalpha);
+        const float dL_dG = r1.y * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+        const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+        v[C + 0] = fmaf(w, p.gd, v[C + 0]);
+        v[C + 1] = fmaf(dL_dG * dG_ddelx, half_w, v[C + 1]);
+        v[C + 2] = fmaf(dL_dG * dG_ddely, half_h, v[C + 2]);
+        const float hq = -0.5f * dL_dG;
+        v[C + 3] = fmaf(hq * gdx, dx, v[C + 3]);
+        v[C + 4] = fmaf(hq * gdx, dy, v[C + 4]);
+        v[C + 5] = fmaf(hq * gdy, dy, v[C + 5]);
+        v[C + 6] = fmaf(G, dL_dalpha, v[C + 6]);
+    }
+}
+
 template <int C, bool GEOM>
-__global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) {
     constexpr int V = GEOM ? C + 7 : C;
     constexpr int VP = next_pow2(V);
     constexpr int SHIFT = 5 - log2c(VP);  // lane >> SHIFT = value index held after the reduction
-    extern __shared__ float s_dyn[];      // [8][BB][V] per-warp accumulators
+    extern __shared__ float s_dyn[];      // [BWD_WARPS][BB][V] per-warp accumulators
     __shared__ float4 s_r0[BB];
     __shared__ float4 s_r1[BB];
     __shared__ float s_col[BB * C];
@@ -64,37 +112,42 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     const int gx = (a.W + 15) / 16;
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int py = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < a.W && py < a.H;
-    const float pxf = (float)px, pyf = (float)py;
+    const int bxi = blockIdx.x * 16 + (warp & 1) * 8, byi = blockIdx.y * 16 + (warp >> 1) * 8;
+    const int px = bxi + (lane & 7);
+    const float pxf = (float)px;
+    const float bx0 = (float)bxi, by0 = (float)byi;
     const size_t HW = (size_t)a.H * a.W;
-    const size_t pix = (size_t)py * a.W + px;
     const uint2 range = a.ranges[tile];
 
-    const int last = inside ? (int)a.n_contrib[pix] : 0;
-    const float T_final = inside ? a.final_T[pix] : 0.f;
-    float T = T_final;
-    float g[C];
-    float gd = 0.f, ga = 0.f, bg_dot = 0.f;
+    PixelState<C> ps[2];
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-        g[c] = inside ? __ldg(a.dL_dcolor + c * HW + pix) : 0.f;
-        if (GEOM) bg_dot = fmaf(__ldg(a.bg + c), g[c], bg_dot);
+    for (int k = 0; k < 2; k++) {
+        const int py = byi + (lane >> 3) + 4 * k;
+        const bool inside = px < a.W && py < a.H;
+        const size_t pix = (size_t)py * a.W + px;
+        PixelState<C>& p = ps[k];
+        p.pyf = (float)py;
+        p.last = inside ? (int)a.n_contrib[pix] : 0;
+        p.T_final = inside ? a.final_T[pix] : 0.f;
+        p.T = p.T_final;
+        p.S = 0.f; p.last_dot = 0.f; p.last_alpha = 0.f; p.gd = 0.f; p.ga = 0.f; p.bg_dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            p.g[c] = inside ? __ldg(a.dL_dcolor + c * HW + pix) : 0.f;
+            if (GEOM) p.bg_dot = fmaf(__ldg(a.bg + c), p.g[c], p.bg_dot);
+        }
+        if (GEOM) {
+            p.gd = (inside && a.dL_ddepth) ? __ldg(a.dL_ddepth + pix) : 0.f;
+            p.ga = (inside && a.dL_dalpha) ? __ldg(a.dL_dalpha + pix) : 0.f;
+        }
     }
-    if (GEOM) {
-        gd = (inside && a.dL_ddepth) ? __ldg(a.dL_ddepth + pix) : 0.f;
-        ga = (inside && a.dL_dalpha) ? __ldg(a.dL_dalpha + pix) : 0.f;
-    }
-    float S = 0.f, last_dot = 0.f, last_alpha = 0.f;
     const float half_w = 0.5f * (float)a.W, half_h = 0.5f * (float)a.H;
-    const float bx0 = (float)(blockIdx.x * 16 + (warp & 1) * 8), by0 = (float)(blockIdx.y * 16 + (warp >> 1) * 4);
 
     // block / warp maxima of the last contributor
     if (threadIdx.x == 0) s_max_last = 0;
-    for (int e = threadIdx.x; e < 8 * BB * V; e += 256) s_dyn[e] = 0.f;
+    for (int e = threadIdx.x; e < BWD_WARPS * BB * V; e += BWD_THREADS) s_dyn[e] = 0.f;
     __syncthreads();
-    int wmax = last;
+    int wmax = max(ps[0].last, ps[1].last);
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, m));
     if (lane == 0 && wmax > 0) atomicMax(&s_max_last, wmax);
@@ -113,7 +166,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
             s_r0[threadIdx.x] = __ldg(a.rec0 + gid);
             s_r1[threadIdx.x] = __ldg(a.rec1 + gid);
         }
-        for (int e = threadIdx.x; e < n * C; e += 256) {
+        for (int e = threadIdx.x; e < n * C; e += BWD_THREADS) {
             const int j = e / C, c = e - j * C;
             const uint32_t gid = a.point_list[range.x + start + j];
             s_col[e] = (c < 3) ? __ldg(a.base + 3 * (size_t)gid + c) : __ldg(a.extra + (size_t)(C - 3) * gid + (c - 3));
@@ -121,69 +174,46 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
         __syncthreads();
         // ---- traverse back to front ----
         if (start < wmax) {
-          const int nw = min(n, wmax - start);
-          for (int grp = ((nw - 1) >> 5) << 5; grp >= 0; grp -= 32) {
-            // warp-level culling (see blend_fwd.cu): lane l tests entry grp+l against the warp's 8x4 block
-            const int idx = grp + lane;
-            bool hit = false;
-            if (idx < nw) hit = ogs_rect_hit(s_r0[idx], s_r1[idx], bx0, by0, bx0 + 7.0f, by0 + 3.0f);
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int bit = 31 - __clz(mask);
-                mask &= ~(1u << bit);
-                const int j = grp + bit;
-                const int pos = start + j;
-                const float4 r0 = s_r0[j];
-                const float4 r1 = s_r1[j];
-                const float dx = r0.x - pxf, dy = r0.y - pyf;
-                const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
-                const float G = __expf(power);
-                const float alpha = fminf(0.99f, r1.y * G);
-                const bool ok = pos < last && power <= 0.0f && alpha >= (1.0f / 255.0f);
-                if (!__any_sync(0xffffffffu, ok)) continue;
-                float v[VP];
+            const int nw = min(n, wmax - start);
+            for (int grp = ((nw - 1) >> 5) << 5; grp >= 0; grp -= 32) {
+                const int idx = grp + lane;
+                bool hit = false;
+                if (idx < nw) hit = ogs_rect_hit(s_r0[idx], s_r1[idx], bx0, by0, bx0 + 7.0f, by0 + 7.0f);
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int bit = 31 - __clz(mask);
+                    mask &= ~(1u << bit);
+                    const int j = grp + bit;
+                    const int pos = start + j;
+                    const float4 r0 = s_r0[j];
+                    const float4 r1 = s_r1[j];
+                    const float dx = r0.x - pxf;
+                    const float dy0 = r0.y - ps[0].pyf, dy1 = r0.y - ps[1].pyf;
+                    const float adx = __fmul_rn(__fmul_rn(r0.z, dx), dx), bdx = __fmul_rn(r0.w, dx);
+                    const float pw0 = ogs_power(adx, bdx, r1.x, dy0);
+                    const float pw1 = ogs_power(adx, bdx, r1.x, dy1);
+                    const float G0 = __expf(pw0), G1 = __expf(pw1);
+                    const float al0 = fminf(0.99f, r1.y * G0), al1 = fminf(0.99f, r1.y * G1);
+                    const bool ok0 = pos < ps[0].last && pw0 <= 0.0f && al0 >= (1.0f / 255.0f);
+                    const bool ok1 = pos < ps[1].last && pw1 <= 0.0f && al1 >= (1.0f / 255.0f);
+                    if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+                    float v[VP];
 #pragma unroll
-                for (int k = 0; k < VP; k++) v[k] = 0.f;
-                if (ok) {
-                    const float inv = __fdividef(1.0f, 1.0f - alpha);
-                    T = T * inv;
-                    const float w = alpha * T;
-#pragma unroll
-                    for (int c = 0; c < C; c++) v[c] = w * g[c];
-                    if (GEOM) {
-                        float dot = fmaf(r1.z, gd, ga);
-#pragma unroll
-                        for (int c = 0; c < C; c++) dot = fmaf(s_col[j * C + c], g[c], dot);
-                        S = fmaf(last_alpha, last_dot, (1.0f - last_alpha) * S);
-                        last_dot = dot;
-                        last_alpha = alpha;
-                        float dL_dalpha = (dot - S) * T;
-                        dL_dalpha = fmaf(-T_final * inv, bg_dot, dL_dalpha);
-                        const float dL_dG = r1.y * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-                        const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-                        v[C + 0] = w * gd;
-                        v[C + 1] = dL_dG * dG_ddelx * half_w;
-                        v[C + 2] = dL_dG * dG_ddely * half_h;
-                        v[C + 3] = -0.5f * gdx * dx * dL_dG;
-                        v[C + 4] = -0.5f * gdx * dy * dL_dG;
-                        v[C + 5] = -0.5f * gdy * dy * dL_dG;
-                        v[C + 6] = G * dL_dalpha;
-                    }
+                    for (int k = 0; k < VP; k++) v[k] = 0.f;
+                    pixel_contrib<C, GEOM, VP>(ps[0], ok0, al0, G0, dx, dy0, r0, r1, s_col + j * C, half_w, half_h, v);
+                    pixel_contrib<C, GEOM, VP>(ps[1], ok1, al1, G1, dx, dy1, r0, r1, s_col + j * C, half_w, half_h, v);
+                    HalvingReduce<VP, 16>::run(v, lane);
+                    const int k = lane >> SHIFT;
+                    if ((lane & ((1 << SHIFT) - 1)) == 0 && k < V) my_acc[j * V + k] += v[0];
                 }
-                HalvingReduce<VP, 16>::run(v, lane);
-                const int k = lane >> SHIFT;
-                if ((lane & ((1 << SHIFT) - 1)) == 0 && k < V) my_acc[j * V + k] += v[0];
             }
-          }
         }
         __syncthreads();
-        // ---- flush: sum the 8 warp rows, one red per value per (tile, Gaussian) ----
-        for (int e = threadIdx.x; e < n * V; e += 256) {
+        // ---- flush: sum the warp rows, one red per value per (tile, Gaussian) ----
+        for (int e = threadIdx.x; e < n * V; e += BWD_THREADS) {
             float sum = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < 8; w8++) {
+            for (int w8 = 0; w8 < BWD_WARPS; w8++) {
                 sum += s_dyn[(size_t)w8 * BB * V + e];
                 s_dyn[(size_t)w8 * BB * V + e] = 0.f;
             }
@@ -199,14 +229,9 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
 template <int C, bool GEOM>
 static int launch_cg(const BlendBwdArgs& a, cudaStream_t s) {
     constexpr int V = GEOM ? C + 7 : C;
-    const size_t smem = (size_t)8 * BB * V * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_done = true;
-    }
+    const size_t smem = (size_t)BWD_WARPS * BB * V * sizeof(float);
     dim3 grid((a.W + 15) / 16, (a.H + 15) / 16);
-    blend_bwd_kernel<C, GEOM><<<grid, 256, smem, s>>>(a);
+    blend_bwd_kernel<C, GEOM><<<grid, BWD_THREADS, smem, s>>>(a);
     return 0;
 }
 

@@ -201,6 +201,14 @@ __device__ __forceinline__ bool ogs_rect_hit(const float4 r0, const float4 r1, f
     }
     return q <= tau2 * 1.001f + 1e-3f;
 }
+
+// Gaussian exponent at one pixel, with the rounding sequence pinned by explicit intrinsics so that
+// the forward and backward kernels take identical skip / contribute decisions:
+//   adx = (A dx) dx, bdx = B dx  (shared by the pixels of a column), power = -(B dx) dy - 0.5 (adx + (C dy) dy).
+__device__ __forceinline__ float ogs_power(float adx, float bdx, float Cc, float dy) {
+    const float q = __fmaf_rn(__fmul_rn(Cc, dy), dy, adx);
+    return __fmaf_rn(-bdx, dy, __fmul_rn(-0.5f, q));
+}
 #endif
 
 // kmeans (kmeans.cu)
