@@ -95,6 +95,11 @@ class Quantize_kMeans():
         self.max_cnt_th = 10000
         self._eq_cache = None                       # lazily built equalize_cluster_size products
         self._eq_mode = "root"
+        # multi-GPU: points sharded over ranks, centres replicated; ONE
+        # all-reduce of the packed [k*D sums | k counts] buffer per Lloyd iteration.  Set by
+        # opengaussian_b200.dist.shard_kmeans(); None = single process (the reference's behaviour).
+        self.process_group = None
+        self.distributed = False
         self.pos_centers = torch.empty(0)
 
     # ------------------------------------------------------------------ lazily materialised lists
@@ -181,15 +186,29 @@ class Quantize_kMeans():
             r = a[idx]
             return r if b is None else torch.cat([r, b[idx] * scale_b], 1)
 
+        dist_on = self.distributed
+        if dist_on:
+            import torch.distributed as dist
+            n_glob = torch.tensor([N], dtype=torch.int64, device=dev)
+            dist.all_reduce(n_glob, group=self.process_group)
+            N_global = int(n_glob)
+        else:
+            N_global = N
         if len(self.centers) == 0 and mode == "root":
             self.centers = rows(torch.randperm(N)[:k1].to(dev)).float()
+            if dist_on:          # rank 0's draw wins
+                dist.broadcast(self.centers, src=dist.get_global_rank(self.process_group, 0)
+                               if self.process_group is not None else 0, group=self.process_group)
         if len(self.leaf_centers) == 0 and mode == "leaf":
             self.leaf_centers = rows(torch.randperm(N)[:k1 * k2 + 1].to(dev)).float()
+            if dist_on:
+                dist.broadcast(self.leaf_centers, src=dist.get_global_rank(self.process_group, 0)
+                               if self.process_group is not None else 0, group=self.process_group)
             self.leaf_cls_ids = torch.ones(N, device=dev).to(torch.int64) * k1 * k2
 
         if mode == "root":
             k = k1
-            n_eps = N // CHUNK + 1                 # chunks visited per pass (strict '>' break, :193)
+            n_eps = N_global // CHUNK + 1          # chunks visited per pass (strict '>' break, :193)
             centers = self.centers.detach().float().contiguous().to(dev)
             select, selected, id_offset = None, -1, 0
             ids = torch.empty(N, dtype=torch.int64, device=dev)
@@ -204,18 +223,20 @@ class Quantize_kMeans():
         else:
             raise ValueError(mode)
 
-        sums = torch.zeros(k, D, dtype=torch.float32, device=dev)
-        cnt = torch.zeros(k, dtype=torch.float32, device=dev)
+        buf = torch.zeros(k * D + k, dtype=torch.float32, device=dev)   # [sums | counts]: one collective
+        sums = buf[:k * D].view(k, D)
+        cnt = buf[k * D:]
         counts_state = torch.full((k,), 1e-6, dtype=torch.float32, device=dev)
         for _ in range(self.num_kmeans_iters):
-            sums.zero_()
-            cnt.zero_()
+            buf.zero_()
             if mode == "root":
                 kmeans_assign(a, b, scale_b, centers, None, -1, 0, ids, sums, cnt)
             else:
                 cur = self.leaf_centers[start_id:start_id + n_sub]
                 # sums/counts rows beyond n_sub stay zero -> those centres become 0 / eps = 0 (:211)
                 kmeans_assign(a, b, scale_b, cur, select, selected, id_offset, ids, sums[:n_sub], cnt[:n_sub])
+            if dist_on:
+                dist.all_reduce(buf, group=self.process_group)
             counts_state += cnt + n_eps * 1e-6
             new_centers = sums / counts_state.unsqueeze(-1)
             if mode == "root":

@@ -109,7 +109,7 @@ def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities,
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra,
-                raster_settings):
+                raster_settings, extra_bg=None):
         L = _lib.lib()
         rs = raster_settings
         dev = means3D.device
@@ -135,7 +135,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                 extra = torch.cat([extra, extra.new_zeros(P, c_tot - 3 - n_extra_user)], 1).contiguous()
                 n_extra = c_tot - 3
         bg = _f32c(rs.bg).reshape(-1)
-        bg_full = bg if n_extra == 0 else torch.cat([bg, bg.new_zeros(n_extra)])
+        if n_extra == 0:
+            bg_full = bg
+        elif extra_bg is None:
+            bg_full = torch.cat([bg, bg.new_zeros(n_extra)])
+        else:
+            eb = _f32c(extra_bg).reshape(-1).to(dev)
+            bg_full = torch.cat([bg, eb, bg.new_zeros(n_extra - eb.numel())])
         rs = rs._replace(viewmatrix=_f32c(rs.viewmatrix), projmatrix=_f32c(rs.projmatrix), campos=_f32c(rs.campos))
 
         color_all = torch.empty(3 + n_extra, H, W, dtype=torch.float32, device=dev)
@@ -209,13 +215,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         _lib.check(rc, "ogs_raster_backward")
         if g_extra is not None and n_extra != ctx.n_extra_user:
             g_extra = g_extra[:, :ctx.n_extra_user].contiguous()
-        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, g_extra, None
+        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, g_extra, None, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, extra_feats=None):
+                        raster_settings, extra_feats=None, extra_bg=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, extra_feats, raster_settings)
+                                     cov3Ds_precomp, extra_feats, raster_settings, extra_bg)
 
 
 class GaussianRasterizer(nn.Module):
@@ -237,7 +243,11 @@ class GaussianRasterizer(nn.Module):
         return out.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, extra_feats=None):
+                cov3D_precomp=None, extra_feats=None, extra_bg=None):
+        """Reference signature (gaussian_renderer/__init__.py:104-112) + ``extra_feats [P,F]`` /
+        ``extra_bg [F]``: F extra channels composited in the same pass (background ``extra_bg``,
+        default 0).  Returns ``(color, radii, depth, alpha)`` or, with extra_feats, a fifth
+        ``feats [F,H,W]``."""
         rs = self.raster_settings
         if means3D.shape[0] > 0:     # upstream passes torch.Tensor([]) for "not given"
             shs, colors_precomp = _none_if_empty(shs), _none_if_empty(colors_precomp)
@@ -248,7 +258,8 @@ class GaussianRasterizer(nn.Module):
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         color_all, radii, depth, alpha = rasterize_gaussians(
-            means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs, extra_feats)
+            means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs, extra_feats,
+            extra_bg)
         if extra_feats is None:
             return color_all, radii, depth, alpha
         return color_all[:3], radii, depth, alpha, color_all[3:]

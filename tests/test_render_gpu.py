@@ -1,0 +1,157 @@
+"""render() drop-in (opengaussian_b200.renderer) on the GPU: the fused pass structure must give the
+same dict as the reference's literal pass structure (fused=False reproduces
+gaussian_renderer/__init__.py:104-163,203-225,327-345 pass by pass on the same rasterizer)."""
+import math
+import types
+
+import pytest
+import torch
+
+from opengaussian_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["render", "alpha", "depth", "silhouette", "ins_feat", "cluster_imgs", "cluster_silhouettes",
+        "leaf_clusters_imgs", "leaf_cluster_silhouettes", "occured_leaf_id", "cluster_occur", "viewspace_points",
+        "visibility_filter", "radii"]
+
+
+class FakeGaussians:
+    """The getters render() consumes (scene/gaussian_model.py:122-175)."""
+
+    def __init__(self, gs, dev, feat_grad=True, geom_grad=False):
+        self._xyz = gs["means3D"].to(dev).requires_grad_(geom_grad)
+        self._scaling = torch.log(gs["scales"]).to(dev).requires_grad_(geom_grad)
+        self._rotation = gs["rotations"].to(dev).requires_grad_(geom_grad)
+        self._opacity = torch.logit(gs["opacities"].clamp(1e-4, 1 - 1e-4)).to(dev).requires_grad_(geom_grad)
+        self._features = gs["shs"].to(dev).requires_grad_(geom_grad)
+        self._ins_feat = (gs["ins_feat"] * 2 - 1).to(dev).requires_grad_(feat_grad)
+        self._ins_feat_q = None
+        self.active_sh_degree = 3
+        self.max_sh_degree = 3
+
+    get_xyz = property(lambda s: s._xyz)
+    get_scaling = property(lambda s: torch.exp(s._scaling))
+    get_rotation = property(lambda s: torch.nn.functional.normalize(s._rotation))
+    get_opacity = property(lambda s: torch.sigmoid(s._opacity))
+    get_features = property(lambda s: s._features)
+
+    def get_ins_feat(self, origin=False):
+        f = self._ins_feat if (origin or self._ins_feat_q is None) else self._ins_feat_q
+        return torch.nn.functional.normalize(f, dim=1)
+
+
+def _cam(c, dev):
+    cam = types.SimpleNamespace(FoVx=c.FoVx, FoVy=c.FoVy, image_height=c.image_height, image_width=c.image_width,
+                                world_view_transform=c.world_view_transform.to(dev),
+                                full_proj_transform=c.full_proj_transform.to(dev),
+                                camera_center=c.camera_center.to(dev), bClusterOccur=None)
+    return cam
+
+
+PIPE = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
+
+
+def _close(a, b, tol):
+    if a is None or b is None:
+        assert a is None and b is None
+        return
+    if isinstance(a, (list, tuple)):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            _close(x, y, tol)
+        return
+    if isinstance(a, torch.Tensor) and a.dtype.is_floating_point:
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= tol
+    elif isinstance(a, torch.Tensor):
+        assert torch.equal(a, b)
+    else:
+        assert a == b
+
+
+@pytest.mark.parametrize("rescale", [False, True])
+def test_stage1_fused_equals_reference_pass_structure(rescale):
+    from opengaussian_b200.renderer import render
+    dev = "cuda"
+    gs = synth.make_gaussians(6000, "blender", 0, scale_mult=1.2)
+    cam = _cam(synth.orbit_cameras(3, 4.0, 160, 120, 0.69, 1.0)[1], dev)
+    bg = torch.tensor([0.2, 0.5, 0.8], device=dev)
+    outs, grads = [], []
+    for fused in (True, False):
+        pc = FakeGaussians(gs, dev)
+        torch.manual_seed(3 if rescale else 0)        # same CPU RNG draws for the rescale factor
+        pkg = render(cam, pc, PIPE, bg, 1, rescale=rescale, fused=fused)
+        assert list(pkg.keys()) == KEYS
+        loss = (pkg["ins_feat"] * torch.linspace(0, 1, 6, device=dev)[:, None, None]).sum() + pkg["render"].sum()
+        loss.backward()
+        outs.append(pkg)
+        grads.append(pc._ins_feat.grad.clone())
+    for k in KEYS:
+        if k == "viewspace_points":
+            continue
+        _close(outs[0][k], outs[1][k], 2e-5)
+    assert outs[0]["ins_feat"].shape == (6, 120, 160) and outs[0]["silhouette"].shape == (1, 120, 160)
+    rel = float((grads[0] - grads[1]).abs().max() / grads[1].abs().max())
+    assert rel <= 1e-3
+
+
+def test_geometry_gradients_and_viewspace_points():
+    """Stage 0: all parameters train; viewspace_points.grad feeds densification (scene/gaussian_model.py:512-514)."""
+    from opengaussian_b200.renderer import render
+    dev = "cuda"
+    gs = synth.make_gaussians(4000, "blender", 1, scale_mult=1.2)
+    cam = _cam(synth.orbit_cameras(3, 4.0, 128, 96, 0.69, 1.0)[0], dev)
+    bg = torch.zeros(3, device=dev)
+    res = []
+    for fused in (True, False):
+        pc = FakeGaussians(gs, dev, geom_grad=True)
+        torch.manual_seed(0)
+        pkg = render(cam, pc, PIPE, bg, 1, rescale=False, fused=fused)
+        w = torch.linspace(0.5, 1.5, 6, device=dev)[:, None, None]
+        ((pkg["render"] ** 2).sum() + (pkg["ins_feat"] * w).sum()).backward()
+        res.append((pkg["viewspace_points"].grad.clone(), pc._xyz.grad.clone(), pc._opacity.grad.clone(),
+                    pc._features.grad.clone()))
+    for a, b in zip(*res):
+        assert float((a - b).abs().max() / (b.abs().max() + 1e-20)) <= 1e-3
+    assert float(res[0][0][:, :2].abs().max()) > 0 and float(res[0][0][:, 2].abs().max()) == 0
+
+
+def test_cluster_and_leaf_passes():
+    from opengaussian_b200.renderer import render
+    dev = "cuda"
+    P = 8000
+    gs = synth.make_gaussians(P, "blender", 2, scale_mult=1.5)
+    cam = _cam(synth.orbit_cameras(3, 4.0, 128, 128, 0.69, 1.0)[2], dev)
+    bg = torch.zeros(3, device=dev)
+    g = torch.Generator().manual_seed(0)
+    cluster_idx = torch.randint(0, 4, (P,), generator=g).to(dev)
+    leaf_idx = (cluster_idx * 3 + torch.randint(0, 3, (P,), generator=g).to(dev))
+    outs = []
+    for fused in (True, False):
+        pc = FakeGaussians(gs, dev)
+        torch.manual_seed(0)
+        pkg = render(cam, pc, PIPE, bg, 1, rescale=False, cluster_idx=cluster_idx, leaf_cluster_idx=leaf_idx,
+                     render_feat_map=False, render_cluster=True, selected_root_id=2, root_num=4, leaf_num=3,
+                     fused=fused)
+        outs.append(pkg)
+    a, b = outs
+    assert a["ins_feat"] is None and a["silhouette"] is None
+    assert len(a["cluster_imgs"]) == 1 and a["cluster_imgs"][0].shape == (6, 128, 128)
+    assert a["occured_leaf_id"] == [6, 7, 8] and a["leaf_cluster_silhouettes"].shape == (3, 128, 128)
+    assert a["cluster_occur"].tolist() == [False, False, True, False]
+    for k in KEYS:
+        if k != "viewspace_points":
+            _close(a[k], b[k], 2e-5)
+
+
+def test_alias_packages_import():
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    import ashawkey_diff_gaussian_rasterization as m1
+    import diff_gaussian_rasterization as m2
+    from opengaussian_b200 import rasterizer
+    assert m1.GaussianRasterizer is rasterizer.GaussianRasterizer is m2.GaussianRasterizer
+    assert math.isclose(1.0, 1.0)
