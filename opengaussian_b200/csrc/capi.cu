@@ -65,6 +65,8 @@ static int ensure_pool(void) {
     return 0;
 }
 
+static thread_local uint64_t g_cap_hint = 0;   // running estimate of num_rendered (+25 %), see ogs_raster_forward
+
 static uint32_t* pinned_scalar(void) {
     static thread_local uint32_t* p = nullptr;
     if (!p) {
@@ -194,7 +196,11 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     float* final_T = (float*)((char*)st->image + il.final_T);
     uint32_t* n_contrib = (uint32_t*)((char*)st->image + il.n_contrib);
 
-    int64_t N = 0;
+    int64_t N = 0, cap = 0;
+    bool speculative = false;
+    uint32_t* h = nullptr;
+    const uint32_t* n_ptr = nullptr;
+    cudaEvent_t n_event = nullptr;
     char* scratch1 = nullptr;
     BinScratch sc;
     memset(&sc, 0, sizeof sc);
@@ -225,49 +231,78 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         rc = depth_sort_and_scan(P, g, sc, s, in->debug);
         prof_end(PF_DEPTH_SORT_SCAN, s);
         if (rc) { cudaFreeAsync(scratch1, s); return rc; }
-        uint32_t* h = pinned_scalar();
+        h = pinned_scalar();
         if (!h) { cudaFreeAsync(scratch1, s); set_error("cudaMallocHost failed"); return 2; }
-        OGS_CUDA(cudaMemcpyAsync(h, sc.offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s));
-        OGS_CUDA(cudaStreamSynchronize(s));
+        n_ptr = sc.offsets + (P - 1);
+        OGS_CUDA(cudaMemcpyAsync(h, n_ptr, 4, cudaMemcpyDeviceToHost, s));
+        // Capacity speculation: the binning buffers are sized from the running estimate g_cap_hint and
+        // the N-dependent kernels take N from device memory, so emit/sort/blend are queued WITHOUT
+        // waiting for the scan; the host reads N only after everything is launched (the scan has long
+        // finished by then).  If the estimate was too small the binning + blend are redone (rare).
+        if (g_cap_hint == 0 || in->debug) {
+            OGS_CUDA(cudaStreamSynchronize(s));
+            N = (int64_t)*h;
+            cap = N;
+        } else {
+            static thread_local cudaEvent_t ev = nullptr;
+            if (!ev) OGS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            OGS_CUDA(cudaEventRecord(ev, s));
+            n_event = ev;
+            cap = (int64_t)g_cap_hint;
+            speculative = true;
+        }
+    }
+    uint32_t* point_list = nullptr;
+    uint2* ranges = nullptr;
+    for (;;) {
+        const BinLayout bl = BinLayout::make(cap, tiles);
+        st->binning = alloc(alloc_user, bl.total, "binning");
+        st->binning_bytes = (int64_t)bl.total;
+        if (!st->binning) { if (scratch1) cudaFreeAsync(scratch1, s); set_error("allocation callback returned NULL"); return -6; }
+        point_list = (uint32_t*)((char*)st->binning + bl.point_list);
+        ranges = (uint2*)((char*)st->binning + bl.ranges);
+        char* scratch2 = nullptr;
+        if (cap > 0 && P > 0) {
+            const size_t k2 = align_up((size_t)cap * 2, 256), v4 = align_up((size_t)cap * 4, 256);
+            const size_t tb = align_up(tile_sort_temp_bytes(cap), 256);
+            OGS_CUDA(cudaMallocAsync((void**)&scratch2, 2 * k2 + v4 + tb, s));
+            sc.cub_temp = scratch2 + 2 * k2 + v4;
+            sc.cub_temp_bytes = tb;
+            rc = emit_sort_ranges(P, W, H, n_ptr, cap, g, sc, (uint16_t*)scratch2, (uint32_t*)(scratch2 + 2 * k2),
+                                  (uint16_t*)(scratch2 + k2), point_list, ranges, s, in->debug);
+        } else {
+            cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "memset ranges");
+        }
+        if (scratch2) cudaFreeAsync(scratch2, s);
+        if (rc) { if (scratch1) cudaFreeAsync(scratch1, s); return rc; }
+
+        BlendFwdArgs ba;
+        ba.W = W; ba.H = H; ba.C = C;
+        ba.ranges = ranges; ba.point_list = point_list; ba.rec0 = g.rec0; ba.rec1 = g.rec1;
+        ba.base = has_sh ? g.rgb : in->colors_precomp;
+        ba.extra = in->extra; ba.bg = in->bg;
+        ba.out_color = out->color; ba.out_depth = out->depth; ba.out_alpha = out->alpha;
+        ba.final_T = final_T; ba.n_contrib = n_contrib;
+        prof_begin(PF_BLEND_FWD, s);
+        rc = launch_blend_forward(ba, s);
+        prof_end(PF_BLEND_FWD, s);
+        if (rc) { if (scratch1) cudaFreeAsync(scratch1, s); return rc; }
+        OGS_KERNEL_CHECK("blend_forward", in->debug, s);
+        if (!speculative) break;
+        OGS_CUDA(cudaEventSynchronize(n_event));
         N = (int64_t)*h;
+        speculative = false;
+        if (N <= cap) break;
+        cap = N;                       // estimate too small: redo binning + blend with the exact size
+    }
+    if (scratch1) cudaFreeAsync(scratch1, s);
+    if (P > 0) {
+        const uint64_t want = (uint64_t)N + (uint64_t)N / 4 + 65536;
+        const uint64_t decay = g_cap_hint - g_cap_hint / 32;
+        g_cap_hint = want > decay ? want : decay;
     }
     st->num_rendered = N;
-    const BinLayout bl = BinLayout::make(N, tiles);
-    st->binning = alloc(alloc_user, bl.total, "binning");
-    st->binning_bytes = (int64_t)bl.total;
-    if (!st->binning) { if (scratch1) cudaFreeAsync(scratch1, s); set_error("allocation callback returned NULL"); return -6; }
-    uint32_t* point_list = (uint32_t*)((char*)st->binning + bl.point_list);
-    uint2* ranges = (uint2*)((char*)st->binning + bl.ranges);
-
-    char* scratch2 = nullptr;
-    if (N > 0) {
-        const size_t k2 = align_up((size_t)N * 2, 256), v4 = align_up((size_t)N * 4, 256);
-        const size_t tb = align_up(tile_sort_temp_bytes(N), 256);
-        OGS_CUDA(cudaMallocAsync((void**)&scratch2, 2 * k2 + v4 + tb, s));
-        sc.cub_temp = scratch2 + 2 * k2 + v4;
-        sc.cub_temp_bytes = tb;
-        rc = emit_sort_ranges(P, W, H, N, g, sc, (uint16_t*)scratch2, (uint32_t*)(scratch2 + 2 * k2),
-                              (uint16_t*)(scratch2 + k2), point_list, ranges, s, in->debug);
-    } else {
-        cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "memset ranges");
-    }
-    if (scratch2) cudaFreeAsync(scratch2, s);
-    if (scratch1) cudaFreeAsync(scratch1, s);
-    if (rc) return rc;
-
-    BlendFwdArgs ba;
-    ba.W = W; ba.H = H; ba.C = C;
-    ba.ranges = ranges; ba.point_list = point_list; ba.rec0 = g.rec0; ba.rec1 = g.rec1;
-    ba.base = has_sh ? g.rgb : in->colors_precomp;
-    ba.extra = in->extra; ba.bg = in->bg;
-    ba.out_color = out->color; ba.out_depth = out->depth; ba.out_alpha = out->alpha;
-    ba.final_T = final_T; ba.n_contrib = n_contrib;
-    prof_begin(PF_BLEND_FWD, s);
-    rc = launch_blend_forward(ba, s);
-    prof_end(PF_BLEND_FWD, s);
-    if (rc) return rc;
-    OGS_KERNEL_CHECK("blend_forward", in->debug, s);
     return 0;
 }
 

@@ -79,9 +79,9 @@ struct BinLayout {
     size_t point_list, ranges, total;
     __host__ static BinLayout make(int64_t N, int tiles) {
         BinLayout b;
-        size_t o = 0;
-        b.point_list = o; o = align_up(o + (size_t)(N > 0 ? N : 1) * 4, 256);
+        size_t o = 0;   // ranges first: their offset must not depend on the (speculative) capacity
         b.ranges = o; o = align_up(o + (size_t)tiles * 8, 256);
+        b.point_list = o; o = align_up(o + (size_t)(N > 0 ? N : 1) * 4, 256);
         b.total = o;
         return b;
     }
@@ -121,8 +121,8 @@ struct BinScratch {
 };
 size_t binning_temp_bytes(int P, int64_t N_cap);
 int depth_sort_and_scan(int P, const GeomPtrs& g, BinScratch& sc, cudaStream_t s, int debug);
-int emit_sort_ranges(int P, int W, int H, int64_t N, const GeomPtrs& g, BinScratch& sc,
-                     uint16_t* tkeys_in, uint32_t* tvals_in, uint16_t* tkeys_out,
+int emit_sort_ranges(int P, int W, int H, const uint32_t* n_ptr, int64_t cap, const GeomPtrs& g, BinScratch& sc,
+                     uint16_t* tkeys_a, uint32_t* tvals_a, uint16_t* tkeys_b,
                      uint32_t* point_list, uint2* ranges, cudaStream_t s, int debug);
 size_t tile_sort_temp_bytes(int64_t N);
 size_t depth_sort_temp_bytes(int P);

@@ -1,0 +1,339 @@
+// radix.cu -- hand-written stable LSD radix sort (pairs) and inclusive scan for the binning stage.
+//
+// Replaces the cub::DeviceRadixSort::SortPairs / cub::DeviceScan::InclusiveSum calls of the
+// upstream rasterizer for the two sorts of binning.cu:
+//   * depth sort: P items, 32-bit keys (depth bits), 32-bit values (Gaussian index), 4 digit passes;
+//   * tile sort : N items, 16-bit keys (tile id), 32-bit values, 2 digit passes (<= 13 key bits).
+// Design (one kernel per digit pass, each key/value read once and written once -- HBM-bound):
+//   1. rs_hist_kernel: digit histograms of ALL passes in one sweep over the keys;
+//   2. rs_pass_kernel ("onesweep"): a CTA takes a 4096-item tile through a ticket counter (so that
+//      tile t only ever waits on tiles < t that have already started), ranks its keys stably
+//      (__match_any_sync peer groups + per-warp digit counters), publishes its digit counts and
+//      resolves its global digit offsets by decoupled look-back over the preceding tiles' published
+//      (aggregate | inclusive) words, reorders keys/values by local rank in shared memory and writes
+//      each digit run with coalesced stores.
+// The item count is read from DEVICE memory (n_ptr): the grid is sized for a capacity and CTAs
+// past the end exit, which is what lets ogs_raster_forward run without a host round trip.
+#include "common.cuh"
+
+namespace ogs {
+
+#define RS_THREADS 256
+#define RS_WARPS 8
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)   // 4096
+#define RS_RADIX 256
+#define RS_FLAG_AGG 0x40000000u
+#define RS_FLAG_INC 0x80000000u
+#define RS_VAL_MASK 0x3FFFFFFFu
+#define RS_LB 8
+
+struct RsPasses {
+    int num;
+    int shift[4];
+    int bits[4];
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
+                                                             uint32_t cap, RsPasses ps, uint32_t* __restrict__ ghist /*[num][256]*/) {
+    __shared__ uint32_t s_h[4 * RS_RADIX];
+    for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS) s_h[e] = 0;
+    __syncthreads();
+    const uint32_t n = min(*n_ptr, cap);
+    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) {
+        const uint32_t k = (uint32_t)keys[i];
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+            if (p < ps.num) atomicAdd(&s_h[p * RS_RADIX + ((k >> ps.shift[p]) & ((1u << ps.bits[p]) - 1u))], 1u);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS)
+        if (s_h[e]) atomicAdd(&ghist[e], s_h[e]);
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS, 4) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
+                                                             const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
+                                                             const uint32_t* __restrict__ n_ptr, uint32_t cap, int shift, int bits,
+                                                             const uint32_t* __restrict__ ghist /*[256] of this pass*/,
+                                                             uint32_t* tile_state /*[tiles][256]*/, uint32_t* ticket) {
+    __shared__ uint32_t s_wh[RS_WARPS * RS_RADIX];   // per-warp digit counters -> exclusive warp offsets
+    __shared__ uint32_t s_dstart[RS_RADIX];          // local exclusive start of each digit in the tile
+    __shared__ uint32_t s_gbase[RS_RADIX];           // global position of local sorted slot 0 of the digit
+    __shared__ KeyT s_keys[RS_TILE];
+    __shared__ uint32_t s_vals[RS_TILE];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int e = tid; e < RS_WARPS * RS_RADIX; e += RS_THREADS) s_wh[e] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t n = min(*n_ptr, cap);
+    const uint32_t tile_start = tile * (uint32_t)RS_TILE;
+    if (tile_start >= n) return;
+    const uint32_t tile_n = min((uint32_t)RS_TILE, n - tile_start);
+    const uint32_t dmask = (1u << bits) - 1u;
+
+    // ---- load (warp-striped: item i of lane l = chunk[i*32 + l]) and rank ----
+    const uint32_t wbase = tile_start + warp * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* wh = s_wh + warp * RS_RADIX;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        key[i] = idx < n ? (uint32_t)kin[idx] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t d = valid ? ((key[i] >> shift) & dmask) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pre = 0;
+        if (valid && lane == leader) {
+            pre = wh[d];
+            wh[d] = pre + __popc(peers);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rank[i] = pre + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: warp-exclusive offsets, tile count, local digit starts ----
+    uint32_t count = 0;
+    {
+        const int d = tid;   // RS_THREADS == RS_RADIX
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            const uint32_t t = s_wh[w * RS_RADIX + d];
+            s_wh[w * RS_RADIX + d] = count;
+            count += t;
+        }
+    }
+    __syncthreads();
+    // exclusive scans over the 256 digits: local tile counts (s_dstart) and global totals (digit base)
+    uint32_t dstart = 0, dbase = 0;
+    {
+        // warp-level scan of 256 values: each warp scans 32, then warp totals are combined
+        const uint32_t gtot = ghist[tid];
+        uint32_t a = count, b = gtot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+            if (lane >= o) { a += ta; b += tb; }
+        }
+        __shared__ uint32_t s_wa[RS_WARPS], s_wb[RS_WARPS];
+        if (lane == 31) { s_wa[warp] = a; s_wb[warp] = b; }
+        __syncthreads();
+        uint32_t oa = 0, ob = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++)
+            if (w < warp) { oa += s_wa[w]; ob += s_wb[w]; }
+        dstart = oa + a - count;
+        dbase = ob + b - gtot;
+    }
+    // ---- decoupled look-back for digit `tid` ----
+    {
+        const int d = tid;
+        volatile uint32_t* st = tile_state;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st[(size_t)tile * RS_RADIX + d] = count | RS_FLAG_INC;
+        } else {
+            st[(size_t)tile * RS_RADIX + d] = count | RS_FLAG_AGG;
+            __threadfence();
+            // look back RS_LB predecessor tiles per round trip (independent loads in flight): a thread
+            // walking one tile per ~700-cycle load would serialise a whole wave of CTAs
+            int t = (int)tile - 1;
+            while (t >= 0) {
+                uint32_t v[RS_LB];
+#pragma unroll
+                for (int q = 0; q < RS_LB; q++)
+                    v[q] = (t - q >= 0) ? st[(size_t)(t - q) * RS_RADIX + d] : RS_FLAG_INC;
+#pragma unroll
+                for (int q = 0; q < RS_LB; q++) {
+                    if (v[q] & RS_FLAG_INC) { excl += v[q] & RS_VAL_MASK; t = -1; break; }
+                    if (v[q] & RS_FLAG_AGG) { excl += v[q] & RS_VAL_MASK; t--; }
+                    else break;
+                }
+            }
+            st[(size_t)tile * RS_RADIX + d] = (excl + count) | RS_FLAG_INC;
+        }
+        s_dstart[d] = dstart;
+        s_gbase[d] = dbase + excl - dstart;
+    }
+    __syncthreads();
+
+    // ---- reorder by local rank in shared memory ----
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (key[i] >> shift) & dmask;
+            const uint32_t pos = s_dstart[d] + s_wh[warp * RS_RADIX + d] + rank[i];
+            s_keys[pos] = (KeyT)key[i];
+            s_vals[pos] = vin[idx];
+        }
+    }
+    __syncthreads();
+    // ---- coalesced write-out of the digit runs ----
+    for (uint32_t j = tid; j < tile_n; j += RS_THREADS) {
+        const KeyT k = s_keys[j];
+        const uint32_t d = ((uint32_t)k >> shift) & dmask;
+        const uint32_t dst = s_gbase[d] + j;
+        kout[dst] = k;
+        vout[dst] = s_vals[j];
+    }
+}
+
+// scratch layout for one sort: [ghist 4*256][ticket 4 (one per pass) + pad][tile_state passes * tiles * 256]
+size_t radix_scratch_bytes(uint64_t capacity, int passes) {
+    const size_t tiles = (size_t)((capacity + RS_TILE - 1) / RS_TILE) + 1;
+    return align_up((size_t)4 * RS_RADIX * 4, 256) + 256 + (size_t)passes * tiles * RS_RADIX * 4;
+}
+
+template <typename KeyT>
+static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
+                              int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
+    RsPasses ps;
+    ps.num = 0;
+    for (int b = begin_bit; b < end_bit && ps.num < 4; b += 8) {
+        ps.shift[ps.num] = b;
+        ps.bits[ps.num] = (end_bit - b) < 8 ? (end_bit - b) : 8;
+        ps.num++;
+    }
+    // balance a short last digit with the one before (e.g. 13 bits -> 7 + 6 instead of 8 + 5)
+    if (ps.num >= 2 && ps.bits[ps.num - 1] < 8) {
+        const int tot = ps.bits[ps.num - 2] + ps.bits[ps.num - 1];
+        ps.bits[ps.num - 2] = (tot + 1) / 2;
+        ps.shift[ps.num - 1] = ps.shift[ps.num - 2] + ps.bits[ps.num - 2];
+        ps.bits[ps.num - 1] = tot - ps.bits[ps.num - 2];
+    }
+    const size_t tiles = (size_t)((capacity + RS_TILE - 1) / RS_TILE) + 1;
+    char* base = (char*)scratch;
+    uint32_t* ghist = (uint32_t*)base;
+    uint32_t* tickets = (uint32_t*)(base + align_up((size_t)4 * RS_RADIX * 4, 256));
+    uint32_t* states = (uint32_t*)(base + align_up((size_t)4 * RS_RADIX * 4, 256) + 256);
+    OGS_CUDA(cudaMemsetAsync(scratch, 0, radix_scratch_bytes(capacity, ps.num), s));
+    int hist_grid = (int)((capacity + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
+    if (hist_grid > OGS_NUM_SMS * 8) hist_grid = OGS_NUM_SMS * 8;
+    if (hist_grid < 1) hist_grid = 1;
+    rs_hist_kernel<KeyT><<<hist_grid, RS_THREADS, 0, s>>>(k0, n_ptr, (uint32_t)capacity, ps, ghist);
+    KeyT* ka = k0; KeyT* kb = k1;
+    uint32_t* va = v0; uint32_t* vb = v1;
+    const unsigned grid = (unsigned)((capacity + RS_TILE - 1) / RS_TILE);
+    for (int p = 0; p < ps.num; p++) {
+        rs_pass_kernel<KeyT><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_ptr, (uint32_t)capacity, ps.shift[p], ps.bits[p],
+                                                         ghist + p * RS_RADIX, states + (size_t)p * tiles * RS_RADIX,
+                                                         tickets + p);
+        KeyT* tk = ka; ka = kb; kb = tk;
+        uint32_t* tv = va; va = vb; vb = tv;
+    }
+    *result_in_second = (ps.num & 1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "radix_sort_pairs");
+    return 0;
+}
+
+int radix_sort_pairs_u32(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
+                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
+    return radix_sort_pairs_t<uint32_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second);
+}
+int radix_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
+                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
+    return radix_sort_pairs_t<uint16_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inclusive scan of tiles_touched gathered in depth order: out[i] = sum_{j<=i} tiles[order[j]].
+// Single pass, decoupled look-back over 2048-item tiles (same ticket scheme as the sort).
+#define SC_THREADS 256
+#define SC_ITEMS 8
+#define SC_TILE (SC_THREADS * SC_ITEMS)
+
+__global__ void __launch_bounds__(SC_THREADS) scan_gather_kernel(int P, const uint32_t* __restrict__ order,
+                                                                 const uint32_t* __restrict__ tiles, uint32_t* __restrict__ out,
+                                                                 uint32_t* tile_state, uint32_t* ticket) {
+    __shared__ uint32_t s_tile, s_warp[SC_THREADS / 32], s_excl;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int base = (int)tile * SC_TILE + tid * SC_ITEMS;
+    uint32_t v[SC_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const int idx = base + i;
+        v[i] = idx < P ? tiles[order[idx]] : 0u;
+        sum += v[i];
+        v[i] = sum;
+    }
+    uint32_t a = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, a, o);
+        if (lane >= o) a += t;
+    }
+    if (lane == 31) s_warp[warp] = a;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; w++) {
+        if (w < warp) woff += s_warp[w];
+        total += s_warp[w];
+    }
+    if (tid == 0) {
+        volatile uint32_t* st = tile_state;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st[0] = total | RS_FLAG_INC;
+        } else {
+            st[tile] = total | RS_FLAG_AGG;
+            __threadfence();
+            int t = (int)tile - 1;
+            while (t >= 0) {
+                uint32_t x[RS_LB];
+#pragma unroll
+                for (int q = 0; q < RS_LB; q++) x[q] = (t - q >= 0) ? st[t - q] : RS_FLAG_INC;
+#pragma unroll
+                for (int q = 0; q < RS_LB; q++) {
+                    if (x[q] & RS_FLAG_INC) { excl += x[q] & RS_VAL_MASK; t = -1; break; }
+                    if (x[q] & RS_FLAG_AGG) { excl += x[q] & RS_VAL_MASK; t--; }
+                    else break;
+                }
+            }
+            st[tile] = (excl + total) | RS_FLAG_INC;
+        }
+        s_excl = excl;
+    }
+    __syncthreads();
+    const uint32_t off = s_excl + woff + (a - sum);
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const int idx = base + i;
+        if (idx < P) out[idx] = off + v[i];
+    }
+}
+
+size_t scan_scratch_bytes(int P) { return ((size_t)(P + SC_TILE - 1) / SC_TILE + 2) * 4 + 256; }
+
+int scan_gather(int P, const uint32_t* order, const uint32_t* tiles, uint32_t* out, void* scratch, cudaStream_t s) {
+    if (P <= 0) return 0;
+    const int ntiles = (P + SC_TILE - 1) / SC_TILE;
+    OGS_CUDA(cudaMemsetAsync(scratch, 0, scan_scratch_bytes(P), s));
+    uint32_t* ticket = (uint32_t*)scratch;
+    uint32_t* states = (uint32_t*)((char*)scratch + 256);
+    scan_gather_kernel<<<ntiles, SC_THREADS, 0, s>>>(P, order, tiles, out, states, ticket);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "scan_gather");
+    return 0;
+}
+
+}  // namespace ogs
