@@ -9,23 +9,29 @@
 // T' < 1e-4 stops BEFORE applying; colour = sum c alpha T + T_final bg; depth = sum z alpha T;
 // alpha_out = 1 - T_final.
 //
-// Layout: one CTA of 128 threads per 16x16 tile (the tile size is part of the bit-exact binning
-// contract).  Warp w owns an 8x8 pixel block, every lane TWO pixels (rows y and y+4): the shared
-// memory reads of a Gaussian, the warp-level culling test and the loop overhead are amortised over
-// 64 pixels and each thread carries two independent dependency chains.  Gaussians are staged 256
-// per round in shared memory (two float4 records + C colours, gathered once per tile and
-// broadcast-read).  Per group of 32 staged Gaussians, lane l tests Gaussian l against the warp's
-// block (ogs_rect_hit) and only the ballot survivors are blended.
-// Bound: FP32 ALU + MUFU.EX2 issue, not HBM.
+// Layout: one CTA per 16x16 tile (the tile size is part of the bit-exact binning contract).  A warp
+// owns an 8 x (8*PAIRS) pixel block and every lane 2*PAIRS pixels (rows y, y+4, ...).  The pixels
+// of a lane are processed as PACKED PAIRS with Blackwell's two-wide FP32 instructions
+// (fma.rn.f32x2 / mul.f32x2 / add.f32x2 -> FFMA2/FMUL2/FADD2): the kernel is FP32-issue bound
+//  and a scalar FFMA occupies the issue slot as long as an FFMA2 that does
+// two.  Contributions are masked arithmetically (w = 0) instead of branched, so both halves of a
+// pair always run the same instruction stream.  Gaussians are staged 256 per round in shared
+// memory (two float4 records + C colours, gathered once per tile, broadcast-read); per group of 32
+// staged Gaussians lane l tests Gaussian l against the warp's block (ogs_rect_hit) and only the
+// ballot survivors are blended.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ogs {
 
 #define BATCH 256
-#define FWD_THREADS 128
 
-template <int C>
-__global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(BlendFwdArgs a) {
+__device__ __forceinline__ float2 s2(float v) { return make_float2(v, v); }
+
+template <int C, int PAIRS>
+__global__ void __launch_bounds__(128 / PAIRS) blend_fwd_kernel(BlendFwdArgs a) {
+    constexpr int THREADS = 128 / PAIRS;      // 4 / PAIRS warps
+    constexpr int NPX = 2 * PAIRS;            // pixels per lane
     __shared__ float4 s_r0[BATCH];
     __shared__ float4 s_r1[BATCH];
     __shared__ float s_col[BATCH * C];
@@ -33,29 +39,42 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(BlendFwdArgs a) 
     const int gx = (a.W + 15) / 16;
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bxi = blockIdx.x * 16 + (warp & 1) * 8, byi = blockIdx.y * 16 + (warp >> 1) * 8;
+    const int bxi = blockIdx.x * 16 + (warp & 1) * 8, byi = blockIdx.y * 16 + (warp >> 1) * 8 * PAIRS;
     const int px = bxi + (lane & 7);
-    const int py0 = byi + (lane >> 3), py1 = py0 + 4;
-    const bool in0 = px < a.W && py0 < a.H, in1 = px < a.W && py1 < a.H;
-    const float pxf = (float)px, pyf0 = (float)py0, pyf1 = (float)py1;
+    const float pxf = (float)px;
     const float bx0 = (float)bxi, by0 = (float)byi;
 
     const uint2 range = a.ranges[tile];
     int todo = (int)(range.y - range.x);
     const int rounds = (todo + BATCH - 1) / BATCH;
 
-    bool done0 = !in0, done1 = !in1;
-    float T0 = 1.0f, T1 = 1.0f, D0 = 0.f, D1 = 0.f;
-    float acc0[C], acc1[C];
+    bool done[NPX];
+    uint32_t last[NPX];
+    float2 npy[PAIRS], T2[PAIRS], D2[PAIRS], acc[PAIRS][C];
 #pragma unroll
-    for (int c = 0; c < C; c++) { acc0[c] = 0.f; acc1[c] = 0.f; }
-    uint32_t last0 = 0, last1 = 0;
+    for (int p = 0; p < PAIRS; p++) {
+        const int ya = byi + (lane >> 3) + 8 * p, yb = ya + 4;
+        npy[p] = make_float2(-(float)ya, -(float)yb);
+        done[2 * p] = !(px < a.W && ya < a.H);
+        done[2 * p + 1] = !(px < a.W && yb < a.H);
+        last[2 * p] = last[2 * p + 1] = 0;
+        T2[p] = s2(1.0f);
+        D2[p] = s2(0.0f);
+#pragma unroll
+        for (int c = 0; c < C; c++) acc[p][c] = s2(0.0f);
+    }
+    auto all_done = [&]() {
+        bool d = true;
+#pragma unroll
+        for (int k = 0; k < NPX; k++) d = d && done[k];
+        return d;
+    };
 
     for (int r = 0; r < rounds; r++, todo -= BATCH) {
-        if (__syncthreads_count(done0 && done1) == FWD_THREADS) break;
+        if (__syncthreads_count(all_done()) == THREADS) break;
 #pragma unroll
-        for (int h = 0; h < BATCH / FWD_THREADS; h++) {
-            const int slot = threadIdx.x + h * FWD_THREADS;
+        for (int h = 0; h < BATCH / THREADS; h++) {
+            const int slot = threadIdx.x + h * THREADS;
             const int idx = r * BATCH + slot;
             if (range.x + idx < range.y) {
                 const uint32_t g = a.point_list[range.x + idx];
@@ -69,11 +88,11 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(BlendFwdArgs a) 
         }
         __syncthreads();
         const int n = todo < BATCH ? todo : BATCH;
-        if (!__all_sync(0xffffffffu, done0 && done1)) {
+        if (!__all_sync(0xffffffffu, all_done())) {
             for (int grp = 0; grp < n; grp += 32) {
                 const int idx = grp + lane;
                 bool hit = false;
-                if (idx < n) hit = ogs_rect_hit(s_r0[idx], s_r1[idx], bx0, by0, bx0 + 7.0f, by0 + 7.0f);
+                if (idx < n) hit = ogs_rect_hit(s_r0[idx], s_r1[idx], bx0, by0, bx0 + 7.0f, by0 + (float)(8 * PAIRS - 1));
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
                 while (mask) {
                     const int j = grp + __ffs(mask) - 1;
@@ -81,69 +100,62 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(BlendFwdArgs a) 
                     const float4 r0 = s_r0[j];
                     const float4 r1 = s_r1[j];
                     const float dx = r0.x - pxf;
-                    const float dya = r0.y - pyf0, dyb = r0.y - pyf1;
-                    const float adx = __fmul_rn(__fmul_rn(r0.z, dx), dx), bdx = __fmul_rn(r0.w, dx);
-                    const float pw0 = ogs_power(adx, bdx, r1.x, dya);
-                    const float pw1 = ogs_power(adx, bdx, r1.x, dyb);
-                    const float al0 = fminf(0.99f, r1.y * __expf(pw0));
-                    const float al1 = fminf(0.99f, r1.y * __expf(pw1));
-                    const bool ok0 = !done0 && pw0 <= 0.0f && al0 >= (1.0f / 255.0f);
-                    const bool ok1 = !done1 && pw1 <= 0.0f && al1 >= (1.0f / 255.0f);
+                    const float adx = __fmul_rn(__fmul_rn(r0.z, dx), dx), nbdx = -__fmul_rn(r0.w, dx);
                     const uint32_t pos = (uint32_t)(r * BATCH + j + 1);
-                    if (ok0) {
-                        const float test_T = T0 * (1.0f - al0);
-                        if (test_T < 0.0001f) done0 = true;
-                        else {
-                            const float w = al0 * T0;
 #pragma unroll
-                            for (int c = 0; c < C; c++) acc0[c] = fmaf(s_col[j * C + c], w, acc0[c]);
-                            D0 = fmaf(r1.z, w, D0);
-                            T0 = test_T;
-                            last0 = pos;
-                        }
-                    }
-                    if (ok1) {
-                        const float test_T = T1 * (1.0f - al1);
-                        if (test_T < 0.0001f) done1 = true;
-                        else {
-                            const float w = al1 * T1;
+                    for (int p = 0; p < PAIRS; p++) {
+                        // power = -(B dx) dy - 0.5 (adx + (C dy) dy): same rounding sequence as ogs_power()
+                        const float2 dy = __fadd2_rn(s2(r0.y), npy[p]);
+                        const float2 q = __ffma2_rn(__fmul2_rn(s2(r1.x), dy), dy, s2(adx));
+                        const float2 pw = __ffma2_rn(s2(nbdx), dy, __fmul2_rn(s2(-0.5f), q));
+                        float2 al = __fmul2_rn(s2(r1.y), make_float2(__expf(pw.x), __expf(pw.y)));
+                        al.x = fminf(0.99f, al.x);
+                        al.y = fminf(0.99f, al.y);
+                        const bool oka = !done[2 * p] && pw.x <= 0.0f && al.x >= (1.0f / 255.0f);
+                        const bool okb = !done[2 * p + 1] && pw.y <= 0.0f && al.y >= (1.0f / 255.0f);
+                        const float2 tT = __fmul2_rn(T2[p], __fadd2_rn(s2(1.0f), make_float2(-al.x, -al.y)));
+                        const float2 w = __fmul2_rn(al, T2[p]);
+                        const bool apa = oka && !(tT.x < 0.0001f), apb = okb && !(tT.y < 0.0001f);
+                        done[2 * p] = done[2 * p] || (oka && !apa);
+                        done[2 * p + 1] = done[2 * p + 1] || (okb && !apb);
+                        const float2 wm = make_float2(apa ? w.x : 0.0f, apb ? w.y : 0.0f);
 #pragma unroll
-                            for (int c = 0; c < C; c++) acc1[c] = fmaf(s_col[j * C + c], w, acc1[c]);
-                            D1 = fmaf(r1.z, w, D1);
-                            T1 = test_T;
-                            last1 = pos;
-                        }
+                        for (int c = 0; c < C; c++) acc[p][c] = __ffma2_rn(s2(s_col[j * C + c]), wm, acc[p][c]);
+                        D2[p] = __ffma2_rn(s2(r1.z), wm, D2[p]);
+                        T2[p] = make_float2(apa ? tT.x : T2[p].x, apb ? tT.y : T2[p].y);
+                        last[2 * p] = apa ? pos : last[2 * p];
+                        last[2 * p + 1] = apb ? pos : last[2 * p + 1];
                     }
                 }
-                if (__all_sync(0xffffffffu, done0 && done1)) break;
+                if (__all_sync(0xffffffffu, all_done())) break;
             }
         }
     }
     const size_t HW = (size_t)a.H * a.W;
-    if (in0) {
-        const size_t pix = (size_t)py0 * a.W + px;
-        a.final_T[pix] = T0;
-        a.n_contrib[pix] = last0;
 #pragma unroll
-        for (int c = 0; c < C; c++) a.out_color[c * HW + pix] = acc0[c] + T0 * __ldg(a.bg + c);
-        a.out_depth[pix] = D0;
-        a.out_alpha[pix] = 1.0f - T0;
-    }
-    if (in1) {
-        const size_t pix = (size_t)py1 * a.W + px;
-        a.final_T[pix] = T1;
-        a.n_contrib[pix] = last1;
+    for (int k = 0; k < NPX; k++) {
+        const int p = k >> 1;
+        const int py = byi + (lane >> 3) + 8 * p + 4 * (k & 1);
+        if (px < a.W && py < a.H) {
+            const size_t pix = (size_t)py * a.W + px;
+            const float T = (k & 1) ? T2[p].y : T2[p].x;
+            a.final_T[pix] = T;
+            a.n_contrib[pix] = last[k];
 #pragma unroll
-        for (int c = 0; c < C; c++) a.out_color[c * HW + pix] = acc1[c] + T1 * __ldg(a.bg + c);
-        a.out_depth[pix] = D1;
-        a.out_alpha[pix] = 1.0f - T1;
+            for (int c = 0; c < C; c++)
+                a.out_color[c * HW + pix] = ((k & 1) ? acc[p][c].y : acc[p][c].x) + T * __ldg(a.bg + c);
+            a.out_depth[pix] = (k & 1) ? D2[p].y : D2[p].x;
+            a.out_alpha[pix] = 1.0f - T;
+        }
     }
 }
 
 template <int C>
 static int launch_c(const BlendFwdArgs& a, cudaStream_t s) {
     dim3 grid((a.W + 15) / 16, (a.H + 15) / 16);
-    blend_fwd_kernel<C><<<grid, FWD_THREADS, 0, s>>>(a);
+    static const int pairs = getenv("OGS_FWD_PAIRS") ? atoi(getenv("OGS_FWD_PAIRS")) : OGS_FWD_PAIRS;  // tuning knob
+    if (pairs == 2) blend_fwd_kernel<C, 2><<<grid, 64, 0, s>>>(a);
+    else blend_fwd_kernel<C, 1><<<grid, 128, 0, s>>>(a);
     return 0;
 }
 

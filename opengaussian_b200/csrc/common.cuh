@@ -6,7 +6,13 @@
 
 #include "../../include/ogs_b200.h"
 
-#define OGS_BLOCK 256              // threads per tile CTA (16x16 pixels)
+#define OGS_BLOCK 256              // pixels per tile CTA (16x16)
+#ifndef OGS_FWD_PAIRS
+#define OGS_FWD_PAIRS 1            // packed pixel pairs per lane in blend_fwd (1: 8x8 px per warp, 2: 8x16)
+#endif
+#ifndef OGS_BWD_PAIRS
+#define OGS_BWD_PAIRS 1
+#endif
 #define OGS_NUM_SMS 148
 
 namespace ogs {

@@ -7,7 +7,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from opengaussian_b200 import synth  # noqa: E402
+from opengaussian_b200 import _lib, synth  # noqa: E402
 from opengaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer  # noqa: E402
 
 
@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--feat_only", type=int, default=0)
     ap.add_argument("--sync", type=int, default=1)
+    ap.add_argument("--prof", type=int, default=1)
     a = ap.parse_args()
     gs, cams = synth.make_scene(a.scene, n_views=4, P=a.P)
     dev = "cuda"
@@ -50,6 +51,8 @@ def main():
                 t.grad = None
             if it == 3:
                 torch.cuda.synchronize(); t_all0 = time.perf_counter()
+                if a.prof:
+                    _lib.profile_enable(True); _lib.profile_read()
             ev[0].record()
             h0 = time.perf_counter()
             out = rast(means2D=m2, extra_feats=extra, **leaves)
@@ -70,6 +73,9 @@ def main():
                 tf += ev[0].elapsed_time(ev[1])
                 tb += ev[1].elapsed_time(ev[2])
         torch.cuda.synchronize()
+        if a.prof:
+            pr = _lib.profile_read(); _lib.profile_enable(False)
+            print("  stages:", {k: round(ms / max(n, 1), 3) for k, (ms, n) in pr.items() if n})
         wall = (time.perf_counter() - t_all0) / a.iters * 1e3
         print(f"  host: fwd call {hf / a.iters * 1e3:.3f} ms, bwd call {hb / a.iters * 1e3:.3f} ms, wall/step {wall:.3f} ms")
         N = out[0].grad_fn.num_rendered if hasattr(out[0].grad_fn, "num_rendered") else -1
