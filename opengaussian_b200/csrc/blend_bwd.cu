@@ -8,16 +8,20 @@
 //  * the "colour behind" recursion is carried as ONE scalar per pixel: with d_i = <c_i, g> (dot of
 //    the Gaussian's channel vector incl. depth and 1 with the pixel's incoming gradients),
 //    S <- a_prev d_prev + (1 - a_prev) S and dL/dalpha = (d_i - S) T -- C-independent state;
-//  * 128 threads per 16x16 tile, warp = 8x8 pixel block, TWO pixels per lane: the two pixels'
-//    contributions are added in registers first, so the cross-lane reduction, the shared-memory
-//    reads and the culling test are amortised over 64 pixels;
-//  * per (warp, Gaussian) the lanes' contributions are summed with a recursive-halving
-//    (transpose) reduction: V values cost ~V + 5 shuffles instead of 5 V;
-//  * warp-level culling (ogs_rect_hit): lane l tests Gaussian l of a 32-group against the warp's
+//  * 128 threads per 16x16 tile, warp = 8x8 pixel block, TWO pixels per lane evaluated as a packed
+//    pair (FADD2/FMUL2/FFMA2, same staged records and exponent arithmetic as blend_fwd.cu, so the
+//    skip decisions are bit-identical); non-contributing pixels are masked arithmetically
+//    (alpha = G = 0 leaves T, S and every sum unchanged) so both halves share one instruction stream;
+//  * geometry gradients are reduced as the raw moments of u = G dL/dalpha (sum u, u dx, u dy,
+//    u dx^2, u dx dy, u dy^2): dL/dmean2D and dL/dconic are linear in them with per-Gaussian
+//    factors, which preprocess_bwd applies once per Gaussian instead of once per (pixel, Gaussian);
+//  * per (warp, Gaussian) the lanes' sums are combined with a recursive-halving (transpose)
+//    reduction over power-of-two chunks of the value vector: V values cost ~V + 5 shuffles;
+//  * warp-level culling (ogs_rect_hit_s): lane l tests Gaussian l of a 32-group against the warp's
 //    block; only ballot survivors are evaluated;
-//  * each warp accumulates into its own shared-memory rows (no shared atomics); once per batch of
-//    64 Gaussians the 4 warp rows are summed and ONE red.global.add per value per (tile, Gaussian)
-//    is issued, skipping zeros;
+//  * each warp stores into its own shared-memory rows (a (warp, Gaussian) pair is visited once per
+//    batch: plain stores, no read-modify-write); once per batch of 64 Gaussians the 4 warp rows are
+//    summed and ONE red.global.add per value per (tile, Gaussian) is issued, skipping zeros;
 //  * GEOM=false specialisation (OpenGaussian stages 1-2 detach geometry, train.py:431-436): only
 //    w = alpha T and dL/dc are evaluated.
 #include "common.cuh"
@@ -51,61 +55,39 @@ struct HalvingReduce {
     }
 };
 
-constexpr int next_pow2(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
+constexpr int floor_pow2(int v) { return v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1))); }
 constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v / 2); }
 
-int blend_bwd_stride(int C, int geom) { return geom ? C + 7 : C; }
-
-template <int C>
-struct PixelState {
-    float T, T_final, S, last_dot, last_alpha, gd, ga, bg_dot, pyf;
-    float g[C];
-    int last;
+// Sums v[BASE..BASE+N) over the 32 lanes, chunk by chunk (largest power of two first), and stores
+// the totals to row[BASE..BASE+N): after a chunk of S values, lane l with (l % (32/S)) == 0 holds
+// the total of value l / (32/S).
+template <int N, int BASE>
+struct ChunkReduceStore {
+    template <int VT>
+    __device__ __forceinline__ static void run(const float (&v)[VT], int lane, float* row) {
+        if constexpr (N > 0) {
+            constexpr int S = floor_pow2(N);
+            constexpr int SH = 5 - log2c(S);
+            float t[S];
+#pragma unroll
+            for (int k = 0; k < S; k++) t[k] = v[BASE + k];
+            HalvingReduce<S, 16>::run(t, lane);
+            if ((lane & ((1 << SH) - 1)) == 0) row[BASE + (lane >> SH)] = t[0];
+            ChunkReduceStore<N - S, BASE + S>::run(v, lane, row);
+        }
+    }
 };
 
-template <int C, bool GEOM, int VP>
-__device__ __forceinline__ void pixel_contrib(PixelState<C>& p, bool ok, float alpha, float G, float dx, float dy,
-                                              const float4& r0, const float4& r1, const float* __restrict__ col,
-                                              float half_w, float half_h, float (&v)[VP]) {
-    if (!ok) return;
-    const float inv = __fdividef(1.0f, 1.0f - alpha);
-    p.T = p.T * inv;
-    const float w = alpha * p.T;
-#pragma unroll
-    for (int c = 0; c < C; c++) v[c] = fmaf(w, p.g[c], v[c]);
-    if (GEOM) {
-        float dot = fmaf(r1.z, p.gd, p.ga);
-#pragma unroll
-        for (int c = 0; c < C; c++) dot = fmaf(col[c], p.g[c], dot);
-        p.S = fmaf(p.last_alpha, p.last_dot, (1.0f - p.last_alpha) * p.S);
-        p.last_dot = dot;
-        p.last_alpha = alpha;
-        float dL_dalpha = (dot - p.S) * p.T;
-        dL_dalpha = fmaf(-p.T_final * inv, p.bg_dot, dL_dalpha);
-        const float dL_dG = r1.y * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-        const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-        v[C + 0] = fmaf(w, p.gd, v[C + 0]);
-        v[C + 1] = fmaf(dL_dG * dG_ddelx, half_w, v[C + 1]);
-        v[C + 2] = fmaf(dL_dG * dG_ddely, half_h, v[C + 2]);
-        const float hq = -0.5f * dL_dG;
-        v[C + 3] = fmaf(hq * gdx, dx, v[C + 3]);
-        v[C + 4] = fmaf(hq * gdx, dy, v[C + 4]);
-        v[C + 5] = fmaf(hq * gdy, dy, v[C + 5]);
-        v[C + 6] = fmaf(G, dL_dalpha, v[C + 6]);
-    }
-}
+int blend_bwd_stride(int C, int geom) { return geom ? C + 7 : C; }
 
 template <int C, bool GEOM>
 __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) {
     constexpr int V = GEOM ? C + 7 : C;
-    constexpr int VP = next_pow2(V);
-    constexpr int SHIFT = 5 - log2c(VP);  // lane >> SHIFT = value index held after the reduction
-    extern __shared__ float s_dyn[];      // [BWD_WARPS][BB][V] per-warp accumulators
-    __shared__ float4 s_r0[BB];
-    __shared__ float4 s_r1[BB];
-    __shared__ float s_col[BB * C];
+    constexpr int CH = (C + 1 + 3) & ~3;  // colours + depth, padded to float4
+    extern __shared__ float s_dyn[];      // [BWD_WARPS][BB][V] per-warp sums
+    __shared__ float4 s_a[BB];
+    __shared__ float2 s_b[BB];
+    __shared__ __align__(16) float s_ch[BB * CH];
     __shared__ uint32_t s_id[BB];
     __shared__ int s_max_last;
 
@@ -119,35 +101,46 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) 
     const size_t HW = (size_t)a.H * a.W;
     const uint2 range = a.ranges[tile];
 
-    PixelState<C> ps[2];
+    // per-lane state of the pixel pair (.x: row y, .y: row y + 4)
+    float2 T2, S2 = s2(0.f), om2 = s2(1.f), prod2 = s2(0.f), gd2 = s2(0.f), ga2 = s2(0.f), tfbg2 = s2(0.f), npy;
+    float2 g2[C];
+    int last[2];
+    {
+        float Tf[2], gdv[2] = {0.f, 0.f}, gav[2] = {0.f, 0.f}, bgd[2] = {0.f, 0.f};
+        float gv[2][C];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int py = byi + (lane >> 3) + 4 * k;
-        const bool inside = px < a.W && py < a.H;
-        const size_t pix = (size_t)py * a.W + px;
-        PixelState<C>& p = ps[k];
-        p.pyf = (float)py;
-        p.last = inside ? (int)a.n_contrib[pix] : 0;
-        p.T_final = inside ? a.final_T[pix] : 0.f;
-        p.T = p.T_final;
-        p.S = 0.f; p.last_dot = 0.f; p.last_alpha = 0.f; p.gd = 0.f; p.ga = 0.f; p.bg_dot = 0.f;
+        for (int k = 0; k < 2; k++) {
+            const int py = byi + (lane >> 3) + 4 * k;
+            const bool inside = px < a.W && py < a.H;
+            const size_t pix = (size_t)py * a.W + px;
+            last[k] = inside ? (int)a.n_contrib[pix] : 0;
+            Tf[k] = inside ? a.final_T[pix] : 0.f;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            p.g[c] = inside ? __ldg(a.dL_dcolor + c * HW + pix) : 0.f;
-            if (GEOM) p.bg_dot = fmaf(__ldg(a.bg + c), p.g[c], p.bg_dot);
+            for (int c = 0; c < C; c++) {
+                gv[k][c] = inside ? __ldg(a.dL_dcolor + c * HW + pix) : 0.f;
+                if (GEOM) bgd[k] = fmaf(__ldg(a.bg + c), gv[k][c], bgd[k]);
+            }
+            if (GEOM) {
+                gdv[k] = (inside && a.dL_ddepth) ? __ldg(a.dL_ddepth + pix) : 0.f;
+                gav[k] = (inside && a.dL_dalpha) ? __ldg(a.dL_dalpha + pix) : 0.f;
+            }
         }
+        npy = make_float2(-(float)(byi + (lane >> 3)), -(float)(byi + (lane >> 3) + 4));
+        T2 = make_float2(Tf[0], Tf[1]);
+#pragma unroll
+        for (int c = 0; c < C; c++) g2[c] = make_float2(gv[0][c], gv[1][c]);
         if (GEOM) {
-            p.gd = (inside && a.dL_ddepth) ? __ldg(a.dL_ddepth + pix) : 0.f;
-            p.ga = (inside && a.dL_dalpha) ? __ldg(a.dL_dalpha + pix) : 0.f;
+            gd2 = make_float2(gdv[0], gdv[1]);
+            ga2 = make_float2(gav[0], gav[1]);
+            tfbg2 = make_float2(Tf[0] * bgd[0], Tf[1] * bgd[1]);
         }
     }
-    const float half_w = 0.5f * (float)a.W, half_h = 0.5f * (float)a.H;
 
     // block / warp maxima of the last contributor
     if (threadIdx.x == 0) s_max_last = 0;
     for (int e = threadIdx.x; e < BWD_WARPS * BB * V; e += BWD_THREADS) s_dyn[e] = 0.f;
     __syncthreads();
-    int wmax = max(ps[0].last, ps[1].last);
+    int wmax = max(last[0], last[1]);
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, m));
     if (lane == 0 && wmax > 0) atomicMax(&s_max_last, wmax);
@@ -159,17 +152,18 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) 
     for (int b = (max_last - 1) / BB; b >= 0; b--) {
         const int start = b * BB;
         const int n = min(BB, max_last - start);
-        // ---- stage the batch ----
+        // ---- stage the batch (pre-scaled records, colours + depth) ----
         if (threadIdx.x < n) {
             const uint32_t gid = a.point_list[range.x + start + threadIdx.x];
             s_id[threadIdx.x] = gid;
-            s_r0[threadIdx.x] = __ldg(a.rec0 + gid);
-            s_r1[threadIdx.x] = __ldg(a.rec1 + gid);
+            const float4 r1 = __ldg(a.rec1 + gid);
+            ogs_stage(__ldg(a.rec0 + gid), r1, s_a[threadIdx.x], s_b[threadIdx.x]);
+            s_ch[threadIdx.x * CH + C] = r1.z;
         }
         for (int e = threadIdx.x; e < n * C; e += BWD_THREADS) {
             const int j = e / C, c = e - j * C;
             const uint32_t gid = a.point_list[range.x + start + j];
-            s_col[e] = (c < 3) ? __ldg(a.base + 3 * (size_t)gid + c) : __ldg(a.extra + (size_t)(C - 3) * gid + (c - 3));
+            s_ch[j * CH + c] = (c < 3) ? __ldg(a.base + 3 * (size_t)gid + c) : __ldg(a.extra + (size_t)(C - 3) * gid + (c - 3));
         }
         __syncthreads();
         // ---- traverse back to front ----
@@ -178,33 +172,69 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) 
             for (int grp = ((nw - 1) >> 5) << 5; grp >= 0; grp -= 32) {
                 const int idx = grp + lane;
                 bool hit = false;
-                if (idx < nw) hit = ogs_rect_hit(s_r0[idx], s_r1[idx], bx0, by0, bx0 + 7.0f, by0 + 7.0f);
+                if (idx < nw) hit = ogs_rect_hit_s(s_a[idx], s_b[idx], bx0, by0, bx0 + 7.0f, by0 + 7.0f);
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
                 while (mask) {
                     const int bit = 31 - __clz(mask);
                     mask &= ~(1u << bit);
                     const int j = grp + bit;
                     const int pos = start + j;
-                    const float4 r0 = s_r0[j];
-                    const float4 r1 = s_r1[j];
-                    const float dx = r0.x - pxf;
-                    const float dy0 = r0.y - ps[0].pyf, dy1 = r0.y - ps[1].pyf;
-                    const float adx = __fmul_rn(__fmul_rn(r0.z, dx), dx), bdx = __fmul_rn(r0.w, dx);
-                    const float pw0 = ogs_power(adx, bdx, r1.x, dy0);
-                    const float pw1 = ogs_power(adx, bdx, r1.x, dy1);
-                    const float G0 = __expf(pw0), G1 = __expf(pw1);
-                    const float al0 = fminf(0.99f, r1.y * G0), al1 = fminf(0.99f, r1.y * G1);
-                    const bool ok0 = pos < ps[0].last && pw0 <= 0.0f && al0 >= (1.0f / 255.0f);
-                    const bool ok1 = pos < ps[1].last && pw1 <= 0.0f && al1 >= (1.0f / 255.0f);
-                    if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
-                    float v[VP];
+                    const float4 ra = s_a[j];
+                    const float2 rb = s_b[j];
+                    const float dx = ra.x - pxf;
+                    const float adx = __fmul_rn(__fmul_rn(ra.z, dx), dx), bdx = __fmul_rn(ra.w, dx);
+                    float2 dy;
+                    const float2 pw = ogs_pair_power(adx, bdx, rb.x, ra.y, npy, dy);
+                    const float2 G = make_float2(ogs_ex2(pw.x), ogs_ex2(pw.y));
+                    float2 al = __fmul2_rn(s2(rb.y), G);
+                    al.x = fminf(0.99f, al.x);
+                    al.y = fminf(0.99f, al.y);
+                    const bool oka = pos < last[0] && pw.x <= 0.0f && al.x >= (1.0f / 255.0f);
+                    const bool okb = pos < last[1] && pw.y <= 0.0f && al.y >= (1.0f / 255.0f);
+                    if (!__any_sync(0xffffffffu, oka || okb)) continue;
+                    float chv[CH];
 #pragma unroll
-                    for (int k = 0; k < VP; k++) v[k] = 0.f;
-                    pixel_contrib<C, GEOM, VP>(ps[0], ok0, al0, G0, dx, dy0, r0, r1, s_col + j * C, half_w, half_h, v);
-                    pixel_contrib<C, GEOM, VP>(ps[1], ok1, al1, G1, dx, dy1, r0, r1, s_col + j * C, half_w, half_h, v);
-                    HalvingReduce<VP, 16>::run(v, lane);
-                    const int k = lane >> SHIFT;
-                    if ((lane & ((1 << SHIFT) - 1)) == 0 && k < V) my_acc[j * V + k] += v[0];
+                    for (int q = 0; q < CH / 4; q++) {
+                        const float4 t = reinterpret_cast<const float4*>(s_ch + j * CH)[q];
+                        chv[4 * q] = t.x; chv[4 * q + 1] = t.y; chv[4 * q + 2] = t.z; chv[4 * q + 3] = t.w;
+                    }
+                    const float2 alm = make_float2(oka ? al.x : 0.f, okb ? al.y : 0.f);
+                    const float2 om = __fadd2_rn(s2(1.0f), make_float2(-alm.x, -alm.y));
+                    const float2 inv = make_float2(ogs_rcp(om.x), ogs_rcp(om.y));
+                    T2 = __fmul2_rn(T2, inv);
+                    const float2 w = __fmul2_rn(alm, T2);
+                    float v[V];
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const float2 t = __fmul2_rn(w, g2[c]);
+                        v[c] = t.x + t.y;
+                    }
+                    if (GEOM) {
+                        float2 dot = __ffma2_rn(s2(chv[0]), g2[0], ga2);
+#pragma unroll
+                        for (int c = 1; c < C; c++) dot = __ffma2_rn(s2(chv[c]), g2[c], dot);
+                        dot = __ffma2_rn(s2(chv[C]), gd2, dot);
+                        S2 = __ffma2_rn(om2, S2, prod2);          // S <- a_prev d_prev + (1 - a_prev) S
+                        prod2 = __fmul2_rn(alm, dot);
+                        om2 = om;
+                        const float2 dS = __fadd2_rn(dot, make_float2(-S2.x, -S2.y));
+                        const float2 dLda = __ffma2_rn(make_float2(-tfbg2.x, -tfbg2.y), inv, __fmul2_rn(dS, T2));
+                        const float2 Gm = make_float2(oka ? G.x : 0.f, okb ? G.y : 0.f);
+                        const float2 u = __fmul2_rn(Gm, dLda);
+                        const float2 uy = __fmul2_rn(u, dy);
+                        const float2 uyy = __fmul2_rn(uy, dy);
+                        const float2 wd = __fmul2_rn(w, gd2);
+                        const float su = u.x + u.y, suy = uy.x + uy.y;
+                        const float sux = su * dx;
+                        v[C + 0] = wd.x + wd.y;
+                        v[C + 1] = su;
+                        v[C + 2] = sux;
+                        v[C + 3] = suy;
+                        v[C + 4] = sux * dx;
+                        v[C + 5] = suy * dx;
+                        v[C + 6] = uyy.x + uyy.y;
+                    }
+                    ChunkReduceStore<V, 0>::run(v, lane, my_acc + j * V);
                 }
             }
         }

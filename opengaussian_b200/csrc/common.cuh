@@ -156,8 +156,10 @@ struct BlendBwdArgs {
     float* acc;                 // [P][stride] accumulators (zeroed by the launcher)
     int stride;                 // floats per Gaussian in acc
 };
-// acc layout per Gaussian: [0..C) dL_dcolors, then (geom) C+0 dL_ddepth, C+1 dmean2D.x, C+2 dmean2D.y,
-// C+3 dconic.a, C+4 dconic.b(half), C+5 dconic.c, C+6 dopacity
+// acc layout per Gaussian: [0..C) dL_dcolors, then (geom) C+0 dL_ddepth and the raw moments of
+// u = G dL/dalpha over the contributing pixels (d = mean2D - pixel):
+// C+1 sum u (= dL_dopacity), C+2 sum u dx, C+3 sum u dy, C+4 sum u dx^2, C+5 sum u dx dy, C+6 sum u dy^2.
+// preprocess_bwd turns them into dL_dmean2D / dL_dconic (linear in the moments, per-Gaussian factors).
 int blend_bwd_stride(int C, int geom);
 int launch_blend_backward(const BlendBwdArgs& a, cudaStream_t s);
 
@@ -214,6 +216,68 @@ __device__ __forceinline__ bool ogs_rect_hit(const float4 r0, const float4 r1, f
 __device__ __forceinline__ float ogs_power(float adx, float bdx, float Cc, float dy) {
     const float q = __fmaf_rn(__fmul_rn(Cc, dy), dy, adx);
     return __fmaf_rn(-bdx, dy, __fmul_rn(-0.5f, q));
+}
+
+// ---- blend kernels: staged (pre-scaled) Gaussian records and packed two-pixel arithmetic ----
+// The blend kernels stage each list entry in shared memory with the conic pre-multiplied so that
+// the exponent comes out directly in the log2 domain (one MUFU.EX2, no range fix-up):
+//   sa = {x, y, A' = -0.5 log2(e) A, B' = -log2(e) B},  sb = {C' = -0.5 log2(e) C, opacity}
+//   power2 = (A' dx) dx + (C' dy) dy + (B' dx) dy  ( = log2(e) * power ),  G = 2^power2.
+// Two pixels of a lane (same column, rows y and y+4) are evaluated with Blackwell's packed FP32
+// instructions (FADD2 / FMUL2 / FFMA2).  Forward and backward share ogs_stage/ogs_pair_power/
+// ogs_ex2 so that they take bit-identical skip / contribute decisions.
+#define OGS_LOG2E 1.44269504088896340736f
+__device__ __forceinline__ float2 s2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float ogs_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ogs_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void ogs_stage(const float4 r0, const float4 r1, float4& sa, float2& sb) {
+    sa = make_float4(r0.x, r0.y, __fmul_rn(-0.5f * OGS_LOG2E, r0.z), __fmul_rn(-OGS_LOG2E, r0.w));
+    sb = make_float2(__fmul_rn(-0.5f * OGS_LOG2E, r1.x), r1.y);
+}
+// adx = (A' dx) dx, bdx = B' dx (per column); npy = -(pixel rows); returns power2 of the two pixels, dy by reference
+__device__ __forceinline__ float2 ogs_pair_power(float adx, float bdx, float Cs, float y, float2 npy, float2& dy) {
+    dy = __fadd2_rn(s2(y), npy);
+    const float2 t = __fmul2_rn(s2(Cs), dy);
+    const float2 q = __ffma2_rn(t, dy, s2(adx));
+    return __ffma2_rn(s2(bdx), dy, q);
+}
+// ogs_rect_hit on a staged record: alpha >= 1/255 somewhere in the rectangle needs
+// q'(d) = a dx^2 + 2 hb dx dy + c dy^2 <= log2(255 opacity) with a = -A', hb = -B'/2, c = -C'.
+__device__ __forceinline__ bool ogs_rect_hit_s(const float4 sa, const float2 sb, float x0, float y0, float x1, float y1) {
+    const float A = -sa.z, B = -0.5f * sa.w, C = -sb.x;
+    const float o255 = 255.0f * sb.y;
+    if (!(o255 >= 1.0f)) return false;
+    if (!(A > 0.f && C > 0.f)) return true;
+    const float tau = __log2f(o255);
+    const float dxl = sa.x - x1, dxh = sa.x - x0, dyl = sa.y - y1, dyh = sa.y - y0;
+    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;
+    const float nbc = -B / C, nba = -B / A;
+    float q = 3.0e38f;
+    {
+        const float c = dxl, d = fminf(dyh, fmaxf(dyl, nbc * c));
+        q = fminf(q, A * c * c + 2.f * B * c * d + C * d * d);
+    }
+    {
+        const float c = dxh, d = fminf(dyh, fmaxf(dyl, nbc * c));
+        q = fminf(q, A * c * c + 2.f * B * c * d + C * d * d);
+    }
+    {
+        const float c = dyl, d = fminf(dxh, fmaxf(dxl, nba * c));
+        q = fminf(q, A * d * d + 2.f * B * d * c + C * c * c);
+    }
+    {
+        const float c = dyh, d = fminf(dxh, fmaxf(dxl, nba * c));
+        q = fminf(q, A * d * d + 2.f * B * d * c + C * c * c);
+    }
+    return q <= tau * 1.001f + 1e-3f;
 }
 #endif
 

@@ -92,10 +92,20 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
         const float* proj = a.proj;
         const float m0 = a.means3D[3 * (size_t)i], m1 = a.means3D[3 * (size_t)i + 1], m2 = a.means3D[3 * (size_t)i + 2];
         const float dL_ddepth = acc[C + 0];
-        dm2x = acc[C + 1];
-        dm2y = acc[C + 2];
-        const float dLA = acc[C + 3], dLBh = acc[C + 4], dLC = acc[C + 5];
-        dop = acc[C + 6];
+        // blend_bwd delivers the raw moments of u = G dL/dalpha (common.cuh, acc layout); with
+        // dL/dG = opacity * dL/dalpha: dL/dmean2D = -(W/2, H/2) * conic * (sum dL/dG G d),
+        // dL/dconic = -1/2 sum dL/dG G d d^T  (b carries the half factor of the symmetric pair)
+        float dLA, dLBh, dLC;
+        {
+            const float4 q0 = a.g.rec0[i], q1 = a.g.rec1[i];
+            const float op = q1.y;
+            const float e1 = op * acc[C + 2], e2 = op * acc[C + 3];
+            dop = acc[C + 1];
+            dm2x = -0.5f * (float)a.W * (q0.z * e1 + q0.w * e2);
+            dm2y = -0.5f * (float)a.H * (q1.x * e2 + q0.w * e1);
+            const float hop = -0.5f * op;
+            dLA = hop * acc[C + 4]; dLBh = hop * acc[C + 5]; dLC = hop * acc[C + 6];
+        }
 
         // cov3D (recomputed)
         float c6[6];
