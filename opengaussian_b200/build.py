@@ -49,6 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(os.path.dirname(HERE), "include", "ogs_b200.h"))
     headers.append(os.path.abspath(__file__))
     nvcc = _nvcc()
+    dev_flags = os.environ.get("OGS_NVCC_FLAGS", "").split()   # developer tuning knobs (-DPB=64 ...); pass force=True with them
     jobs = []
     objs = []
     for src, extra in UNITS.items():
@@ -58,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         op = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(op)
         if force or _stale(op, [sp] + headers):
-            jobs.append(([nvcc] + ARCH + COMMON + extra + ["-c", sp, "-o", op], op))
+            jobs.append(([nvcc] + ARCH + COMMON + extra + dev_flags + ["-c", sp, "-o", op], op))
 
     def run(job):
         cmd, op = job

@@ -22,8 +22,11 @@ namespace ogs {
 
 int radix_sort_pairs_u32(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
                          int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second);
-int radix_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
-                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second);
+int tile_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
+                        int bits, void* scratch, cudaStream_t s);
+size_t tile_sort_scratch_bytes(uint64_t capacity);
+void tile_sort_plan(int bits, int* passes, int* bits0);
+uint32_t* tile_sort_pass0_counts(void* scratch);
 size_t radix_scratch_bytes(uint64_t capacity, int passes);
 size_t scan_scratch_bytes(int P);
 int scan_gather(int P, const uint32_t* order, const uint32_t* tiles, uint32_t* out, void* scratch, cudaStream_t s);
@@ -33,7 +36,7 @@ size_t depth_sort_temp_bytes(int P) {
     return (a > b ? a : b);
 }
 
-size_t tile_sort_temp_bytes(int64_t cap) { return radix_scratch_bytes((uint64_t)cap, 2); }
+size_t tile_sort_temp_bytes(int64_t cap) { return tile_sort_scratch_bytes((uint64_t)cap); }
 
 __global__ void set_scalar_kernel(uint32_t* p, uint32_t v) { *p = v; }
 
@@ -64,11 +67,16 @@ __device__ __forceinline__ int imax_(int a, int b) { return a > b ? a : b; }
 // entry-parallel (owner = 8-step binary search in shared memory).  Every store is coalesced and
 // every CTA does the same amount of work, however skewed the per-Gaussian tile counts are (the
 // nearest Gaussians -- first in depth order -- cover thousands of tiles each).
-#define EMIT_CHUNK 2048
+// A chunk is one tile of the tile sort (radix.cu RS_TILE): the CTA also counts the first sort digit
+// of its entries and writes its column of the [digit][chunk] histogram, so the sort's first pass
+// needs no counting sweep.
+#define EMIT_CHUNK 4096
 __global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, const uint32_t* __restrict__ n_ptr, uint32_t cap,
                                                    const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                                                    const float4* __restrict__ rec0, const float4* __restrict__ rec1,
-                                                   uint16_t* __restrict__ tkeys, uint32_t* __restrict__ tvals) {
+                                                   uint16_t* __restrict__ tkeys, uint32_t* __restrict__ tvals,
+                                                   int bits0, uint32_t* __restrict__ cnt0 /*[1<<bits0][gridDim.x]*/) {
+    __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_start[256];
     __shared__ uint32_t s_g[256];
     __shared__ uint32_t s_rect[256];   // x0 | y0 << 16
@@ -77,7 +85,12 @@ __global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, const 
     const int t = threadIdx.x;
     const uint32_t N = min(*n_ptr, cap);     // never write past the capacity (an overflow is re-run by the host)
     const uint32_t chunk_lo = blockIdx.x * (uint32_t)EMIT_CHUNK;
-    if (chunk_lo >= N) return;
+    const uint32_t dmask = (1u << bits0) - 1u;
+    if (chunk_lo >= N) {
+        if (t < (1 << bits0)) cnt0[(size_t)t * gridDim.x + blockIdx.x] = 0u;
+        return;
+    }
+    s_hist[t] = 0;
     const uint32_t chunk_hi = min(N, chunk_lo + (uint32_t)EMIT_CHUNK);
     // first sorted slot whose inclusive offset exceeds chunk_lo (it owns entry chunk_lo)
     int lo = 0, hi = P;
@@ -123,26 +136,46 @@ __global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, const 
             const uint32_t local = e - s_start[j];
             const uint32_t w = s_w[j];
             const uint32_t dy = local / w, dx = local - dy * w;
-            tkeys[e] = (uint16_t)(((rc >> 16) + dy) * gx + (rc & 0xFFFFu) + dx);
+            const uint32_t key = ((rc >> 16) + dy) * gx + (rc & 0xFFFFu) + dx;
+            tkeys[e] = (uint16_t)key;
             tvals[e] = s_g[j];
+            atomicAdd(&s_hist[key & dmask], 1u);
         }
         __syncthreads();
         if (e_hi >= chunk_hi) break;
     }
+    __syncthreads();
+    if (t < (1 << bits0)) cnt0[(size_t)t * gridDim.x + blockIdx.x] = s_hist[t];
 }
 
+// ranges[t] = [first, last+1) of tile t in the sorted key list; 8 keys (one 16-byte load) per thread
 __global__ void __launch_bounds__(256) ranges_kernel(const uint32_t* __restrict__ n_ptr, uint32_t cap,
                                                      const uint16_t* __restrict__ tk, uint2* __restrict__ ranges) {
     const uint32_t N = min(*n_ptr, cap);
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= N) return;
-    const uint32_t t = tk[i];
-    if (i == 0) ranges[t].x = 0;
-    else {
-        const uint32_t pt = tk[i - 1];
-        if (t != pt) { ranges[pt].y = i; ranges[t].x = i; }
+    const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 8u;
+    if (i0 >= N) return;
+    uint32_t k[8];
+    if (i0 + 8 <= N) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i0));
+        k[0] = q.x & 0xFFFFu; k[1] = q.x >> 16; k[2] = q.y & 0xFFFFu; k[3] = q.y >> 16;
+        k[4] = q.z & 0xFFFFu; k[5] = q.z >> 16; k[6] = q.w & 0xFFFFu; k[7] = q.w >> 16;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) k[j] = (i0 + j < N) ? tk[i0 + j] : 0xFFFFFFFFu;
     }
-    if (i == N - 1) ranges[t].y = N;
+    uint32_t prev = (i0 == 0) ? 0xFFFFFFFFu : tk[i0 - 1];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t i = i0 + j;
+        if (i < N) {
+            if (k[j] != prev) {
+                ranges[k[j]].x = i;
+                if (i > 0) ranges[prev].y = i;
+            }
+            if (i == N - 1) ranges[k[j]].y = N;
+            prev = k[j];
+        }
+    }
 }
 
 // n_ptr: device count of entries (last inclusive offset); cap: capacity of the key/value buffers.
@@ -158,25 +191,26 @@ int emit_sort_ranges(int P, int W, int H, const uint32_t* n_ptr, int64_t cap, co
     int bits = 0;
     while ((1 << bits) < tiles) bits++;
     if (bits == 0) bits = 1;
-    const int passes = (bits + 7) / 8;
-    uint16_t *kX, *kY;
-    uint32_t *vX, *vY;
-    if (passes & 1) { kX = tkeys_a; vX = tvals_a; kY = tkeys_b; vY = point_list; }
-    else { kX = tkeys_b; vX = point_list; kY = tkeys_a; vY = tvals_a; }
+    int passes = 1, bits0 = bits;
+    tile_sort_plan(bits, &passes, &bits0);
+    // emit writes (k0, v0); the sort leaves the result in (k1, v1) after one pass, (k0, v0) after two
+    uint16_t* k0 = tkeys_a; uint16_t* k1 = tkeys_b;
+    uint32_t* v0 = passes == 2 ? point_list : tvals_a;
+    uint32_t* v1 = passes == 2 ? tvals_a : point_list;
     prof_begin(PF_EMIT, s);
     emit_kernel<<<(unsigned)((cap + EMIT_CHUNK - 1) / EMIT_CHUNK), 256, 0, s>>>(P, gx, gy, n_ptr, (uint32_t)cap, sc.dvals_out,
-                                                                                sc.offsets, g.rec0, g.rec1, kX, vX);
+                                                                                sc.offsets, g.rec0, g.rec1, k0, v0, bits0,
+                                                                                tile_sort_pass0_counts(sc.cub_temp));
     prof_end(PF_EMIT, s);
     OGS_KERNEL_CHECK("emit_kernel", debug, s);
-    int second = 0;
     prof_begin(PF_TILE_SORT, s);
-    const int rc = radix_sort_pairs_u16(kX, kY, vX, vY, n_ptr, (uint64_t)cap, 0, bits, sc.cub_temp, s, &second);
+    const int rc = tile_sort_pairs_u16(k0, k1, v0, v1, n_ptr, (uint64_t)cap, bits, sc.cub_temp, s);
     prof_end(PF_TILE_SORT, s);
     if (rc) return rc;
     OGS_KERNEL_CHECK("tile_sort", debug, s);
-    const uint16_t* sorted_keys = second ? kY : kX;
+    const uint16_t* sorted_keys = passes == 2 ? k0 : k1;
     ProfScope ps(PF_RANGES, s);
-    ranges_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(n_ptr, (uint32_t)cap, sorted_keys, ranges);
+    ranges_kernel<<<(unsigned)((cap + 2047) / 2048), 256, 0, s>>>(n_ptr, (uint32_t)cap, sorted_keys, ranges);
     OGS_KERNEL_CHECK("ranges_kernel", debug, s);
     return 0;
 }

@@ -25,11 +25,14 @@ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 template <bool STAGE_SH>
 __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, int i, float* s_row, bool vis);
 
+#ifndef PB
+#define PB 128   // Gaussians (= threads) per CTA: 25 KB SH slab, several CTAs per SM overlap their load / compute / store phases
+#endif
 template <bool STAGE_SH>
-__global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(PreprocessBwdArgs a) {
+__global__ void __launch_bounds__(PB, 4) preprocess_bwd_kernel(PreprocessBwdArgs a) {
     extern __shared__ float s_sh[];
-    __shared__ uint8_t s_vis[256];
-    const int i = blockIdx.x * 256 + threadIdx.x;
+    __shared__ uint8_t s_vis[PB];
+    const int i = blockIdx.x * PB + threadIdx.x;
     const bool active = i < a.P;
     bool vis = false;
     if (active) vis = __float_as_int(a.g.rec1[i].w) > 0;
@@ -37,9 +40,9 @@ __global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(PreprocessBwdArg
     if (STAGE_SH) {
         s_vis[threadIdx.x] = vis;
         __syncthreads();
-        const size_t base = (size_t)blockIdx.x * 256 * per;
+        const size_t base = (size_t)blockIdx.x * PB * per;
         const float4* src = reinterpret_cast<const float4*>(a.shs + base);
-        for (int e = threadIdx.x; e < 64 * per; e += 256) {     // 256 * per / 4 float4 (per % 4 == 0)
+        for (int e = threadIdx.x; e < PB / 4 * per; e += PB) {     // PB * per / 4 float4 (per % 4 == 0)
             const int f = e * 4;
             const int gi = f / per, k = f - gi * per;
             if (s_vis[gi]) {
@@ -53,10 +56,10 @@ __global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(PreprocessBwdArg
     if (active) preprocess_bwd_body<STAGE_SH>(a, i, STAGE_SH ? s_sh + threadIdx.x * (per + 1) : nullptr, vis);
     if (STAGE_SH && a.dL_dshs) {
         __syncthreads();
-        const size_t base = (size_t)blockIdx.x * 256 * per;
+        const size_t base = (size_t)blockIdx.x * PB * per;
         float4* dst = reinterpret_cast<float4*>(a.dL_dshs + base);
-        const int rows = min(256, a.P - blockIdx.x * 256);
-        for (int e = threadIdx.x; e < rows * per / 4; e += 256) {
+        const int rows = min(PB, a.P - blockIdx.x * PB);
+        for (int e = threadIdx.x; e < rows * per / 4; e += PB) {
             const int f = e * 4;
             const int gi = f / per, k = f - gi * per;
             const float* d = s_sh + gi * (per + 1) + k;
@@ -328,16 +331,16 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
 int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
     if (a.P <= 0) return 0;
     const int per = a.M * 3;
-    const size_t smem = (size_t)256 * (per + 1) * sizeof(float);
+    const size_t smem = (size_t)PB * (per + 1) * sizeof(float);
     if (a.geom && a.shs && (per % 4) == 0 && smem <= 100 * 1024) {
         static bool attr_done = false;
         if (!attr_done) {
             cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_done = true;
         }
-        preprocess_bwd_kernel<true><<<(a.P + 255) / 256, 256, smem, s>>>(a);
+        preprocess_bwd_kernel<true><<<(a.P + PB - 1) / PB, PB, smem, s>>>(a);
     } else {
-        preprocess_bwd_kernel<false><<<(a.P + 255) / 256, 256, 0, s>>>(a);
+        preprocess_bwd_kernel<false><<<(a.P + PB - 1) / PB, PB, 0, s>>>(a);
     }
     return 0;
 }

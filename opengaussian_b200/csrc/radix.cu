@@ -52,12 +52,16 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
         if (s_h[e]) atomicAdd(&ghist[e], s_h[e]);
 }
 
-template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS, 4) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
+// LOOKBACK = true : onesweep (ticketed tiles, decoupled look-back over tile_state[tile][256]).
+// LOOKBACK = false: plain scatter; the tile's exclusive digit offsets were computed beforehand
+//                   (rs_tile_hist_kernel / emit + rs_tile_scan_kernel) and are read from
+//                   tile_state[digit * ntiles + tile]; ghist holds the digit totals.
+template <typename KeyT, bool LOOKBACK>
+__global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
                                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                              const uint32_t* __restrict__ n_ptr, uint32_t cap, int shift, int bits,
                                                              const uint32_t* __restrict__ ghist /*[256] of this pass*/,
-                                                             uint32_t* tile_state /*[tiles][256]*/, uint32_t* ticket) {
+                                                             uint32_t* tile_state, uint32_t* ticket, uint32_t ntiles) {
     __shared__ uint32_t s_wh[RS_WARPS * RS_RADIX];   // per-warp digit counters -> exclusive warp offsets
     __shared__ uint32_t s_dstart[RS_RADIX];          // local exclusive start of each digit in the tile
     __shared__ uint32_t s_gbase[RS_RADIX];           // global position of local sorted slot 0 of the digit
@@ -66,10 +70,10 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_pass_kernel(const KeyT* __re
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (LOOKBACK && tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int e = tid; e < RS_WARPS * RS_RADIX; e += RS_THREADS) s_wh[e] = 0;
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = LOOKBACK ? s_tile : blockIdx.x;
     const uint32_t n = min(*n_ptr, cap);
     const uint32_t tile_start = tile * (uint32_t)RS_TILE;
     if (tile_start >= n) return;
@@ -92,7 +96,18 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_pass_kernel(const KeyT* __re
         const uint32_t idx = wbase + i * 32 + lane;
         const bool valid = idx < n;
         const uint32_t d = valid ? ((key[i] >> shift) & dmask) : 0xFFFFFFFFu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        // lanes holding the same digit: one ballot per digit bit.  (MATCH.ANY costs one round per
+        // DISTINCT value in the warp, and here nearly all 32 digits differ.)
+        uint32_t peers = __ballot_sync(0xffffffffu, valid);
+        if (!valid) peers = ~peers;
+#pragma unroll
+        for (int bb = 0; bb < 8; bb++) {
+            if (bb < bits) {
+                const bool bit = (d >> bb) & 1u;
+                const uint32_t m = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? m : ~m;
+            }
+        }
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
         if (valid && lane == leader) {
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_pass_kernel(const KeyT* __re
     uint32_t dstart = 0, dbase = 0;
     {
         // warp-level scan of 256 values: each warp scans 32, then warp totals are combined
-        const uint32_t gtot = ghist[tid];
+        const uint32_t gtot = (LOOKBACK || tid < (1 << bits)) ? ghist[tid] : 0u;
         uint32_t a = count, b = gtot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -138,8 +153,13 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_pass_kernel(const KeyT* __re
         dstart = oa + a - count;
         dbase = ob + b - gtot;
     }
-    // ---- decoupled look-back for digit `tid` ----
-    {
+    // ---- global offset of this tile's digit `tid`: precomputed, or decoupled look-back ----
+    if (!LOOKBACK) {
+        const int d = tid;
+        const uint32_t excl = (d < (1 << bits)) ? tile_state[(size_t)d * ntiles + tile] : 0u;
+        s_dstart[d] = dstart;
+        s_gbase[d] = dbase + excl - dstart;
+    } else {
         const int d = tid;
         volatile uint32_t* st = tile_state;
         uint32_t excl = 0;
@@ -229,9 +249,9 @@ static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, co
     uint32_t* va = v0; uint32_t* vb = v1;
     const unsigned grid = (unsigned)((capacity + RS_TILE - 1) / RS_TILE);
     for (int p = 0; p < ps.num; p++) {
-        rs_pass_kernel<KeyT><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_ptr, (uint32_t)capacity, ps.shift[p], ps.bits[p],
-                                                         ghist + p * RS_RADIX, states + (size_t)p * tiles * RS_RADIX,
-                                                         tickets + p);
+        rs_pass_kernel<KeyT, true><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_ptr, (uint32_t)capacity, ps.shift[p],
+                                                               ps.bits[p], ghist + p * RS_RADIX,
+                                                               states + (size_t)p * tiles * RS_RADIX, tickets + p, 0u);
         KeyT* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;
     }
@@ -248,6 +268,129 @@ int radix_sort_pairs_u32(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1,
 int radix_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
                          int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
     return radix_sort_pairs_t<uint16_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile sort (N entries, 16-bit tile ids, <= 2 digit passes): counting passes WITHOUT look-back.
+// With thousands of 4096-item tiles in flight a look-back walk is hundreds of predecessors long
+// (every CTA re-reads their 1 KB state rows through L2); here each pass is
+//   per-tile digit histogram [digit][tile]  (pass 1: written by the emit kernel itself,
+//                                            pass 2: rs_tile_hist_kernel)
+//   -> rs_tile_scan_kernel (one CTA per digit: exclusive scan along the tiles + digit total)
+//   -> rs_pass_kernel<LOOKBACK=false> (rank in shared memory, coalesced scatter).
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_tile_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
+                                                                  uint32_t cap, int shift, int bits, uint32_t ntiles,
+                                                                  uint32_t* __restrict__ cnt /*[1<<bits][ntiles]*/) {
+    __shared__ uint32_t s_h[RS_RADIX];
+    const int tid = threadIdx.x;
+    s_h[tid] = 0;
+    __syncthreads();
+    const uint32_t n = min(*n_ptr, cap);
+    const uint32_t tile = blockIdx.x, start = tile * (uint32_t)RS_TILE;
+    const uint32_t dmask = (1u << bits) - 1u;
+    if (start < n) {
+        const uint32_t end = min(n, start + (uint32_t)RS_TILE);
+        if (sizeof(KeyT) == 2 && end - start == RS_TILE) {   // full tile of 16-bit keys: 16-byte loads
+            const uint4* src = reinterpret_cast<const uint4*>(keys + start);
+            for (int e = tid; e < RS_TILE / 8; e += RS_THREADS) {
+                const uint4 q = __ldg(src + e);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    atomicAdd(&s_h[((w[k] & 0xFFFFu) >> shift) & dmask], 1u);
+                    atomicAdd(&s_h[((w[k] >> 16) >> shift) & dmask], 1u);
+                }
+            }
+        } else {
+            for (uint32_t i = start + tid; i < end; i += RS_THREADS) atomicAdd(&s_h[((uint32_t)keys[i] >> shift) & dmask], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < (1 << bits)) cnt[(size_t)tid * ntiles + tile] = s_h[tid];
+}
+
+// cnt[digit][0..ntiles) -> exclusive scan in place; totals[digit] = sum.  One CTA per digit.
+__global__ void __launch_bounds__(RS_THREADS) rs_tile_scan_kernel(uint32_t* __restrict__ cnt, uint32_t ntiles,
+                                                                  uint32_t* __restrict__ totals /*[256]*/) {
+    __shared__ uint32_t s_w[RS_WARPS];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t* row = cnt + (size_t)blockIdx.x * ntiles;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += RS_THREADS * 4) {
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t idx = base + tid * 4 + i;
+            v[i] = idx < ntiles ? row[idx] : 0u;
+            sum += v[i];
+        }
+        uint32_t a = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, a, o);
+            if (lane >= o) a += t;
+        }
+        if (lane == 31) s_w[warp] = a;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            if (w < warp) woff += s_w[w];
+            total += s_w[w];
+        }
+        uint32_t run = s_carry + woff + (a - sum);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t idx = base + tid * 4 + i;
+            if (idx < ntiles) row[idx] = run;
+            run += v[i];
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) totals[blockIdx.x] = s_carry;
+}
+
+// scratch: [totals 2*256][cnt pass0: 256*ntiles][cnt pass1: 256*ntiles]
+static size_t tile_sort_ntiles(uint64_t capacity) { return (size_t)((capacity + RS_TILE - 1) / RS_TILE); }
+size_t tile_sort_scratch_bytes(uint64_t capacity) {
+    return align_up((size_t)2 * RS_RADIX * 4, 256) + (size_t)2 * RS_RADIX * tile_sort_ntiles(capacity) * 4;
+}
+// digit split of a `bits`-wide tile id: one pass up to 8 bits, else two balanced passes
+void tile_sort_plan(int bits, int* passes, int* bits0) {
+    if (bits <= 8) { *passes = 1; *bits0 = bits; }
+    else { *passes = 2; *bits0 = (bits + 1) / 2; }
+}
+uint32_t* tile_sort_pass0_counts(void* scratch) { return (uint32_t*)((char*)scratch + align_up((size_t)2 * RS_RADIX * 4, 256)); }
+
+// Sorts (k0, v0)[0..*n_ptr) by the low `bits` bits of the 16-bit keys.  The per-tile histogram of the
+// FIRST digit must already be in tile_sort_pass0_counts(scratch) ([digit][ntiles], written by the
+// producer of k0 -- the emit kernel).  Result lands in (k1, v1) after 1 pass, (k0, v0) after 2.
+int tile_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
+                        int bits, void* scratch, cudaStream_t s) {
+    int passes, bits0;
+    tile_sort_plan(bits, &passes, &bits0);
+    const uint32_t ntiles = (uint32_t)tile_sort_ntiles(capacity);
+    uint32_t* totals = (uint32_t*)scratch;
+    uint32_t* cnt0 = tile_sort_pass0_counts(scratch);
+    uint32_t* cnt1 = cnt0 + (size_t)RS_RADIX * ntiles;
+    rs_tile_scan_kernel<<<1 << bits0, RS_THREADS, 0, s>>>(cnt0, ntiles, totals);
+    rs_pass_kernel<uint16_t, false><<<ntiles, RS_THREADS, 0, s>>>(k0, k1, v0, v1, n_ptr, (uint32_t)capacity, 0, bits0, totals,
+                                                                  cnt0, nullptr, ntiles);
+    if (passes == 2) {
+        const int bits1 = bits - bits0;
+        rs_tile_hist_kernel<uint16_t><<<ntiles, RS_THREADS, 0, s>>>(k1, n_ptr, (uint32_t)capacity, bits0, bits1, ntiles, cnt1);
+        rs_tile_scan_kernel<<<1 << bits1, RS_THREADS, 0, s>>>(cnt1, ntiles, totals + RS_RADIX);
+        rs_pass_kernel<uint16_t, false><<<ntiles, RS_THREADS, 0, s>>>(k1, k0, v1, v0, n_ptr, (uint32_t)capacity, bits0, bits1,
+                                                                      totals + RS_RADIX, cnt1, nullptr, ntiles);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "tile_sort_pairs");
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
