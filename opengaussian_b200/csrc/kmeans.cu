@@ -4,14 +4,23 @@
 // :200-201,:223-224,:237-238), one-hot @ feat centroid sums and counts (:82-87,:183-187,:202-205),
 // centres = sums / counts (:208-214), gather + straight-through (:273-275).
 //
-// Arithmetic contract (shared with oracle/kmeans_oracle.c so that ids are bit-exact):
-//   dist2(x, c) = fold_d fmaf(x_d - c_d, x_d - c_d, acc), acc0 = 0, d ascending;
-//   id = lowest index of the minimum (strict '<' scan) -- torch.argmin's tie rule.
-// The contraction is D <= 16 deep: FMA cores, not tensor cores (BASELINE.json north_star).
+// Arithmetic contract (shared with oracle/kmeans_oracle.c so that ids are bit-exact) -- the matmul
+// form that torch.cdist itself uses for these sizes (||x||^2 is constant per point and dropped):
+//   cn_j     = fold_d fmaf(c_jd, c_jd, acc), acc0 = 0, d ascending            (once per centre)
+//   s_j      = fold_d fmaf(x_d, c_jd, acc),  acc0 = 0, d ascending
+//   score_j  = fmaf(-2, s_j, cn_j)           ( = ||x - c_j||^2 - ||x||^2 )
+//   id = lowest index of the minimum score (strict '<' scan) -- torch.argmin's tie rule.
+// The contraction is D <= 16 deep: FMA cores, not tensor cores (BASELINE.json north_star).  One FMA
+// per (point, centre, dimension): the FP32 pipe is the bound at k = 64 (packed FFMA2 occupies it
+// for two cycles, so the direct (x-c)^2 form -- a subtract and an FMA -- would cost twice as much).
+//
+// Throughput: a thread owns FOUR points, held as two packed pairs; per (pair, centre, dimension)
+// the work is one FFMA2 -- bit-identical to the scalar fmaf of the contract -- and one centre row
+// ([c_0..c_D-1, cn], padded to float4s, broadcast LDS.128) is reused by all four points.
 //
 // Fusion: the centroid sums are accumulated in the SAME pass that assigns.  Each warp owns a
 // private [k][D+1] accumulator in shared memory; lanes with equal ids are serialised by their rank
-// inside the __match_any_sync peer group, so every update is a plain LDS/FADD/STS (no shared or
+// inside the peer group (ballot per id bit), so every update is a plain LDS/FADD/STS (no shared or
 // global atomics) and the result is deterministic.  Block partials go to a [grid][k][D+1] scratch
 // that a second tiny kernel reduces in fixed order.
 // HBM-bound at the fine level (k <= 10), FP32-bound at the coarse level (k = 64, D = 9).
@@ -21,68 +30,178 @@ namespace ogs {
 
 #define KM_THREADS 256
 #define KM_MAX_D 16
+#define KM_PPT 4                              // points per thread (two packed pairs)
+#define KM_CTA_POINTS (KM_THREADS * KM_PPT)   // 1024
 
+// ---- TMA bulk copy (global -> shared, completion on an mbarrier) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// Persistent CTAs walk 1024-point tiles.  A tile's rows (a: [1024][Da], b: [1024][Db], contiguous in
+// global memory) are brought into shared memory by ONE cp.async.bulk per array, double-buffered on
+// two mbarriers, so the next tile streams in while the current one is scored; the ragged last tile
+// (or unaligned inputs) is staged by plain cooperative loads.
 template <int D>
 __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
     int64_t N, const float* __restrict__ a, int Da, const float* __restrict__ b, int Db, float scale_b,
     const float* __restrict__ centers, int k, const int64_t* __restrict__ select_ids, int64_t selected,
-    int64_t id_offset, int64_t* __restrict__ ids_out, float* __restrict__ partials /* [grid][k][D+1] or NULL */) {
-    extern __shared__ float smem[];
-    float* s_c = smem;                       // [k][D]
-    float* s_acc = smem + (size_t)k * D;     // [8][k][D+1] (only when partials)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t id_offset, int64_t* __restrict__ ids_out, float* __restrict__ partials /* [grid][k][D+1] or NULL */,
+    int bulk_ok) {
+    constexpr int DP = (D + 1 + 3) & ~3;      // centre row [c_0..c_D-1, ||c||^2] padded to whole float4s
     constexpr int ROW = D + 1;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int tile_floats = KM_CTA_POINTS * D;            // a rows then b rows of one tile
+    float* s_pts = smem;                                  // [2][tile_floats]
+    float* s_c = smem + 2 * (size_t)tile_floats;          // [k][DP]
+    float* s_acc = s_c + (size_t)k * DP;                  // [8][k][D+1] (only when partials)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int e = threadIdx.x; e < k * D; e += KM_THREADS) s_c[e] = centers[e];
+    for (int j = threadIdx.x; j < k; j += KM_THREADS) {
+        float cn = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const float c = centers[j * D + d];
+            s_c[j * DP + d] = c;
+            cn = __fmaf_rn(c, c, cn);
+        }
+        s_c[j * DP + D] = cn;
+#pragma unroll
+        for (int d = D + 1; d < DP; d++) s_c[j * DP + d] = 0.f;
+    }
     if (partials)
         for (int e = threadIdx.x; e < 8 * k * ROW; e += KM_THREADS) s_acc[e] = 0.f;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     float* my_acc = s_acc + (size_t)warp * k * ROW;
+    int id_bits = 0;
+    while ((1 << id_bits) < k) id_bits++;
 
-    const int64_t stride = (int64_t)gridDim.x * KM_THREADS;
-    const int64_t n_round = (N + stride - 1) / stride;
-    for (int64_t it = 0; it < n_round; it++) {
-        const int64_t i = it * stride + (int64_t)blockIdx.x * KM_THREADS + threadIdx.x;
-        bool active = i < N;
-        if (active && select_ids) active = (select_ids[i] == selected);
-        float x[D];
-        int best_j = -1;
-        if (active) {
+    const int64_t n_tiles = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
+    auto tile_is_bulk = [&](int64_t t) { return bulk_ok && (t + 1) * KM_CTA_POINTS <= N; };
+    auto issue = [&](int64_t t, int buf) {   // one thread: arm the barrier and start both bulk copies
+        float* dst = s_pts + (size_t)buf * tile_floats;
+        const uint32_t ba = (uint32_t)(KM_CTA_POINTS * Da * sizeof(float)), bb = (uint32_t)(KM_CTA_POINTS * Db * sizeof(float));
+        mbar_expect_tx(&s_bar[buf], ba + bb);
+        bulk_g2s(dst, a + t * KM_CTA_POINTS * Da, ba, &s_bar[buf]);
+        if (Db > 0) bulk_g2s(dst + KM_CTA_POINTS * Da, b + t * KM_CTA_POINTS * Db, bb, &s_bar[buf]);
+    };
+    uint32_t phases = 0u;   // bit b: parity the next wait on barrier b expects
+    int buf = 0;
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(blockIdx.x)) issue(blockIdx.x, 0);
+
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        const int64_t tn = t + gridDim.x;
+        if (threadIdx.x == 0 && tn < n_tiles && tile_is_bulk(tn)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // buffer was last read through the generic proxy
+            issue(tn, buf ^ 1);
+        }
+        const float* pa = s_pts + (size_t)buf * tile_floats;
+        const float* pb = pa + KM_CTA_POINTS * Da;
+        const int64_t tile_start = t * KM_CTA_POINTS;
+        if (tile_is_bulk(t)) {
+            mbar_wait(&s_bar[buf], (phases >> buf) & 1u);
+            phases ^= 1u << buf;
+        } else {
+            const int64_t rem = N - tile_start < KM_CTA_POINTS ? N - tile_start : KM_CTA_POINTS;
+            float* wa = s_pts + (size_t)buf * tile_floats;
+            for (int64_t e = threadIdx.x; e < rem * Da; e += KM_THREADS) wa[e] = __ldg(a + tile_start * Da + e);
+            for (int64_t e = threadIdx.x; e < rem * Db; e += KM_THREADS) wa[KM_CTA_POINTS * Da + e] = __ldg(b + tile_start * Db + e);
+            __syncthreads();
+        }
+        // warp w owns 128 consecutive points of the tile; slot q of lane l is local point 128 w + 32 q + l
+        const int lbase = warp * (32 * KM_PPT) + lane;
+        const int64_t base = tile_start + lbase;
+        bool active[KM_PPT];
+        float2 X[KM_PPT / 2][D];
+#pragma unroll
+        for (int q = 0; q < KM_PPT; q++) {
+            const int64_t i = base + 32 * q;
+            active[q] = i < N;
+            if (active[q] && select_ids) active[q] = (select_ids[i] == selected);
+            const int li = lbase + 32 * q;
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                x[d] = (d < Da) ? __ldg(a + i * Da + d) : __fmul_rn(__ldg(b + i * Db + (d - Da)), scale_b);
+                float v = 0.f;
+                if (active[q]) v = (d < Da) ? pa[li * Da + d] : __fmul_rn(pb[li * Db + (d - Da)], scale_b);
+                if (q & 1) X[q >> 1][d].y = v; else X[q >> 1][d].x = v;
             }
-            float best = INFINITY;
-            best_j = 0;
-            for (int j = 0; j < k; j++) {
-                const float* c = s_c + j * D;
-                float acc = 0.f;
-#pragma unroll
-                for (int d = 0; d < D; d++) {
-                    const float df = __fsub_rn(x[d], c[d]);
-                    acc = __fmaf_rn(df, df, acc);
-                }
-                if (acc < best) { best = acc; best_j = j; }
-            }
-            ids_out[i] = id_offset + best_j;
         }
+        float2 best[KM_PPT / 2];
+        int best_j[KM_PPT];
+#pragma unroll
+        for (int p = 0; p < KM_PPT / 2; p++) { best[p] = s2(INFINITY); best_j[2 * p] = best_j[2 * p + 1] = 0; }
+#pragma unroll 4
+        for (int j = 0; j < k; j++) {
+            float c[DP];
+#pragma unroll
+            for (int q4 = 0; q4 < DP / 4; q4++) {
+                const float4 tt = reinterpret_cast<const float4*>(s_c + j * DP)[q4];
+                c[4 * q4] = tt.x; c[4 * q4 + 1] = tt.y; c[4 * q4 + 2] = tt.z; c[4 * q4 + 3] = tt.w;
+            }
+#pragma unroll
+            for (int p = 0; p < KM_PPT / 2; p++) {
+                float2 acc = s2(0.f);
+#pragma unroll
+                for (int d = 0; d < D; d++) acc = __ffma2_rn(X[p][d], s2(c[d]), acc);
+                acc = __ffma2_rn(s2(-2.0f), acc, s2(c[D]));
+                if (acc.x < best[p].x) { best[p].x = acc.x; best_j[2 * p] = j; }
+                if (acc.y < best[p].y) { best[p].y = acc.y; best_j[2 * p + 1] = j; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KM_PPT; q++)
+            if (active[q]) ids_out[base + 32 * q] = id_offset + best_j[q];
         if (partials) {
             // conflict-free, atomic-free accumulate: lanes sharing an id go in rank order
-            const unsigned peers = __match_any_sync(0xffffffffu, best_j);
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            int max_rank = active ? rank : 0;
 #pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) max_rank = max(max_rank, __shfl_xor_sync(0xffffffffu, max_rank, m));
-            for (int r = 0; r <= max_rank; r++) {
-                if (active && rank == r) {
-                    float* row = my_acc + best_j * ROW;
-#pragma unroll
-                    for (int d = 0; d < D; d++) row[d] += x[d];
-                    row[D] += 1.0f;
+            for (int q = 0; q < KM_PPT; q++) {
+                unsigned peers = __ballot_sync(0xffffffffu, active[q]);
+                if (!active[q]) peers = ~peers;
+                for (int bb = 0; bb < id_bits; bb++) {
+                    const bool bit = (best_j[q] >> bb) & 1;
+                    const unsigned m = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? m : ~m;
                 }
-                __syncwarp();
+                const int rank = __popc(peers & ((1u << lane) - 1u));
+                int max_rank = active[q] ? rank : 0;
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) max_rank = max(max_rank, __shfl_xor_sync(0xffffffffu, max_rank, m));
+                for (int r = 0; r <= max_rank; r++) {
+                    if (active[q] && rank == r) {
+                        float* row = my_acc + best_j[q] * ROW;
+#pragma unroll
+                        for (int d = 0; d < D; d++) row[d] += (q & 1) ? X[q >> 1][d].y : X[q >> 1][d].x;
+                        row[D] += 1.0f;
+                    }
+                    __syncwarp();
+                }
             }
         }
+        __syncthreads();   // everyone is done with s_pts[buf] before it is refilled two tiles from now
     }
     if (partials) {
         __syncthreads();
@@ -113,21 +232,24 @@ static int launch_assign_d(int64_t N, const float* a, int Da, const float* b, in
                            const float* centers, int k, const int64_t* select_ids, int64_t selected,
                            int64_t id_offset, int64_t* ids_out, float* sums, float* counts, cudaStream_t s) {
     const bool fuse = (sums != nullptr) || (counts != nullptr);
-    size_t smem = (size_t)k * D * sizeof(float);
+    size_t smem = (size_t)2 * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
     if (fuse) smem += (size_t)8 * k * (D + 1) * sizeof(float);
-    if (smem > 200 * 1024) { set_error("kmeans_assign: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
+    if (smem > 220 * 1024) { set_error("kmeans_assign: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    int64_t want = (N + KM_THREADS - 1) / KM_THREADS;
-    int grid = (int)(want < (int64_t)OGS_NUM_SMS * 4 ? want : (int64_t)OGS_NUM_SMS * 4);
+    // bulk copies need 16-byte aligned sources and sizes: tile strides are multiples of 4096 bytes
+    const int bulk_ok = (((uintptr_t)a & 15) == 0 && (Db == 0 || ((uintptr_t)b & 15) == 0)) ? 1 : 0;
+    int64_t want = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
+    const int per_sm = smem > 110 * 1024 ? 1 : 2;
+    int grid = (int)(want < (int64_t)OGS_NUM_SMS * per_sm ? want : (int64_t)OGS_NUM_SMS * per_sm);
     if (grid < 1) grid = 1;
     float* partials = nullptr;
     if (fuse) OGS_CUDA(cudaMallocAsync((void**)&partials, (size_t)grid * k * (D + 1) * sizeof(float), s));
     kmeans_assign_kernel<D><<<grid, KM_THREADS, smem, s>>>(N, a, Da, b, Db, scale_b, centers, k, select_ids, selected,
-                                                           id_offset, ids_out, partials);
+                                                           id_offset, ids_out, partials, bulk_ok);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && fuse) {
         const int tot = k * (D + 1);

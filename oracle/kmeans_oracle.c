@@ -9,11 +9,14 @@
  * tests/golden/make_kmeans_golden.py runs it (torch CPU) and commits centres + ids as
  * fixtures; tests/test_kmeans_oracle.py checks this restatement against those fixtures.
  *
- * Arithmetic contract shared with the CUDA kernels (so ids are bit-exact):
- *   dist2(x, c) = fold_{d=0..D-1} fmaf(x_d - c_d, x_d - c_d, acc), acc0 = 0   (fp32)
- *   id = lowest index of the minimum (strict '<' scan) -- torch.argmin tie rule (:182).
- *   The reference takes sqrt of a matmul-form distance (torch.cdist, :51-54); sqrt and the
- *   algebraic form do not change the argmin except on near-ties, which the pin test counts.
+ * Arithmetic contract shared with the CUDA kernels (so ids are bit-exact) -- the matmul form
+ * that torch.cdist (:51-54) itself takes for these sizes, with ||x||^2 (constant per point) dropped:
+ *   cn_j    = fold_{d=0..D-1} fmaf(c_jd, c_jd, acc), acc0 = 0                  (fp32)
+ *   s_j     = fold_{d=0..D-1} fmaf(x_d, c_jd, acc),  acc0 = 0
+ *   score_j = fmaf(-2, s_j, cn_j)        ( = ||x - c_j||^2 - ||x||^2 )
+ *   id = lowest index of the minimum score (strict '<' scan) -- torch.argmin tie rule (:182).
+ *   The reference takes sqrt(clamp(.)) of the same expansion evaluated by a BLAS GEMM in an
+ *   unspecified order; sqrt does not change the argmin except on near-ties, which the pin test counts.
  *   A point is the concatenation [a (Da floats) | b (Db floats) * scale_b] -- the reference
  *   builds cat(_ins_feat, _xyz * pos_weight) (:254-257); the product is a single fp32 multiply.
  *   Centroid sums: points are split into consecutive groups of `group` points; inside a
@@ -43,6 +46,12 @@ int ogs_oracle_kmeans_assign(int64_t N, const float* a, int Da, const float* b, 
     const int D = Da + Db;
     float x[64];
     if (D > 64) return -1;
+    float* cn = (float*)malloc(sizeof(float) * (size_t)(k > 0 ? k : 1));
+    for (int j = 0; j < k; j++) {
+        float acc = 0.f;
+        for (int d = 0; d < D; d++) acc = fmaf(centers[j * D + d], centers[j * D + d], acc);
+        cn[j] = acc;
+    }
     for (int64_t i = 0; i < N; i++) {
         if (select_ids && select_ids[i] != selected) continue;
         for (int d = 0; d < D; d++) x[d] = point_coord(a, Da, b, Db, scale_b, i, d);
@@ -50,14 +59,13 @@ int ogs_oracle_kmeans_assign(int64_t N, const float* a, int Da, const float* b, 
         int best_j = 0;
         for (int j = 0; j < k; j++) {
             float acc = 0.f;
-            for (int d = 0; d < D; d++) {
-                float df = x[d] - centers[j * D + d];
-                acc = fmaf(df, df, acc);
-            }
+            for (int d = 0; d < D; d++) acc = fmaf(x[d], centers[j * D + d], acc);
+            acc = fmaf(-2.0f, acc, cn[j]);
             if (acc < best) { best = acc; best_j = j; }
         }
         ids_out[i] = id_offset + best_j;
     }
+    free(cn);
     return 0;
 }
 
