@@ -50,6 +50,22 @@ def projection_matrix(fovx: float, fovy: float, znear: float = ZNEAR, zfar: floa
     return P
 
 
+def camera_from_RT(R, T, FoVx: float, FoVy: float, W: int, H: int) -> SynthCamera:
+    """Camera from the (R, T) pair the reference's dataset readers store (R = camera-to-world rotation,
+    T = world-to-camera translation), composed as scene/cameras.py:71-78 does: transposed world-view
+    (utils/graphics_utils.py getWorld2View2 with trans = 0, scale = 1), transposed projection, their
+    product and the camera centre."""
+    R = torch.as_tensor(R, dtype=torch.float64)
+    T = torch.as_tensor(T, dtype=torch.float64)
+    V = torch.eye(4, dtype=torch.float64)
+    V[:3, :3] = R.t()
+    V[:3, 3] = T
+    wvt = V.t().contiguous()
+    full = (wvt @ projection_matrix(FoVx, FoVy).t()).contiguous()
+    center = torch.linalg.inv(wvt)[3, :3]
+    return SynthCamera(W, H, FoVx, FoVy, wvt.float(), full.float(), center.float())
+
+
 def look_at(eye, target, W: int, H: int, fovx: float, up=(0.0, 0.0, 1.0)) -> SynthCamera:
     """COLMAP-style camera (x right, y down, z forward) at `eye` looking at `target`."""
     eye = torch.as_tensor(eye, dtype=torch.float64)

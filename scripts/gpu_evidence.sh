@@ -1,0 +1,18 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): parity tests, the bench line, the ncu launch list of the same
+# bench command, and one `ncu --set full` capture of the blend / preprocess / sort / k-means kernels.
+# Everything lands in gpurun_out/; scripts/summarize_profiles.py turns it into profiles/.
+set -u
+TAG=${1:-r1}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" 
+python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+python bench.py --steps 3 --warmup 3 --no-kmeans --no-cpu-baseline > /dev/null 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-kmeans --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+python scripts/quick_bench.py --iters 3 --prof 0 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"blend|preprocess|rs_pass|emit|scan_gather|rs_tile|ranges" -s 60 -c 14 \
+    -o gpurun_out/${TAG}_raster python scripts/quick_bench.py --iters 3 --prof 0 > gpurun_out/${TAG}_ncu_raster.log 2>&1; echo "ncu raster rc=$?"
+python scripts/kmeans_bench.py --iters 2 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:kmeans_assign -s 3 -c 1 \
+    -o gpurun_out/${TAG}_kmeans python scripts/kmeans_bench.py --iters 2 > gpurun_out/${TAG}_ncu_kmeans.log 2>&1; echo "ncu kmeans rc=$?"

@@ -145,3 +145,62 @@ def test_raster_oracle_structure():
     st0 = orc.forward(to_oracle_cam(cam), g["means3D"][:0], g["opacities"][:0], g["scales"][:0], g["rotations"][:0],
                       shs=g["shs"][:0], bg=np.array([0.2, 0.4, 0.6], np.float32))
     assert st0.N == 0 and np.allclose(st0.color[1], 0.4)
+
+
+# ---- the reference's own Python code for pieces of the rasterizer path (tests/golden/make_raster_golden.py) ----
+RGOLD = os.path.join(os.path.dirname(__file__), "golden", "raster_pieces_golden.npz")
+
+
+def _raster_golden_inputs():
+    spec = importlib.util.spec_from_file_location("mrg", os.path.join(os.path.dirname(RGOLD), "make_raster_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.inputs()
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_raster_oracle_sh_colours_vs_reference_eval_sh(deg):
+    """oracle SH -> RGB (+0.5, clamp at 0, clamp mask) == utils/sh_utils.py::eval_sh as used at
+    gaussian_renderer/__init__.py:90-96, on the committed golden vectors."""
+    from opengaussian_b200 import synth
+    inp, gold = _raster_golden_inputs(), np.load(RGOLD)
+    cam = synth.look_at(tuple(float(v) for v in inp["campos"]), (0.0, 0.0, 0.0), 640, 480, 1.3)
+    oc = to_oracle_cam(cam, sh_degree=deg)
+    P = inp["xyz"].shape[0]
+    radii, xy, depth, cov3D, co, rgb, clamped, tiles = orc.preprocess(
+        oc, inp["xyz"], np.full((P, 1), 0.5, np.float32), inp["scales"], inp["rot"], None, inp["shs"])
+    vis = radii > 0
+    assert vis.mean() > 0.8
+    assert np.abs(rgb[vis] - gold[f"rgb_deg{deg}"][vis]).max() <= 2e-6
+    unclamped = gold[f"rgb_unclamped_deg{deg}"][vis]
+    sure = np.abs(unclamped) > 1e-5                       # away from the clamp threshold
+    assert np.array_equal((clamped[vis] != 0)[sure], (unclamped < 0)[sure])
+
+
+@pytest.mark.parametrize("mod", [1.0, 0.7])
+def test_raster_oracle_cov3d_vs_reference_build_covariance(mod):
+    """oracle cov3D (scale_modifier * scale, quaternion (r,x,y,z), packing xx,xy,xz,yy,yz,zz) ==
+    utils/general_utils.py build_scaling_rotation / strip_symmetric (scene/gaussian_model.py:63-67)."""
+    from opengaussian_b200 import synth
+    inp, gold = _raster_golden_inputs(), np.load(RGOLD)
+    cam = synth.look_at(tuple(float(v) for v in inp["campos"]), (0.0, 0.0, 0.0), 640, 480, 1.3)
+    oc = to_oracle_cam(cam, scale_modifier=mod)
+    P = inp["xyz"].shape[0]
+    radii, xy, depth, cov3D, co, rgb, clamped, tiles = orc.preprocess(
+        oc, inp["xyz"], np.full((P, 1), 0.5, np.float32), inp["scales"], inp["rot"], None, inp["shs"])
+    vis = radii > 0
+    want = gold[f"cov3D_mod{mod}"][vis]
+    assert np.abs(cov3D[vis] - want).max() <= 1e-6 * np.abs(want).max() + 1e-9
+
+
+def test_camera_matrices_vs_reference_graphics_utils():
+    """synth.camera_from_RT == scene/cameras.py:71-78 built from utils/graphics_utils.py (golden)."""
+    from opengaussian_b200 import synth
+    inp, gold = _raster_golden_inputs(), np.load(RGOLD)
+    for i, (R, T, fx, fy) in enumerate(inp["cams"]):
+        c = synth.camera_from_RT(R, T, fx, fy, 640, 480)
+        assert np.abs(c.world_view_transform.numpy() - gold[f"cam{i}_world_view"]).max() <= 1e-6
+        assert np.abs(c.full_proj_transform.numpy() - gold[f"cam{i}_full_proj"]).max() <= 2e-5
+        assert np.abs(c.camera_center.numpy() - gold[f"cam{i}_center"]).max() <= 1e-5
+        assert abs(c.tanfovx - gold[f"cam{i}_tan"][0]) <= 1e-12 and abs(c.tanfovy - gold[f"cam{i}_tan"][1]) <= 1e-12
+        assert np.abs(synth.projection_matrix(fx, fy).t().float().numpy() - gold[f"cam{i}_proj"]).max() <= 1e-6

@@ -270,3 +270,27 @@ def test_medium_scene_properties():
     a = out["alpha"].cpu().numpy()
     assert a.min() >= 0.0 and a.max() <= 1.0
     assert np.allclose(a, 1.0 - out["final_T"].cpu().numpy(), atol=1e-7)
+
+
+@pytest.mark.parametrize("deg", [0, 3])
+def test_cuda_sh_colours_vs_reference_eval_sh(deg):
+    """CUDA preprocess SH colours against the golden vectors made by the reference's own
+    utils/sh_utils.py::eval_sh (tests/golden/make_raster_golden.py) -- no oracle in between."""
+    import importlib.util
+    import os
+    from opengaussian_b200 import synth
+    from opengaussian_b200.debug import forward_with_state
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("mrg", os.path.join(gdir, "make_raster_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    inp, gold = m.inputs(), np.load(os.path.join(gdir, "raster_pieces_golden.npz"))
+    cam = synth.look_at(tuple(float(v) for v in inp["campos"]), (0.0, 0.0, 0.0), 640, 480, 1.3)
+    rs = _settings(cam, [0.0, 0.0, 0.0], sh_degree=deg)
+    t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    P = inp["xyz"].shape[0]
+    st = forward_with_state(rs, t(inp["xyz"]), torch.full((P, 1), 0.5, device="cuda"), shs=t(inp["shs"]),
+                            scales=t(inp["scales"]), rotations=t(inp["rot"]))
+    vis = (st["radii"] > 0).cpu().numpy()
+    assert vis.mean() > 0.8
+    assert np.abs(st["rgb"].cpu().numpy()[vis] - gold[f"rgb_deg{deg}"][vis]).max() <= 2e-6
