@@ -25,12 +25,11 @@
 //  * GEOM=false specialisation (OpenGaussian stages 1-2 detach geometry, train.py:431-436): only
 //    w = alpha T and dL/dc are evaluated.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ogs {
 
 #define BB 64            // Gaussians per backward batch
-#define BWD_THREADS 128
-#define BWD_WARPS 4
 
 template <int CUR, int M>
 struct HalvingReduce {
@@ -80,40 +79,48 @@ struct ChunkReduceStore {
 
 int blend_bwd_stride(int C, int geom) { return geom ? C + 7 : C; }
 
-template <int C, bool GEOM>
-__global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) {
+// PAIRS packed pixel pairs per lane: the warp's block is 8 x (8 * PAIRS) pixels and a 16x16 tile takes
+// 4 / PAIRS warps.  More pixels per lane amortise the cross-lane reduction and the per-entry loop
+// overhead (about half of the instructions at PAIRS = 1) at the price of coarser culling.
+template <int C, bool GEOM, int PAIRS>
+__global__ void __launch_bounds__(128 / PAIRS) blend_bwd_kernel(BlendBwdArgs a) {
+    constexpr int BWD_THREADS = 128 / PAIRS, BWD_WARPS = 4 / PAIRS, NPX = 2 * PAIRS;
     constexpr int V = GEOM ? C + 7 : C;
     constexpr int CH = (C + 1 + 3) & ~3;  // colours + depth, padded to float4
-    extern __shared__ float s_dyn[];      // [BWD_WARPS][BB][V] per-warp sums
-    __shared__ float4 s_a[BB];
-    __shared__ float2 s_b[BB];
-    __shared__ __align__(16) float s_ch[BB * CH];
-    __shared__ uint32_t s_id[BB];
+    // everything is double-buffered by batch parity: batch b-1 is staged while batch b is traversed,
+    // and batch b is flushed (after the ONE barrier per batch) while the fast warps start on b-1
+    extern __shared__ float s_dyn[];      // [2][BWD_WARPS][BB][V] per-warp sums
+    __shared__ float4 s_a2[2][BB];
+    __shared__ float2 s_b2[2][BB];
+    __shared__ __align__(16) float s_ch2[2][BB * CH];
+    __shared__ uint32_t s_id2[2][BB];
     __shared__ int s_max_last;
 
     const int gx = (a.W + 15) / 16;
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bxi = blockIdx.x * 16 + (warp & 1) * 8, byi = blockIdx.y * 16 + (warp >> 1) * 8;
+    const int bxi = blockIdx.x * 16 + (warp & 1) * 8, byi = blockIdx.y * 16 + (warp >> 1) * 8 * PAIRS;
     const int px = bxi + (lane & 7);
     const float pxf = (float)px;
     const float bx0 = (float)bxi, by0 = (float)byi;
     const size_t HW = (size_t)a.H * a.W;
     const uint2 range = a.ranges[tile];
 
-    // per-lane state of the pixel pair (.x: row y, .y: row y + 4)
-    float2 T2, S2 = s2(0.f), om2 = s2(1.f), prod2 = s2(0.f), gd2 = s2(0.f), ga2 = s2(0.f), tfbg2 = s2(0.f), npy;
-    float2 g2[C];
-    int last[2];
-    {
+    // per-lane state of the pixel pairs (.x: row y + 8 p, .y: row y + 8 p + 4)
+    float2 T2[PAIRS], S2[PAIRS], om2[PAIRS], prod2[PAIRS], gd2[PAIRS], ga2[PAIRS], tfbg2[PAIRS], npy[PAIRS];
+    float2 g2[PAIRS][C];
+    int last[NPX];
+#pragma unroll
+    for (int p = 0; p < PAIRS; p++) {
         float Tf[2], gdv[2] = {0.f, 0.f}, gav[2] = {0.f, 0.f}, bgd[2] = {0.f, 0.f};
         float gv[2][C];
+        const int y0 = byi + (lane >> 3) + 8 * p;
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const int py = byi + (lane >> 3) + 4 * k;
+            const int py = y0 + 4 * k;
             const bool inside = px < a.W && py < a.H;
             const size_t pix = (size_t)py * a.W + px;
-            last[k] = inside ? (int)a.n_contrib[pix] : 0;
+            last[2 * p + k] = inside ? (int)a.n_contrib[pix] : 0;
             Tf[k] = inside ? a.final_T[pix] : 0.f;
 #pragma unroll
             for (int c = 0; c < C; c++) {
@@ -125,54 +132,67 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) 
                 gav[k] = (inside && a.dL_dalpha) ? __ldg(a.dL_dalpha + pix) : 0.f;
             }
         }
-        npy = make_float2(-(float)(byi + (lane >> 3)), -(float)(byi + (lane >> 3) + 4));
-        T2 = make_float2(Tf[0], Tf[1]);
+        npy[p] = make_float2(-(float)y0, -(float)(y0 + 4));
+        T2[p] = make_float2(Tf[0], Tf[1]);
+        S2[p] = s2(0.f); om2[p] = s2(1.f); prod2[p] = s2(0.f);
 #pragma unroll
-        for (int c = 0; c < C; c++) g2[c] = make_float2(gv[0][c], gv[1][c]);
-        if (GEOM) {
-            gd2 = make_float2(gdv[0], gdv[1]);
-            ga2 = make_float2(gav[0], gav[1]);
-            tfbg2 = make_float2(Tf[0] * bgd[0], Tf[1] * bgd[1]);
-        }
+        for (int c = 0; c < C; c++) g2[p][c] = make_float2(gv[0][c], gv[1][c]);
+        gd2[p] = make_float2(gdv[0], gdv[1]);
+        ga2[p] = make_float2(gav[0], gav[1]);
+        tfbg2[p] = make_float2(Tf[0] * bgd[0], Tf[1] * bgd[1]);
     }
 
     // block / warp maxima of the last contributor
     if (threadIdx.x == 0) s_max_last = 0;
-    for (int e = threadIdx.x; e < BWD_WARPS * BB * V; e += BWD_THREADS) s_dyn[e] = 0.f;
+    for (int e = threadIdx.x; e < 2 * BWD_WARPS * BB * V; e += BWD_THREADS) s_dyn[e] = 0.f;
     __syncthreads();
-    int wmax = max(last[0], last[1]);
+    int wmax = 0;
+#pragma unroll
+    for (int k = 0; k < NPX; k++) wmax = max(wmax, last[k]);
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, m));
     if (lane == 0 && wmax > 0) atomicMax(&s_max_last, wmax);
     __syncthreads();
     const int max_last = s_max_last;
     if (max_last == 0) return;
-    float* my_acc = s_dyn + (size_t)warp * BB * V;
-
-    for (int b = (max_last - 1) / BB; b >= 0; b--) {
+    // ---- stage one batch (pre-scaled records, colours + depth) into buffer `sb` ----
+    auto stage = [&](int b, int sb) {
         const int start = b * BB;
         const int n = min(BB, max_last - start);
-        // ---- stage the batch (pre-scaled records, colours + depth) ----
-        if (threadIdx.x < n) {
-            const uint32_t gid = a.point_list[range.x + start + threadIdx.x];
-            s_id[threadIdx.x] = gid;
+        for (int t = threadIdx.x; t < n; t += BWD_THREADS) {
+            const uint32_t gid = a.point_list[range.x + start + t];
+            s_id2[sb][t] = gid;
             const float4 r1 = __ldg(a.rec1 + gid);
-            ogs_stage(__ldg(a.rec0 + gid), r1, s_a[threadIdx.x], s_b[threadIdx.x]);
-            s_ch[threadIdx.x * CH + C] = r1.z;
+            ogs_stage(__ldg(a.rec0 + gid), r1, s_a2[sb][t], s_b2[sb][t]);
+            s_ch2[sb][t * CH + C] = r1.z;
         }
         for (int e = threadIdx.x; e < n * C; e += BWD_THREADS) {
             const int j = e / C, c = e - j * C;
             const uint32_t gid = a.point_list[range.x + start + j];
-            s_ch[j * CH + c] = (c < 3) ? __ldg(a.base + 3 * (size_t)gid + c) : __ldg(a.extra + (size_t)(C - 3) * gid + (c - 3));
+            s_ch2[sb][j * CH + c] = (c < 3) ? __ldg(a.base + 3 * (size_t)gid + c) : __ldg(a.extra + (size_t)(C - 3) * gid + (c - 3));
         }
-        __syncthreads();
+    };
+    const int b_first = (max_last - 1) / BB;
+    stage(b_first, b_first & 1);
+    __syncthreads();
+
+    for (int b = b_first; b >= 0; b--) {
+        const int start = b * BB;
+        const int n = min(BB, max_last - start);
+        const int sb = b & 1;
+        if (b > 0) stage(b - 1, sb ^ 1);     // its loads are in flight while this batch is traversed
+        const float4* s_a = s_a2[sb];
+        const float2* s_b = s_b2[sb];
+        const float* s_ch = s_ch2[sb];
+        float* acc_b = s_dyn + (size_t)sb * BWD_WARPS * BB * V;
+        float* my_acc = acc_b + (size_t)warp * BB * V;
         // ---- traverse back to front ----
         if (start < wmax) {
             const int nw = min(n, wmax - start);
             for (int grp = ((nw - 1) >> 5) << 5; grp >= 0; grp -= 32) {
                 const int idx = grp + lane;
                 bool hit = false;
-                if (idx < nw) hit = ogs_rect_hit_s(s_a[idx], s_b[idx], bx0, by0, bx0 + 7.0f, by0 + 7.0f);
+                if (idx < nw) hit = ogs_rect_hit_s(s_a[idx], s_b[idx], bx0, by0, bx0 + 7.0f, by0 + (float)(8 * PAIRS - 1));
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
                 while (mask) {
                     const int bit = 31 - __clz(mask);
@@ -183,85 +203,110 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(BlendBwdArgs a) 
                     const float2 rb = s_b[j];
                     const float dx = ra.x - pxf;
                     const float adx = __fmul_rn(__fmul_rn(ra.z, dx), dx), bdx = __fmul_rn(ra.w, dx);
-                    float2 dy;
-                    const float2 pw = ogs_pair_power(adx, bdx, rb.x, ra.y, npy, dy);
-                    const float2 G = make_float2(ogs_ex2(pw.x), ogs_ex2(pw.y));
-                    float2 al = __fmul2_rn(s2(rb.y), G);
-                    al.x = fminf(0.99f, al.x);
-                    al.y = fminf(0.99f, al.y);
-                    const bool oka = pos < last[0] && pw.x <= 0.0f && al.x >= (1.0f / 255.0f);
-                    const bool okb = pos < last[1] && pw.y <= 0.0f && al.y >= (1.0f / 255.0f);
-                    if (!__any_sync(0xffffffffu, oka || okb)) continue;
+                    float2 dy[PAIRS], G[PAIRS], al[PAIRS];
+                    bool ok[NPX];
+                    bool any = false;
+#pragma unroll
+                    for (int p = 0; p < PAIRS; p++) {
+                        const float2 pw = ogs_pair_power(adx, bdx, rb.x, ra.y, npy[p], dy[p]);
+                        G[p] = make_float2(ogs_ex2(pw.x), ogs_ex2(pw.y));
+                        al[p] = __fmul2_rn(s2(rb.y), G[p]);
+                        al[p].x = fminf(0.99f, al[p].x);
+                        al[p].y = fminf(0.99f, al[p].y);
+                        ok[2 * p] = pos < last[2 * p] && pw.x <= 0.0f && al[p].x >= (1.0f / 255.0f);
+                        ok[2 * p + 1] = pos < last[2 * p + 1] && pw.y <= 0.0f && al[p].y >= (1.0f / 255.0f);
+                        any = any || ok[2 * p] || ok[2 * p + 1];
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;
                     float chv[CH];
 #pragma unroll
                     for (int q = 0; q < CH / 4; q++) {
                         const float4 t = reinterpret_cast<const float4*>(s_ch + j * CH)[q];
                         chv[4 * q] = t.x; chv[4 * q + 1] = t.y; chv[4 * q + 2] = t.z; chv[4 * q + 3] = t.w;
                     }
-                    const float2 alm = make_float2(oka ? al.x : 0.f, okb ? al.y : 0.f);
-                    const float2 om = __fadd2_rn(s2(1.0f), make_float2(-alm.x, -alm.y));
-                    const float2 inv = make_float2(ogs_rcp(om.x), ogs_rcp(om.y));
-                    T2 = __fmul2_rn(T2, inv);
-                    const float2 w = __fmul2_rn(alm, T2);
+                    // packed sums over the lane's pairs; .x + .y is taken once at the end
+                    float2 vc[C], vd = s2(0.f), su2 = s2(0.f), suy2 = s2(0.f), suyy2 = s2(0.f);
+#pragma unroll
+                    for (int c = 0; c < C; c++) vc[c] = s2(0.f);
+#pragma unroll
+                    for (int p = 0; p < PAIRS; p++) {
+                        const float2 alm = make_float2(ok[2 * p] ? al[p].x : 0.f, ok[2 * p + 1] ? al[p].y : 0.f);
+                        const float2 om = __fadd2_rn(s2(1.0f), make_float2(-alm.x, -alm.y));
+                        const float2 inv = make_float2(ogs_rcp(om.x), ogs_rcp(om.y));
+                        T2[p] = __fmul2_rn(T2[p], inv);
+                        const float2 w = __fmul2_rn(alm, T2[p]);
+#pragma unroll
+                        for (int c = 0; c < C; c++) vc[c] = __ffma2_rn(w, g2[p][c], vc[c]);
+                        if (GEOM) {
+                            float2 dot = __ffma2_rn(s2(chv[0]), g2[p][0], ga2[p]);
+#pragma unroll
+                            for (int c = 1; c < C; c++) dot = __ffma2_rn(s2(chv[c]), g2[p][c], dot);
+                            dot = __ffma2_rn(s2(chv[C]), gd2[p], dot);
+                            S2[p] = __ffma2_rn(om2[p], S2[p], prod2[p]);   // S <- a_prev d_prev + (1 - a_prev) S
+                            prod2[p] = __fmul2_rn(alm, dot);
+                            om2[p] = om;
+                            const float2 dS = __fadd2_rn(dot, make_float2(-S2[p].x, -S2[p].y));
+                            const float2 dLda = __ffma2_rn(make_float2(-tfbg2[p].x, -tfbg2[p].y), inv, __fmul2_rn(dS, T2[p]));
+                            const float2 Gm = make_float2(ok[2 * p] ? G[p].x : 0.f, ok[2 * p + 1] ? G[p].y : 0.f);
+                            const float2 u = __fmul2_rn(Gm, dLda);
+                            const float2 uy = __fmul2_rn(u, dy[p]);
+                            su2 = __fadd2_rn(su2, u);
+                            suy2 = __fadd2_rn(suy2, uy);
+                            suyy2 = __ffma2_rn(uy, dy[p], suyy2);
+                            vd = __ffma2_rn(w, gd2[p], vd);
+                        }
+                    }
                     float v[V];
 #pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const float2 t = __fmul2_rn(w, g2[c]);
-                        v[c] = t.x + t.y;
-                    }
+                    for (int c = 0; c < C; c++) v[c] = vc[c].x + vc[c].y;
                     if (GEOM) {
-                        float2 dot = __ffma2_rn(s2(chv[0]), g2[0], ga2);
-#pragma unroll
-                        for (int c = 1; c < C; c++) dot = __ffma2_rn(s2(chv[c]), g2[c], dot);
-                        dot = __ffma2_rn(s2(chv[C]), gd2, dot);
-                        S2 = __ffma2_rn(om2, S2, prod2);          // S <- a_prev d_prev + (1 - a_prev) S
-                        prod2 = __fmul2_rn(alm, dot);
-                        om2 = om;
-                        const float2 dS = __fadd2_rn(dot, make_float2(-S2.x, -S2.y));
-                        const float2 dLda = __ffma2_rn(make_float2(-tfbg2.x, -tfbg2.y), inv, __fmul2_rn(dS, T2));
-                        const float2 Gm = make_float2(oka ? G.x : 0.f, okb ? G.y : 0.f);
-                        const float2 u = __fmul2_rn(Gm, dLda);
-                        const float2 uy = __fmul2_rn(u, dy);
-                        const float2 uyy = __fmul2_rn(uy, dy);
-                        const float2 wd = __fmul2_rn(w, gd2);
-                        const float su = u.x + u.y, suy = uy.x + uy.y;
+                        const float su = su2.x + su2.y, suy = suy2.x + suy2.y;
                         const float sux = su * dx;
-                        v[C + 0] = wd.x + wd.y;
+                        v[C + 0] = vd.x + vd.y;
                         v[C + 1] = su;
                         v[C + 2] = sux;
                         v[C + 3] = suy;
                         v[C + 4] = sux * dx;
                         v[C + 5] = suy * dx;
-                        v[C + 6] = uyy.x + uyy.y;
+                        v[C + 6] = suyy2.x + suyy2.y;
                     }
                     ChunkReduceStore<V, 0>::run(v, lane, my_acc + j * V);
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // batch b fully traversed by every warp; batch b-1 fully staged
         // ---- flush: sum the warp rows, one red per value per (tile, Gaussian) ----
         for (int e = threadIdx.x; e < n * V; e += BWD_THREADS) {
             float sum = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < BWD_WARPS; w8++) {
-                sum += s_dyn[(size_t)w8 * BB * V + e];
-                s_dyn[(size_t)w8 * BB * V + e] = 0.f;
+                sum += acc_b[(size_t)w8 * BB * V + e];
+                acc_b[(size_t)w8 * BB * V + e] = 0.f;
             }
             if (sum != 0.f) {
                 const int j = e / V, k = e - j * V;
-                atomicAdd(a.acc + (size_t)s_id[j] * a.stride + k, sum);
+                atomicAdd(a.acc + (size_t)s_id2[sb][j] * a.stride + k, sum);
             }
         }
-        __syncthreads();
     }
 }
 
 template <int C, bool GEOM>
 static int launch_cg(const BlendBwdArgs& a, cudaStream_t s) {
     constexpr int V = GEOM ? C + 7 : C;
-    const size_t smem = (size_t)BWD_WARPS * BB * V * sizeof(float);
+    // two pairs per lane pay off while the pixel state fits the register file comfortably (measured: C <= 9)
+    static const int env_pairs = getenv("OGS_BWD_PAIRS") ? atoi(getenv("OGS_BWD_PAIRS")) : 0;  // tuning knob
+    const int pairs = env_pairs ? env_pairs : (C <= 9 ? 2 : 1);
     dim3 grid((a.W + 15) / 16, (a.H + 15) / 16);
-    blend_bwd_kernel<C, GEOM><<<grid, BWD_THREADS, smem, s>>>(a);
+    const size_t smem = (size_t)2 * (4 / (pairs == 2 ? 2 : 1)) * BB * V * sizeof(float);
+    static bool attr_done[2] = {false, false};
+    if (smem > 24 * 1024 && !attr_done[pairs == 2]) {   // static + dynamic shared memory may pass the 48 KB default
+        if (pairs == 2) OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        else OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done[pairs == 2] = true;
+    }
+    if (pairs == 2) blend_bwd_kernel<C, GEOM, 2><<<grid, 64, smem, s>>>(a);
+    else blend_bwd_kernel<C, GEOM, 1><<<grid, 128, smem, s>>>(a);
     return 0;
 }
 
