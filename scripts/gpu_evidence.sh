@@ -10,8 +10,9 @@ python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_o
 python bench.py --steps 3 --warmup 3 --no-kmeans --no-cpu-baseline > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-kmeans --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+# quick_bench launches 18 ogs:: kernels per frame; skip 4 frames, capture 2 whole frames
 python scripts/quick_bench.py --iters 3 --prof 0 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"blend|preprocess|rs_pass|emit|scan_gather|rs_tile|ranges" -s 60 -c 14 \
+ncu --set full --clock-control none --import-source on -k regex:"ogs::" -s 72 -c 36 \
     -o gpurun_out/${TAG}_raster python scripts/quick_bench.py --iters 3 --prof 0 > gpurun_out/${TAG}_ncu_raster.log 2>&1; echo "ncu raster rc=$?"
 python scripts/kmeans_bench.py --iters 2 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:kmeans_assign -s 3 -c 1 \

@@ -22,7 +22,7 @@ METRICS = [
     ("launch__registers_per_thread", "regs"),
     ("dram__bytes_read.sum", "dram_read_MB"),
     ("dram__bytes_write.sum", "dram_write_MB"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "pipe_fma_pct"),
