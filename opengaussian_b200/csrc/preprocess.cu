@@ -11,9 +11,12 @@
 // defaults (-prec-div=true -prec-sqrt=true).
 //
 // Memory behaviour (HBM-bound): one thread per Gaussian; a warp reads
-// contiguous 384 B (means3D/scales), 512 B (rotations) slabs; the 192 B/Gaussian SH block is staged
-// through shared memory with coalesced 16-byte loads, then consumed from a conflict-free padded
-// layout.  Outputs are two 16-byte records per Gaussian (the gather set of the blend kernels).
+// contiguous 384 B (means3D/scales), 512 B (rotations) slabs.  Geometry comes first; only the SH rows
+// (192 B/Gaussian, 80 % of the input bytes) of the Gaussians that SURVIVED culling are then staged
+// through shared memory with coalesced 16-byte loads and consumed from a conflict-free padded
+// layout -- a culled Gaussian costs 44 B, not 236 B.  CTAs are small (128 Gaussians, 25 KB slab) so
+// that several per SM overlap their load and compute phases.  Outputs are two 16-byte records per
+// Gaussian (the gather set of the blend kernels).
 #include "common.cuh"
 
 namespace ogs {
@@ -38,42 +41,15 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
     y1 = imin_(gy, imax_(0, (int)((py + r + 15.0f) / 16.0f)));
 }
 
-#define SH_PAD 49   // floats per Gaussian in the shared staging buffer (48 + 1: conflict-free)
+
+#define PF 128   // Gaussians (= threads) per CTA
 
 template <bool HAS_SH>
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
-    extern __shared__ float s_sh[];  // [256][SH_PAD] when HAS_SH
-    const int i = blockIdx.x * 256 + threadIdx.x;
+__global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
+    extern __shared__ float s_sh[];  // [PF][M*3 + 1] when HAS_SH
+    __shared__ uint8_t s_vis[PF];
+    const int i = blockIdx.x * PF + threadIdx.x;
     const int P = a.P;
-
-    if (HAS_SH) {
-        // cooperative, coalesced stage of this block's SH slab: 256 Gaussians x M*3 floats
-        const int per = a.M * 3;
-        const size_t base = (size_t)blockIdx.x * 256 * per;
-        const size_t total = (size_t)P * per;
-        const int n = 256 * per;
-        if ((per & 3) == 0) {
-            const float4* src = reinterpret_cast<const float4*>(a.shs + base);
-            for (int e = threadIdx.x; e < n / 4; e += 256) {
-                if (base + (size_t)e * 4 < total) {
-                    float4 v = __ldg(src + e);
-                    int f = e * 4;
-                    int gi = f / per, k = f - gi * per;   // per % 4 == 0: the 4 floats share gi
-                    float* d = s_sh + gi * (per + 1) + k;
-                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                }
-            }
-        } else {
-            for (int e = threadIdx.x; e < n; e += 256) {
-                if (base + e < total) {
-                    int gi = e / per, k = e - gi * per;
-                    s_sh[gi * (per + 1) + k] = __ldg(a.shs + base + e);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (i >= P) return;
 
     // defaults for culled Gaussians
     int radius_out = 0;
@@ -85,13 +61,15 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
 
     const float* v = a.view;
     const float* pm = a.proj;
-    const float p0 = a.means3D[3 * (size_t)i + 0], p1 = a.means3D[3 * (size_t)i + 1],
-                p2 = a.means3D[3 * (size_t)i + 2];
+    const bool active = i < P;
+    const float p0 = active ? a.means3D[3 * (size_t)i + 0] : 0.f, p1 = active ? a.means3D[3 * (size_t)i + 1] : 0.f,
+                p2 = active ? a.means3D[3 * (size_t)i + 2] : 0.f;
+    bool visible = false;
     float pv0 = v[0] * p0 + v[4] * p1 + v[8] * p2 + v[12];
     float pv1 = v[1] * p0 + v[5] * p1 + v[9] * p2 + v[13];
     float pv2 = v[2] * p0 + v[6] * p1 + v[10] * p2 + v[14];
     do {
-        if (pv2 <= 0.2f) break;  // near cull
+        if (!active || pv2 <= 0.2f) break;  // near cull
         float ph0 = pm[0] * p0 + pm[4] * p1 + pm[8] * p2 + pm[12];
         float ph1 = pm[1] * p0 + pm[5] * p1 + pm[9] * p2 + pm[13];
         float ph3 = pm[3] * p0 + pm[7] * p1 + pm[11] * p2 + pm[15];
@@ -169,7 +147,39 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
         tile_rect(px, py, rad, gx, gy, x0, y0, x1, y1);
         if ((x1 - x0) * (y1 - y0) == 0) break;
 
-        if (HAS_SH) {
+        visible = true;
+        radius_out = rad;
+        tiles = (uint32_t)((y1 - y0) * (x1 - x0));
+        r0 = make_float4(px, py, conA, conB);
+        r1 = make_float4(conC, a.opacities[i], pv2, __int_as_float(rad));
+        dkey = __float_as_uint(pv2);
+    } while (0);
+
+    if (HAS_SH) {
+        // cooperative, coalesced stage of the VISIBLE rows of this block's SH slab
+        s_vis[threadIdx.x] = visible;
+        __syncthreads();
+        const int per = a.M * 3;
+        const size_t base = (size_t)blockIdx.x * PF * per;
+        if ((per & 3) == 0) {
+            const float4* src = reinterpret_cast<const float4*>(a.shs + base);
+            for (int e = threadIdx.x; e < PF / 4 * per; e += PF) {
+                const int f = e * 4;
+                const int gi = f / per, k = f - gi * per;   // per % 4 == 0: the 4 floats share gi
+                if (s_vis[gi]) {
+                    const float4 q = __ldg(src + e);
+                    float* d = s_sh + gi * (per + 1) + k;
+                    d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+                }
+            }
+        } else {
+            for (int e = threadIdx.x; e < PF * per; e += PF) {
+                const int gi = e / per, k = e - gi * per;
+                if (s_vis[gi]) s_sh[gi * (per + 1) + k] = __ldg(a.shs + base + e);
+            }
+        }
+        __syncthreads();
+        if (visible) {
             const float* sh = s_sh + threadIdx.x * (a.M * 3 + 1);
             const float d0 = p0 - a.campos[0], d1 = p1 - a.campos[1], d2 = p2 - a.campos[2];
             const float len = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
@@ -201,12 +211,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
                 rgb[c] = fmaxf(res, 0.0f);
             }
         }
-        radius_out = rad;
-        tiles = (uint32_t)((y1 - y0) * (x1 - x0));
-        r0 = make_float4(px, py, conA, conB);
-        r1 = make_float4(conC, a.opacities[i], pv2, __int_as_float(rad));
-        dkey = __float_as_uint(pv2);
-    } while (0);
+    }
+    if (!active) return;
 
     a.radii[i] = radius_out;
     a.g.rec0[i] = r0;
@@ -224,18 +230,18 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
 
 int launch_preprocess_forward(const PreprocessArgs& a, cudaStream_t s) {
     if (a.P <= 0) return 0;
-    const int blocks = (a.P + 255) / 256;
+    const int blocks = (a.P + PF - 1) / PF;
     if (a.shs) {
-        const size_t smem = (size_t)256 * (a.M * 3 + 1) * sizeof(float);
+        const size_t smem = (size_t)PF * (a.M * 3 + 1) * sizeof(float);
         static bool attr_done = false;
         if (!attr_done) {
             cudaFuncSetAttribute(preprocess_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_done = true;
         }
         if (smem > 100 * 1024) { set_error("preprocess: SH block too large (M=%d)", a.M); return -3; }
-        preprocess_fwd_kernel<true><<<blocks, 256, smem, s>>>(a);
+        preprocess_fwd_kernel<true><<<blocks, PF, smem, s>>>(a);
     } else {
-        preprocess_fwd_kernel<false><<<blocks, 256, 0, s>>>(a);
+        preprocess_fwd_kernel<false><<<blocks, PF, 0, s>>>(a);
     }
     return 0;
 }

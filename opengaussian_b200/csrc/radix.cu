@@ -21,12 +21,14 @@ namespace ogs {
 #define RS_THREADS 256
 #define RS_WARPS 8
 #define RS_ITEMS 16
-#define RS_TILE (RS_THREADS * RS_ITEMS)   // 4096
+#define RS_TILE (RS_THREADS * RS_ITEMS)   // 4096: tile of the N-entry tile sort
+#define RS_ITEMS_SMALL 16
+#define RS_TILE_SMALL (RS_THREADS * RS_ITEMS_SMALL)   // tile of the P-entry depth sort (245 tiles at P = 1 M: one wave)
 #define RS_RADIX 256
 #define RS_FLAG_AGG 0x40000000u
 #define RS_FLAG_INC 0x80000000u
 #define RS_VAL_MASK 0x3FFFFFFFu
-#define RS_LB 8
+#define RS_LB 32   // predecessor tiles read per look-back round trip (independent loads in flight)
 
 struct RsPasses {
     int num;
@@ -41,11 +43,24 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
     for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS) s_h[e] = 0;
     __syncthreads();
     const uint32_t n = min(*n_ptr, cap);
-    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) {
-        const uint32_t k = (uint32_t)keys[i];
+    auto count = [&](uint32_t k) {
 #pragma unroll
         for (int p = 0; p < 4; p++)
             if (p < ps.num) atomicAdd(&s_h[p * RS_RADIX + ((k >> ps.shift[p]) & ((1u << ps.bits[p]) - 1u))], 1u);
+    };
+    if (sizeof(KeyT) == 4) {   // four keys per 16-byte load, two loads in flight per thread
+        const uint32_t n4 = n / 4;
+        const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+        for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n4; i += 2 * gridDim.x * RS_THREADS) {
+            const uint32_t i2 = i + gridDim.x * RS_THREADS;
+            const uint4 qa = __ldg(k4 + i);
+            const uint4 qb = i2 < n4 ? __ldg(k4 + i2) : make_uint4(0, 0, 0, 0);
+            count(qa.x); count(qa.y); count(qa.z); count(qa.w);
+            if (i2 < n4) { count(qb.x); count(qb.y); count(qb.z); count(qb.w); }
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) count((uint32_t)keys[n4 * 4 + threadIdx.x]);
+    } else {
+        for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) count((uint32_t)keys[i]);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS)
@@ -56,17 +71,18 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
 // LOOKBACK = false: plain scatter; the tile's exclusive digit offsets were computed beforehand
 //                   (rs_tile_hist_kernel / emit + rs_tile_scan_kernel) and are read from
 //                   tile_state[digit * ntiles + tile]; ghist holds the digit totals.
-template <typename KeyT, bool LOOKBACK>
+template <typename KeyT, bool LOOKBACK, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
                                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                              const uint32_t* __restrict__ n_ptr, uint32_t cap, int shift, int bits,
                                                              const uint32_t* __restrict__ ghist /*[256] of this pass*/,
                                                              uint32_t* tile_state, uint32_t* ticket, uint32_t ntiles) {
+    constexpr int TILE = RS_THREADS * ITEMS;
     __shared__ uint32_t s_wh[RS_WARPS * RS_RADIX];   // per-warp digit counters -> exclusive warp offsets
     __shared__ uint32_t s_dstart[RS_RADIX];          // local exclusive start of each digit in the tile
     __shared__ uint32_t s_gbase[RS_RADIX];           // global position of local sorted slot 0 of the digit
-    __shared__ KeyT s_keys[RS_TILE];
-    __shared__ uint32_t s_vals[RS_TILE];
+    __shared__ KeyT s_keys[TILE];
+    __shared__ uint32_t s_vals[TILE];
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -75,24 +91,24 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __re
     __syncthreads();
     const uint32_t tile = LOOKBACK ? s_tile : blockIdx.x;
     const uint32_t n = min(*n_ptr, cap);
-    const uint32_t tile_start = tile * (uint32_t)RS_TILE;
+    const uint32_t tile_start = tile * (uint32_t)TILE;
     if (tile_start >= n) return;
-    const uint32_t tile_n = min((uint32_t)RS_TILE, n - tile_start);
+    const uint32_t tile_n = min((uint32_t)TILE, n - tile_start);
     const uint32_t dmask = (1u << bits) - 1u;
 
     // ---- load (warp-striped: item i of lane l = chunk[i*32 + l]) and rank ----
-    const uint32_t wbase = tile_start + warp * (32 * RS_ITEMS);
-    uint32_t key[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
+    const uint32_t wbase = tile_start + warp * (32 * ITEMS);
+    uint32_t key[ITEMS];
+    uint32_t rank[ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* wh = s_wh + warp * RS_RADIX;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = wbase + i * 32 + lane;
         key[i] = idx < n ? (uint32_t)kin[idx] : 0xFFFFFFFFu;
     }
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = wbase + i * 32 + lane;
         const bool valid = idx < n;
         const uint32_t d = valid ? ((key[i] >> shift) & dmask) : 0xFFFFFFFFu;
@@ -192,7 +208,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __re
 
     // ---- reorder by local rank in shared memory ----
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = wbase + i * 32 + lane;
         if (idx < n) {
             const uint32_t d = (key[i] >> shift) & dmask;
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __re
 
 // scratch layout for one sort: [ghist 4*256][ticket 4 (one per pass) + pad][tile_state passes * tiles * 256]
 size_t radix_scratch_bytes(uint64_t capacity, int passes) {
-    const size_t tiles = (size_t)((capacity + RS_TILE - 1) / RS_TILE) + 1;
+    const size_t tiles = (size_t)((capacity + RS_TILE_SMALL - 1) / RS_TILE_SMALL) + 1;
     return align_up((size_t)4 * RS_RADIX * 4, 256) + 256 + (size_t)passes * tiles * RS_RADIX * 4;
 }
 
@@ -235,23 +251,25 @@ static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, co
         ps.shift[ps.num - 1] = ps.shift[ps.num - 2] + ps.bits[ps.num - 2];
         ps.bits[ps.num - 1] = tot - ps.bits[ps.num - 2];
     }
-    const size_t tiles = (size_t)((capacity + RS_TILE - 1) / RS_TILE) + 1;
+    constexpr int ITEMS = sizeof(KeyT) == 4 ? RS_ITEMS_SMALL : RS_ITEMS;
+    constexpr int TILE = RS_THREADS * ITEMS;
+    const size_t tiles = (size_t)((capacity + RS_TILE_SMALL - 1) / RS_TILE_SMALL) + 1;
     char* base = (char*)scratch;
     uint32_t* ghist = (uint32_t*)base;
     uint32_t* tickets = (uint32_t*)(base + align_up((size_t)4 * RS_RADIX * 4, 256));
     uint32_t* states = (uint32_t*)(base + align_up((size_t)4 * RS_RADIX * 4, 256) + 256);
     OGS_CUDA(cudaMemsetAsync(scratch, 0, radix_scratch_bytes(capacity, ps.num), s));
     int hist_grid = (int)((capacity + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
-    if (hist_grid > OGS_NUM_SMS * 8) hist_grid = OGS_NUM_SMS * 8;
+    if (hist_grid > OGS_NUM_SMS * 4) hist_grid = OGS_NUM_SMS * 4;
     if (hist_grid < 1) hist_grid = 1;
     rs_hist_kernel<KeyT><<<hist_grid, RS_THREADS, 0, s>>>(k0, n_ptr, (uint32_t)capacity, ps, ghist);
     KeyT* ka = k0; KeyT* kb = k1;
     uint32_t* va = v0; uint32_t* vb = v1;
-    const unsigned grid = (unsigned)((capacity + RS_TILE - 1) / RS_TILE);
+    const unsigned grid = (unsigned)((capacity + TILE - 1) / TILE);
     for (int p = 0; p < ps.num; p++) {
-        rs_pass_kernel<KeyT, true><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_ptr, (uint32_t)capacity, ps.shift[p],
-                                                               ps.bits[p], ghist + p * RS_RADIX,
-                                                               states + (size_t)p * tiles * RS_RADIX, tickets + p, 0u);
+        rs_pass_kernel<KeyT, true, ITEMS><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_ptr, (uint32_t)capacity, ps.shift[p],
+                                                                      ps.bits[p], ghist + p * RS_RADIX,
+                                                                      states + (size_t)p * tiles * RS_RADIX, tickets + p, 0u);
         KeyT* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;
     }
@@ -265,11 +283,6 @@ int radix_sort_pairs_u32(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1,
                          int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
     return radix_sort_pairs_t<uint32_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second);
 }
-int radix_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
-                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
-    return radix_sort_pairs_t<uint16_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Tile sort (N entries, 16-bit tile ids, <= 2 digit passes): counting passes WITHOUT look-back.
 // With thousands of 4096-item tiles in flight a look-back walk is hundreds of predecessors long
@@ -379,13 +392,13 @@ int tile_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, 
     uint32_t* cnt0 = tile_sort_pass0_counts(scratch);
     uint32_t* cnt1 = cnt0 + (size_t)RS_RADIX * ntiles;
     rs_tile_scan_kernel<<<1 << bits0, RS_THREADS, 0, s>>>(cnt0, ntiles, totals);
-    rs_pass_kernel<uint16_t, false><<<ntiles, RS_THREADS, 0, s>>>(k0, k1, v0, v1, n_ptr, (uint32_t)capacity, 0, bits0, totals,
+    rs_pass_kernel<uint16_t, false, RS_ITEMS><<<ntiles, RS_THREADS, 0, s>>>(k0, k1, v0, v1, n_ptr, (uint32_t)capacity, 0, bits0, totals,
                                                                   cnt0, nullptr, ntiles);
     if (passes == 2) {
         const int bits1 = bits - bits0;
         rs_tile_hist_kernel<uint16_t><<<ntiles, RS_THREADS, 0, s>>>(k1, n_ptr, (uint32_t)capacity, bits0, bits1, ntiles, cnt1);
         rs_tile_scan_kernel<<<1 << bits1, RS_THREADS, 0, s>>>(cnt1, ntiles, totals + RS_RADIX);
-        rs_pass_kernel<uint16_t, false><<<ntiles, RS_THREADS, 0, s>>>(k1, k0, v1, v0, n_ptr, (uint32_t)capacity, bits0, bits1,
+        rs_pass_kernel<uint16_t, false, RS_ITEMS><<<ntiles, RS_THREADS, 0, s>>>(k1, k0, v1, v0, n_ptr, (uint32_t)capacity, bits0, bits1,
                                                                       totals + RS_RADIX, cnt1, nullptr, ntiles);
     }
     cudaError_t e = cudaGetLastError();
@@ -432,29 +445,25 @@ __global__ void __launch_bounds__(SC_THREADS) scan_gather_kernel(int P, const ui
         if (w < warp) woff += s_warp[w];
         total += s_warp[w];
     }
-    if (tid == 0) {
+    // Every tile publishes its total; the tile's threads then sum ALL predecessors' totals
+    // cooperatively (tiles are ticketed, so every predecessor is already running and will publish
+    // without waiting on anyone): one round trip instead of a serial walk over hundreds of tiles.
+    {
         volatile uint32_t* st = tile_state;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            st[0] = total | RS_FLAG_INC;
-        } else {
+        if (tid == 0) {
             st[tile] = total | RS_FLAG_AGG;
-            __threadfence();
-            int t = (int)tile - 1;
-            while (t >= 0) {
-                uint32_t x[RS_LB];
-#pragma unroll
-                for (int q = 0; q < RS_LB; q++) x[q] = (t - q >= 0) ? st[t - q] : RS_FLAG_INC;
-#pragma unroll
-                for (int q = 0; q < RS_LB; q++) {
-                    if (x[q] & RS_FLAG_INC) { excl += x[q] & RS_VAL_MASK; t = -1; break; }
-                    if (x[q] & RS_FLAG_AGG) { excl += x[q] & RS_VAL_MASK; t--; }
-                    else break;
-                }
-            }
-            st[tile] = (excl + total) | RS_FLAG_INC;
+            s_excl = 0;
         }
-        s_excl = excl;
+        __syncthreads();
+        uint32_t part = 0;
+        for (uint32_t t = tid; t < tile; t += SC_THREADS) {
+            uint32_t x;
+            do { x = st[t]; } while (!(x & RS_FLAG_AGG));
+            part += x & RS_VAL_MASK;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+        if (lane == 0 && part) atomicAdd(&s_excl, part);
     }
     __syncthreads();
     const uint32_t off = s_excl + woff + (a - sum);
