@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 3 --warmup 3 --no-kmeans --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 # quick_bench launches 18 ogs:: kernels per frame; skip 4 frames, capture 2 whole frames
 python scripts/quick_bench.py --iters 3 --prof 0 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"ogs::" -s 72 -c 36 \
+ncu --set full --clock-control none --import-source on -k regex:"blend|preprocess|rs_|emit_kernel|scan_gather|ranges_kernel|set_scalar" -s 72 -c 36 \
     -o gpurun_out/${TAG}_raster python scripts/quick_bench.py --iters 3 --prof 0 > gpurun_out/${TAG}_ncu_raster.log 2>&1; echo "ncu raster rc=$?"
 python scripts/kmeans_bench.py --iters 2 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:kmeans_assign -s 3 -c 1 \
