@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128 / PAIRS, (C <= 4 && PAIRS == 2) ? OGS_BWD_
     __shared__ float4 s_a2[2][BB];
     __shared__ float2 s_b2[2][BB];
     __shared__ __align__(16) float s_ch2[2][BB * CH];
-    __shared__ uint32_t s_id2[2][BB];
+    __shared__ uint32_t s_id3[3][BB];     // ids live until the batch's flush, i.e. while batch b-2 is already being staged: 3 slots
     __shared__ int s_max_last;
 
     const int gx = (a.W + 15) / 16;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128 / PAIRS, (C <= 4 && PAIRS == 2) ? OGS_BWD_
         const int n = min(BB, max_last - start);
         for (int t = threadIdx.x; t < n; t += BWD_THREADS) {
             const uint32_t gid = a.point_list[range.x + start + t];
-            s_id2[sb][t] = gid;
+            s_id3[b % 3][t] = gid;
             const float4 r1 = __ldg(a.rec1 + gid);
             ogs_stage(__ldg(a.rec0 + gid), r1, s_a2[sb][t], s_b2[sb][t]);
             s_ch2[sb][t * CH + C] = r1.z;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128 / PAIRS, (C <= 4 && PAIRS == 2) ? OGS_BWD_
             }
             if (sum != 0.f) {
                 const int j = e / V, k = e - j * V;
-                atomicAdd(a.acc + (size_t)s_id2[sb][j] * a.stride + k, sum);
+                atomicAdd(a.acc + (size_t)s_id3[b % 3][j] * a.stride + k, sum);
             }
         }
     }
