@@ -112,9 +112,9 @@ const char* ogs_last_error(void);
 
 /* Optional device timing of the kernel families (CUDA events recorded on the launching stream).
  * Families: 0 preprocess_fwd, 1 depth_sort_scan, 2 emit, 3 tile_sort, 4 tile_ranges, 5 blend_fwd,
- * 6 blend_bwd, 7 preprocess_bwd, 8 kmeans_assign.  ogs_profile_read synchronises the recorded
+ * 6 blend_bwd, 7 preprocess_bwd, 8 kmeans_assign, 9 mask_stats.  ogs_profile_read synchronises the recorded
  * events, writes the summed milliseconds and launch counts of the first n families and resets. */
-#define OGS_PROFILE_FAMILIES 9
+#define OGS_PROFILE_FAMILIES 10
 void ogs_profile_enable(int on);
 int ogs_profile_read(float* ms_out_host, int32_t* launches_out_host, int32_t n);
 
@@ -161,6 +161,29 @@ int ogs_kmeans_gather_st(int64_t N, const float* feat, int32_t Dout, const float
 
 /* Per-cluster member counts: counts_out int64 [k] (zeroed by the call). */
 int ogs_kmeans_count(int64_t N, const int64_t* ids, int32_t k, int64_t* counts_out, void* stream);
+
+/* ---- per-mask feature statistics and the Stage-1 cohesion loss ----
+ * Replace utils/opengs_utlis.py::mask_feature_mean (:240-283) and train.py::cohesion_loss (:102-121).
+ * feat [C,H*W] float (C = 3 or 6), masks [M,H*W] bytes (torch.bool storage, non-zero = inside),
+ * image_mask [H*W] float or NULL (the rendered silhouette, :253-255).  All device pointers.
+ *   mean forward : sums [M,C] = sum_p feat * mask * image_mask, counts [M] = sum_p mask * image_mask
+ *   mean backward: G [M,C] = dL/dmean / max(count,1), K [M] = (count > 1) ? sum_c G * mean : 0;
+ *                  writes dfeat [C,H*W] and (if image_mask) dimg [H*W]
+ *   var forward  : sq [M,C] = sum_p mask * (feat * image_mask - mean)^2
+ *   cohesion fwd : dsum [M] = sum_p mask * ||feat[:,p] - mean[m]||_2, npix [M] = sum_p mask
+ *   cohesion bwd : coef [M] = dL/dloss / (M * max(npix,1)); writes dfeat [C,H*W], dmean [M,C] */
+int ogs_mask_mean_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                          const float* image_mask, float* sums, float* counts, void* stream);
+int ogs_mask_mean_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                           const float* image_mask, const float* G, const float* K, float* dfeat,
+                           float* dimg, void* stream);
+int ogs_mask_var_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                         const float* image_mask, const float* mean, float* sq, void* stream);
+int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                         const float* mean, float* dsum, float* npix, void* stream);
+int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                          const float* mean, const float* coef, float* dfeat, float* dmean,
+                          void* stream);
 
 #ifdef __cplusplus
 }

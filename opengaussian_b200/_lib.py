@@ -60,6 +60,11 @@ EXPORTS = {
     "ogs_kmeans_finalize": (C.c_int, [C.c_int32, C.c_int32, _fp, _fp, C.c_float, _fp, C.c_void_p]),
     "ogs_kmeans_gather_st": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_void_p]),
     "ogs_kmeans_count": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, C.c_void_p]),
+    "ogs_mask_mean_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_mask_mean_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_mask_var_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_cohesion_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_cohesion_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
 }
 
 _LIB = None
@@ -96,7 +101,7 @@ def check(rc: int, what: str):
 
 
 PROFILE_FAMILIES = ("preprocess_fwd", "depth_sort_scan", "emit", "tile_sort", "tile_ranges", "blend_fwd",
-                    "blend_bwd", "preprocess_bwd", "kmeans_assign")
+                    "blend_bwd", "preprocess_bwd", "kmeans_assign", "mask_stats")
 
 
 def profile_enable(on: bool):

@@ -25,6 +25,7 @@ UNITS = {
     "blend_bwd.cu": [],
     "preprocess_bwd.cu": [],
     "kmeans.cu": [],
+    "mask_stats.cu": [],
     "capi.cu": [],
 }
 

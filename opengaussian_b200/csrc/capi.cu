@@ -439,4 +439,71 @@ int ogs_kmeans_count(int64_t N, const int64_t* ids, int32_t k, int64_t* counts_o
     return 0;
 }
 
+#define OGS_MASK_ARGS_OK(what)                                                                          \
+    if (M < 0 || HW < 0 || ((M > 0 || HW > 0) && !feat) || (M > 0 && HW > 0 && !masks)) {                \
+        set_error(what ": bad arguments");                                                               \
+        return -1;                                                                                       \
+    }
+
+int ogs_mask_mean_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                          const float* image_mask, float* sums, float* counts, void* stream_) {
+    OGS_MASK_ARGS_OK("mask_mean_forward");
+    if (M > 0 && (!sums || !counts)) { set_error("mask_mean_forward: outputs must be set"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_mask_mean_forward(M, C, HW, feat, masks, image_mask, sums, counts, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("mask_mean_forward", 0, s);
+    return 0;
+}
+
+int ogs_mask_mean_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                           const float* image_mask, const float* G, const float* K, float* dfeat,
+                           float* dimg, void* stream_) {
+    OGS_MASK_ARGS_OK("mask_mean_backward");
+    if ((M > 0 && (!G || !K)) || (HW > 0 && !dfeat)) { set_error("mask_mean_backward: G/K/dfeat must be set"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_mask_mean_backward(M, C, HW, feat, masks, image_mask, G, K, dfeat, image_mask ? dimg : nullptr, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("mask_mean_backward", 0, s);
+    return 0;
+}
+
+int ogs_mask_var_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                         const float* image_mask, const float* mean, float* sq, void* stream_) {
+    OGS_MASK_ARGS_OK("mask_var_forward");
+    if (M > 0 && (!mean || !sq)) { set_error("mask_var_forward: mean/sq must be set"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_mask_var_forward(M, C, HW, feat, masks, image_mask, mean, sq, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("mask_var_forward", 0, s);
+    return 0;
+}
+
+int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                         const float* mean, float* dsum, float* npix, void* stream_) {
+    OGS_MASK_ARGS_OK("cohesion_forward");
+    if (M > 0 && (!mean || !dsum || !npix)) { set_error("cohesion_forward: mean/outputs must be set"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_cohesion_forward(M, C, HW, feat, masks, mean, dsum, npix, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("cohesion_forward", 0, s);
+    return 0;
+}
+
+int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+                          const float* mean, const float* coef, float* dfeat, float* dmean, void* stream_) {
+    OGS_MASK_ARGS_OK("cohesion_backward");
+    if ((M > 0 && (!mean || !coef || !dmean)) || (HW > 0 && !dfeat)) { set_error("cohesion_backward: inputs/outputs must be set"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_cohesion_backward(M, C, HW, feat, masks, mean, coef, dfeat, dmean, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("cohesion_backward", 0, s);
+    return 0;
+}
+
 }  // extern "C"

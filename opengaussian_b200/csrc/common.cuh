@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns (int)e
 
 // ---- optional per-family device timing (CUDA events on the launching stream) ----
 enum ProfFamily { PF_PREPROCESS_FWD = 0, PF_DEPTH_SORT_SCAN, PF_EMIT, PF_TILE_SORT, PF_RANGES, PF_BLEND_FWD,
-                  PF_BLEND_BWD, PF_PREPROCESS_BWD, PF_KMEANS_ASSIGN, PF_COUNT };
+                  PF_BLEND_BWD, PF_PREPROCESS_BWD, PF_KMEANS_ASSIGN, PF_MASK_STATS, PF_COUNT };
 void prof_begin(int family, cudaStream_t s);
 void prof_end(int family, cudaStream_t s);
 struct ProfScope {
@@ -289,5 +289,18 @@ int launch_kmeans_finalize(int k, int D, const float* sums, const float* counts,
 int launch_kmeans_gather_st(int64_t N, const float* feat, int Dout, const float* centers, int Dc, const int64_t* ids,
                             float* out, cudaStream_t s);
 int launch_kmeans_count(int64_t N, const int64_t* ids, int k, int64_t* counts, cudaStream_t s);
+
+
+// mask statistics (mask_stats.cu)
+int launch_mask_mean_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, float* sums,
+                             float* counts, cudaStream_t s);
+int launch_mask_mean_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, const float* G,
+                              const float* K, float* dfeat, float* dimg, cudaStream_t s);
+int launch_mask_var_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, const float* mean,
+                            float* sq, cudaStream_t s);
+int launch_cohesion_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* mean, float* dsum,
+                            float* npix, cudaStream_t s);
+int launch_cohesion_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* mean, const float* coef,
+                             float* dfeat, float* dmean, cudaStream_t s);
 
 }  // namespace ogs

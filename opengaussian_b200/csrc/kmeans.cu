@@ -101,7 +101,10 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
     while ((1 << id_bits) < k) id_bits++;
 
     const int64_t n_tiles = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
-    auto tile_is_bulk = [&](int64_t t) { return bulk_ok && (t + 1) * KM_CTA_POINTS <= N; };
+    // leaf mode (select_ids): only ~1/k1 of the points take part -- read their rows straight from global
+    // memory instead of streaming every tile through shared memory
+    const bool staged = select_ids == nullptr;
+    auto tile_is_bulk = [&](int64_t t) { return staged && bulk_ok && (t + 1) * KM_CTA_POINTS <= N; };
     auto issue = [&](int64_t t, int buf) {   // one thread: arm the barrier and start both bulk copies
         float* dst = s_pts + (size_t)buf * tile_floats;
         const uint32_t ba = (uint32_t)(KM_CTA_POINTS * Da * sizeof(float)), bb = (uint32_t)(KM_CTA_POINTS * Db * sizeof(float));
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
         if (tile_is_bulk(t)) {
             mbar_wait(&s_bar[buf], (phases >> buf) & 1u);
             phases ^= 1u << buf;
-        } else {
+        } else if (staged) {
             const int64_t rem = N - tile_start < KM_CTA_POINTS ? N - tile_start : KM_CTA_POINTS;
             float* wa = s_pts + (size_t)buf * tile_floats;
             for (int64_t e = threadIdx.x; e < rem * Da; e += KM_THREADS) wa[e] = __ldg(a + tile_start * Da + e);
@@ -146,7 +149,10 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 float v = 0.f;
-                if (active[q]) v = (d < Da) ? pa[li * Da + d] : __fmul_rn(pb[li * Db + (d - Da)], scale_b);
+                if (active[q]) {
+                    if (staged) v = (d < Da) ? pa[li * Da + d] : __fmul_rn(pb[li * Db + (d - Da)], scale_b);
+                    else v = (d < Da) ? __ldg(a + i * Da + d) : __fmul_rn(__ldg(b + i * Db + (d - Da)), scale_b);
+                }
                 if (q & 1) X[q >> 1][d].y = v; else X[q >> 1][d].x = v;
             }
         }
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
                 }
             }
         }
-        __syncthreads();   // everyone is done with s_pts[buf] before it is refilled two tiles from now
+        if (staged) __syncthreads();   // everyone is done with s_pts[buf] before it is refilled two tiles from now
     }
     if (partials) {
         __syncthreads();

@@ -1,0 +1,157 @@
+"""Per-mask feature statistics and the Stage-1 losses on the B200
+streaming kernels of csrc/mask_stats.cu -- drop-ins for
+
+* ``utils/opengs_utlis.py::mask_feature_mean`` (:240-283)  -- same signature and return values,
+* ``train.py::cohesion_loss`` (:102-121) and ``train.py::separation_loss`` (:123-147),
+* ``utils/opengs_utlis.py::pair_mask_feature_mean`` (:184-201).
+
+The reference expands ``feat_map [C,H,W]`` and ``gt_masks [M,H,W]`` to ``[M,C,H,W]`` float tensors
+(processed in 5x5 Python chunks to dodge OOM); here every pass streams the M*H*W mask bytes once.
+Both functions are differentiable (custom autograd, gradients to ``feat_map``, ``image_mask`` and the
+mask means), because ``train.py:450-456`` back-propagates through them.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _prep(feat_map, gt_masks, image_mask=None):
+    if not feat_map.is_cuda:
+        raise _lib.OgsError("mask statistics need CUDA tensors (no CPU path)")
+    Cn, H, W = feat_map.shape
+    M = gt_masks.shape[0]
+    assert tuple(gt_masks.shape[1:]) == (H, W), "gt_masks must be [num_mask, H, W]"
+    feat = feat_map.detach().float().contiguous()
+    masks = gt_masks.detach()
+    if masks.dtype != torch.bool:
+        masks = masks != 0
+    masks = masks.contiguous().view(torch.uint8)
+    img = None
+    if image_mask is not None:
+        img = image_mask.detach().float().expand(1, H, W).contiguous().view(H * W)
+    return feat, masks, img, M, Cn, H * W
+
+
+class _MaskMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat_map, gt_masks, image_mask):
+        feat, masks, img, M, Cn, HW = _prep(feat_map, gt_masks, image_mask)
+        dev = feat.device
+        sums = torch.empty(M, Cn, device=dev)
+        counts = torch.empty(M, device=dev)
+        _lib.check(_lib.lib().ogs_mask_mean_forward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(img),
+                                                   _lib.ptr(sums), _lib.ptr(counts), _stream(dev)), "ogs_mask_mean_forward")
+        cnt = counts.clamp(min=1)
+        mean = sums / cnt[:, None]
+        ctx.save_for_backward(feat, masks, img if img is not None else torch.empty(0, device=dev), counts, mean)
+        ctx.has_img = img is not None
+        ctx.shape = feat_map.shape
+        ctx.img_shape = None if image_mask is None else image_mask.shape
+        ctx.mark_non_differentiable(counts)
+        return mean, counts
+
+    @staticmethod
+    def backward(ctx, g_mean, _g_counts):
+        feat, masks, img, counts, mean = ctx.saved_tensors
+        img = img if ctx.has_img else None
+        M, Cn = mean.shape
+        HW = feat.shape[1] * feat.shape[2]
+        dev = feat.device
+        G = (g_mean.float() / counts.clamp(min=1)[:, None]).contiguous()
+        K = torch.where(counts > 1, (G * mean).sum(1), torch.zeros_like(counts)).contiguous()
+        dfeat = torch.empty_like(feat)
+        dimg = torch.empty(HW, device=dev) if img is not None else None
+        _lib.check(_lib.lib().ogs_mask_mean_backward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(img), _lib.ptr(G),
+                                                    _lib.ptr(K), _lib.ptr(dfeat), _lib.ptr(dimg), _stream(dev)),
+                   "ogs_mask_mean_backward")
+        g_img = None
+        if dimg is not None and ctx.needs_input_grad[2]:
+            g_img = dimg.view(1, feat.shape[1], feat.shape[2]).sum_to_size(ctx.img_shape)
+        return dfeat.view(ctx.shape), None, g_img
+
+
+def mask_feature_mean(feat_map, gt_masks, image_mask=None, return_var=False):
+    """Average instance feature inside each mask: ``[num_mask, C]``; with ``return_var`` also the
+    per-mask variance ``[num_mask]`` and pixel count ``[num_mask]`` (reference :240-283)."""
+    mean, counts = _MaskMean.apply(feat_map, gt_masks, image_mask)
+    if not return_var:
+        return mean
+    feat, masks, img, M, Cn, HW = _prep(feat_map, gt_masks, image_mask)
+    sq = torch.empty(M, Cn, device=feat.device)
+    mean_d = mean.detach().contiguous()
+    _lib.check(_lib.lib().ogs_mask_var_forward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(img), _lib.ptr(mean_d),
+                                              _lib.ptr(sq), _stream(feat.device)), "ogs_mask_var_forward")
+    cnt = counts.clamp(min=1)
+    variance = (sq / cnt[:, None]).mean(dim=1)
+    return mean, variance, cnt
+
+
+class _Cohesion(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat_map, gt_mask, feat_mean_stack):
+        feat, masks, _, M, Cn, HW = _prep(feat_map, gt_mask)
+        dev = feat.device
+        mean = feat_mean_stack.detach().float().contiguous()
+        dsum = torch.empty(M, device=dev)
+        npix = torch.empty(M, device=dev)
+        _lib.check(_lib.lib().ogs_cohesion_forward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(mean), _lib.ptr(dsum),
+                                                  _lib.ptr(npix), _stream(dev)), "ogs_cohesion_forward")
+        ctx.save_for_backward(feat, masks, mean, npix)
+        ctx.shape = feat_map.shape
+        return (dsum / npix.clamp(min=1)).mean() if M > 0 else feat.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, masks, mean, npix = ctx.saved_tensors
+        M, Cn = mean.shape
+        HW = feat.shape[1] * feat.shape[2]
+        dev = feat.device
+        coef = (g.float() / (max(M, 1) * npix.clamp(min=1))).contiguous()
+        dfeat = torch.empty_like(feat)
+        dmean = torch.empty(M, Cn, device=dev)
+        _lib.check(_lib.lib().ogs_cohesion_backward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(mean), _lib.ptr(coef),
+                                                   _lib.ptr(dfeat), _lib.ptr(dmean), _stream(dev)), "ogs_cohesion_backward")
+        return dfeat.view(ctx.shape), None, dmean
+
+
+def cohesion_loss(feat_map, gt_mask, feat_mean_stack):
+    """Intra-mask smoothing loss, Eq. (1) (reference train.py:102-121): mean over masks of the mean
+    L2 distance of the mask's pixels to the mask's mean feature."""
+    return _Cohesion.apply(feat_map, gt_mask, feat_mean_stack)
+
+
+def separation_loss(feat_mean_stack, iteration=None):
+    """Inter-mask contrastive loss, Eq. (2) (reference train.py:123-147).  O(M^2 C) on [M,C]: plain torch."""
+    N = feat_mean_stack.shape[0]
+    diff_squared = (feat_mean_stack.unsqueeze(1) - feat_mean_stack.unsqueeze(0)).pow(2).sum(2)
+    inverse_distance = 1.0 / (diff_squared + 1)
+    mask = torch.eye(N, device=feat_mean_stack.device).bool()
+    inverse_distance = inverse_distance.masked_fill(mask, 0)
+    sorted_indices = inverse_distance.argsort().argsort()
+    loss_weight = (sorted_indices.float() / (N - 1)) * (1.0 - 0.1) + 0.1
+    if iteration is not None and iteration > 35000:
+        loss_weight[loss_weight < 0.9] = 0.1
+    inverse_distance = inverse_distance * loss_weight
+    return inverse_distance.sum() / (N * (N - 1))
+
+
+def pair_mask_feature_mean(feat_map, masks):
+    """Mean feature of N (map, mask) pairs: feat_map [N,C,H,W], masks [N,H,W] -> [N,C] (reference :184-201).
+    One single-mask streaming pass per pair."""
+    outs = []
+    for i in range(feat_map.shape[0]):
+        m = masks[i:i + 1]
+        feat, mk, _, M, Cn, HW = _prep(feat_map[i], m)
+        sums = torch.empty(1, Cn, device=feat.device)
+        counts = torch.empty(1, device=feat.device)
+        w = masks[i].detach().float().contiguous().view(HW)     # the reference multiplies by masks.float()
+        _lib.check(_lib.lib().ogs_mask_mean_forward(1, Cn, HW, _lib.ptr(feat), _lib.ptr(mk), _lib.ptr(w), _lib.ptr(sums),
+                                                   _lib.ptr(counts), _stream(feat.device)), "ogs_mask_mean_forward")
+        outs.append(sums[0] / (counts[0] + 1e-6))
+    return torch.stack(outs) if outs else feat_map.new_zeros(0, feat_map.shape[1])

@@ -44,5 +44,31 @@ def main():
               f"-> {a.N / (kms / max(n, 1)) / 1e6:.2f} Gpts/s, HBM {a.N * (4 * D + 8) / (kms / max(n, 1) * 1e-3) / 1e9:.0f} GB/s")
 
 
+def leaf():
+    """Leaf-level pass as the reference drives it: one coarse cluster per call (train.py:330-332)."""
+    dev = "cuda"
+    N, k1, k2 = 5_000_000, 64, 10
+    g = torch.Generator(device=dev).manual_seed(9)
+    fa = torch.rand(N, 6, device=dev, generator=g)
+    coarse = torch.randint(0, k1, (N,), device=dev, generator=g)
+    cen = fa[:k2].contiguous()
+    ids = torch.zeros(N, dtype=torch.int64, device=dev)
+    s = torch.zeros(k2, 6, device=dev); c = torch.zeros(k2, device=dev)
+    for _ in range(3):
+        kmeans_assign(fa, None, 1.0, cen, select_ids=coarse, selected=3, id_offset=30, ids_out=ids, sums=s, counts=c)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for leaf_id in range(k1):
+        kmeans_assign(fa, None, 1.0, cen, select_ids=coarse, selected=leaf_id, id_offset=leaf_id * k2, ids_out=ids, sums=s, counts=c)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"leaf level: 64 per-cluster passes over N={N} (k2={k2}, D=6): {ms:.3f} ms total, {ms / k1 * 1e3:.1f} us/pass, "
+          f"{N / (ms * 1e-3) / 1e9:.2f} Gpts/s (every point assigned once)")
+
+
 if __name__ == "__main__":
+    if "--leaf" in sys.argv:
+        sys.argv.remove("--leaf")
+        leaf()
+        sys.exit(0)
     main()

@@ -1,0 +1,93 @@
+"""Generates tests/golden/mask_stats_golden.npz by running the REFERENCE's own code (torch CPU):
+
+* utils/opengs_utlis.py::mask_feature_mean (:240-283), pair_mask_feature_mean (:184-201) -- the
+  module is loaded by path with a stub for the missing `bitarray` package;
+* train.py::cohesion_loss (:102-121) and separation_loss (:123-155) -- train.py itself cannot be
+  imported here (pytorch3d, plyfile, a CUDA device ...), so the two function definitions are taken
+  from its source with `ast` and executed unchanged.
+
+Stored: the reference outputs and the autograd gradients of the Stage-1 loss
+(train.py:450-456: loss = separation + 0.1 * cohesion) w.r.t. feat_map and image_mask.
+Run in the build container only:  python tests/golden/make_mask_golden.py
+"""
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+CASES = {
+    # name: (C, H, W, num_mask, with_image_mask)
+    "stage1_6ch": (6, 47, 66, 9, True),         # H*W not a multiple of 4: unaligned mask rows
+    "no_image_mask": (6, 32, 40, 5, False),
+    "rgb_3ch": (3, 24, 28, 4, True),
+}
+
+
+def inputs(name):
+    C, H, W, M, with_img = CASES[name]
+    rs = np.random.RandomState({"stage1_6ch": 31, "no_image_mask": 32, "rgb_3ch": 33}[name])
+    feat = rs.rand(C, H, W).astype(np.float32)
+    # blocky, partly overlapping masks + one empty mask
+    masks = np.zeros((M, H, W), bool)
+    for m in range(M - 1):
+        y0, x0 = rs.randint(0, H - 6), rs.randint(0, W - 6)
+        h, w = rs.randint(4, H // 2), rs.randint(4, W // 2)
+        masks[m, y0:y0 + h, x0:x0 + w] = rs.rand(min(h, H - y0), min(w, W - x0)) > 0.2
+    img = (rs.rand(1, H, W) > 0.15).astype(np.float32) * rs.rand(1, H, W).astype(np.float32) if with_img else None
+    return feat, masks, img
+
+
+def load_reference():
+    sys.modules.setdefault("bitarray", types.SimpleNamespace(bitarray=object))
+    spec = importlib.util.spec_from_file_location("ref_opengs_utlis", os.path.join(REF, "utils/opengs_utlis.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    src = open(os.path.join(REF, "train.py")).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("cohesion_loss", "separation_loss"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "train.py", "exec"), ns)
+    return mod, ns["cohesion_loss"], ns["separation_loss"]
+
+
+def main():
+    ref, cohesion_loss, separation_loss = load_reference()
+    out = {}
+    for name in CASES:
+        feat_np, masks_np, img_np = inputs(name)
+        feat = torch.from_numpy(feat_np).requires_grad_(True)
+        masks = torch.from_numpy(masks_np)
+        img = None if img_np is None else torch.from_numpy(img_np).requires_grad_(True)
+        mean = ref.mask_feature_mean(feat, masks, image_mask=img)
+        loss_c = cohesion_loss(feat, masks, mean)
+        loss_s = separation_loss(mean, 1000)
+        loss = loss_s + 0.1 * loss_c
+        loss.backward()
+        out[f"{name}/mean"] = mean.detach().numpy()
+        out[f"{name}/cohesion"] = loss_c.detach().numpy()
+        out[f"{name}/separation"] = loss_s.detach().numpy()
+        out[f"{name}/dfeat"] = feat.grad.numpy()
+        if img is not None:
+            out[f"{name}/dimg"] = img.grad.numpy()
+        with torch.no_grad():
+            m2, var, cnt = ref.mask_feature_mean(feat.detach(), masks, return_var=True)
+            out[f"{name}/mean_noimg"] = m2.numpy()
+            out[f"{name}/var"] = var.numpy()
+            out[f"{name}/cnt"] = cnt.numpy()
+            pm = ref.pair_mask_feature_mean(feat.detach().unsqueeze(0).repeat(3, 1, 1, 1), masks[:3])
+            out[f"{name}/pair_mean"] = pm.numpy()
+    path = os.path.join(HERE, "mask_stats_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, sorted(out)[:8])
+
+
+if __name__ == "__main__":
+    main()

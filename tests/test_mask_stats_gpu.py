@@ -1,0 +1,107 @@
+"""GPU parity of the mask-statistics kernels (csrc/mask_stats.cu through the C ABI) against the golden
+vectors produced by the reference's own functions and against the CPU oracle at a larger size.
+Tolerances: sums are fp32 with a different (atomic) order: 1e-5 relative; gradients 1e-4 relative."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "mask_stats_golden.npz")
+
+
+def _gm():
+    spec = importlib.util.spec_from_file_location("mmg", os.path.join(os.path.dirname(GOLD), "make_mask_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _close(a, b, rtol, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert np.abs(a - b).max() <= rtol * np.abs(b).max() + 1e-8, (what, np.abs(a - b).max(), np.abs(b).max())
+
+
+@pytest.mark.parametrize("name", ["stage1_6ch", "no_image_mask", "rgb_3ch"])
+def test_stage1_loss_vs_reference_golden(name):
+    from opengaussian_b200.mask_stats import cohesion_loss, mask_feature_mean, pair_mask_feature_mean, separation_loss
+    m, gold = _gm(), np.load(GOLD)
+    feat_np, masks_np, img_np = m.inputs(name)
+    feat = torch.from_numpy(feat_np).cuda().requires_grad_(True)
+    masks = torch.from_numpy(masks_np).cuda()
+    img = None if img_np is None else torch.from_numpy(img_np).cuda().requires_grad_(True)
+    mean = mask_feature_mean(feat, masks, image_mask=img)
+    lc = cohesion_loss(feat, masks, mean)
+    ls = separation_loss(mean, 1000)
+    (ls + 0.1 * lc).backward()
+    _close(mean.detach().cpu(), gold[f"{name}/mean"], 1e-5, "mean")
+    _close(lc.detach().cpu(), gold[f"{name}/cohesion"], 1e-5, "cohesion")
+    _close(ls.detach().cpu(), gold[f"{name}/separation"], 1e-5, "separation")
+    _close(feat.grad.cpu(), gold[f"{name}/dfeat"], 1e-4, "dfeat")
+    if img is not None:
+        _close(img.grad.cpu(), gold[f"{name}/dimg"], 1e-4, "dimg")
+    m2, var, cnt = mask_feature_mean(feat.detach(), masks, return_var=True)
+    _close(m2.cpu(), gold[f"{name}/mean_noimg"], 1e-5, "mean_noimg")
+    _close(var.cpu(), gold[f"{name}/var"], 1e-5, "var")
+    assert np.array_equal(cnt.cpu().numpy(), gold[f"{name}/cnt"])
+    pm = pair_mask_feature_mean(feat.detach().unsqueeze(0).repeat(3, 1, 1, 1), masks[:3])
+    _close(pm.cpu(), gold[f"{name}/pair_mean"], 1e-5, "pair_mean")
+
+
+def _sam_like_masks(M, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.zeros(H, W, dtype=torch.int64)
+    for m in range(1, M):        # overlapping rectangles painted in order: a partition into compact regions
+        y0, x0 = int(torch.randint(0, H - 8, (1,), generator=g)), int(torch.randint(0, W - 8, (1,), generator=g))
+        h, w = int(torch.randint(8, H // 3, (1,), generator=g)), int(torch.randint(8, W // 3, (1,), generator=g))
+        ids[y0:y0 + h, x0:x0 + w] = m
+    return torch.stack([(ids == m) for m in range(M)])
+
+
+def test_stage1_loss_vs_oracle_scannet_size():
+    """BASELINE config 3 image size (1296x968), 120 SAM-like masks, 6 channels: CUDA vs CPU oracle."""
+    from opengaussian_b200.mask_stats import cohesion_loss, mask_feature_mean
+    from oracle import mask_stats as oms
+    C, H, W, M = 6, 968, 1296, 120
+    g = torch.Generator().manual_seed(3)
+    feat0 = torch.rand(C, H, W, generator=g)
+    img0 = (torch.rand(1, H, W, generator=g) > 0.1).float() * torch.rand(1, H, W, generator=g)
+    masks = _sam_like_masks(M, H, W, 4)
+    res = {}
+    for dev in ("cpu", "cuda"):
+        feat = feat0.detach().clone().to(dev).requires_grad_(True)
+        img = img0.detach().clone().to(dev).requires_grad_(True)
+        mk = masks.to(dev)
+        if dev == "cpu":
+            mean = oms.mask_feature_mean(feat, mk, image_mask=img)
+            lc = oms.cohesion_loss(feat, mk, mean)
+        else:
+            mean = mask_feature_mean(feat, mk, image_mask=img)
+            lc = cohesion_loss(feat, mk, mean)
+        (mean.pow(2).sum() + lc).backward()
+        res[dev] = (mean.detach().cpu(), lc.detach().cpu(), feat.grad.cpu(), img.grad.cpu())
+    _close(res["cuda"][0], res["cpu"][0], 2e-5, "mean")
+    _close(res["cuda"][1], res["cpu"][1], 2e-5, "cohesion")
+    _close(res["cuda"][2], res["cpu"][2], 1e-4, "dfeat")
+    _close(res["cuda"][3], res["cpu"][3], 1e-4, "dimg")
+
+
+def test_empty_and_errors():
+    from opengaussian_b200 import _lib
+    from opengaussian_b200.mask_stats import cohesion_loss, mask_feature_mean
+    feat = torch.rand(6, 16, 20, device="cuda", requires_grad=True)
+    none = torch.zeros(0, 16, 20, dtype=torch.bool, device="cuda")
+    assert mask_feature_mean(feat, none).shape == (0, 6)
+    empty = torch.zeros(2, 16, 20, dtype=torch.bool, device="cuda")
+    mean = mask_feature_mean(feat, empty)
+    assert float(mean.abs().max()) == 0.0                       # 0 / clamp(0, min=1)
+    lc = cohesion_loss(feat, empty, mean)
+    lc.backward()
+    assert float(lc) == 0.0 and float(feat.grad.abs().max()) == 0.0
+    with pytest.raises(_lib.OgsError):
+        mask_feature_mean(torch.rand(5, 16, 20, device="cuda"), empty)      # unsupported channel count
+    with pytest.raises(_lib.OgsError):
+        mask_feature_mean(torch.rand(6, 16, 20), empty.cpu())                # no CPU path

@@ -204,3 +204,42 @@ def test_camera_matrices_vs_reference_graphics_utils():
         assert np.abs(c.camera_center.numpy() - gold[f"cam{i}_center"]).max() <= 1e-5
         assert abs(c.tanfovx - gold[f"cam{i}_tan"][0]) <= 1e-12 and abs(c.tanfovy - gold[f"cam{i}_tan"][1]) <= 1e-12
         assert np.abs(synth.projection_matrix(fx, fy).t().float().numpy() - gold[f"cam{i}_proj"]).max() <= 1e-6
+
+
+# ---- per-mask statistics / Stage-1 losses: oracle vs the reference's own functions (golden) ----
+MGOLD = os.path.join(os.path.dirname(__file__), "golden", "mask_stats_golden.npz")
+
+
+def _mask_golden_module():
+    spec = importlib.util.spec_from_file_location("mmg", os.path.join(os.path.dirname(MGOLD), "make_mask_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("name", ["stage1_6ch", "no_image_mask", "rgb_3ch"])
+def test_mask_stats_oracle_vs_reference_golden(name):
+    """oracle/mask_stats.py == utils/opengs_utlis.py::mask_feature_mean + train.py::cohesion_loss /
+    separation_loss run on the CPU (values and autograd gradients of the Stage-1 loss)."""
+    from oracle import mask_stats as oms
+    m, gold = _mask_golden_module(), np.load(MGOLD)
+    feat_np, masks_np, img_np = m.inputs(name)
+    feat = torch.from_numpy(feat_np).requires_grad_(True)
+    masks = torch.from_numpy(masks_np)
+    img = None if img_np is None else torch.from_numpy(img_np).requires_grad_(True)
+    mean = oms.mask_feature_mean(feat, masks, image_mask=img)
+    lc = oms.cohesion_loss(feat, masks, mean)
+    ls = oms.separation_loss(mean, 1000)
+    (ls + 0.1 * lc).backward()
+    assert np.abs(mean.detach().numpy() - gold[f"{name}/mean"]).max() <= 2e-6
+    assert abs(float(lc) - float(gold[f"{name}/cohesion"])) <= 2e-6
+    assert abs(float(ls) - float(gold[f"{name}/separation"])) <= 2e-6
+    gd = gold[f"{name}/dfeat"]
+    assert np.abs(feat.grad.numpy() - gd).max() <= 1e-5 * np.abs(gd).max() + 1e-9
+    if img is not None:
+        gi = gold[f"{name}/dimg"]
+        assert np.abs(img.grad.numpy() - gi).max() <= 1e-5 * np.abs(gi).max() + 1e-9
+    m2, var, cnt = oms.mask_feature_mean(feat.detach(), masks, return_var=True)
+    assert np.abs(m2.numpy() - gold[f"{name}/mean_noimg"]).max() <= 2e-6
+    assert np.abs(var.numpy() - gold[f"{name}/var"]).max() <= 2e-6
+    assert np.array_equal(cnt.numpy(), gold[f"{name}/cnt"])
