@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
 // LOOKBACK = false: plain scatter; the tile's exclusive digit offsets were computed beforehand
 //                   (rs_tile_hist_kernel / emit + rs_tile_scan_kernel) and are read from
 //                   tile_state[digit * ntiles + tile]; ghist holds the digit totals.
+#ifndef RS_MINB
+#define RS_MINB 2
+#endif
 template <typename KeyT, bool LOOKBACK, int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
                                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                              const uint32_t* __restrict__ n_ptr, uint32_t cap, int shift, int bits,
                                                              const uint32_t* __restrict__ ghist /*[256] of this pass*/,
@@ -102,10 +105,16 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __re
     uint32_t rank[ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* wh = s_wh + warp * RS_RADIX;
+    uint32_t val[ITEMS];   // values are fetched with the keys: their latency hides behind the ranking
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = wbase + i * 32 + lane;
         key[i] = idx < n ? (uint32_t)kin[idx] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        val[i] = idx < n ? vin[idx] : 0u;
     }
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_pass_kernel(const KeyT* __re
             const uint32_t d = (key[i] >> shift) & dmask;
             const uint32_t pos = s_dstart[d] + s_wh[warp * RS_RADIX + d] + rank[i];
             s_keys[pos] = (KeyT)key[i];
-            s_vals[pos] = vin[idx];
+            s_vals[pos] = val[i];
         }
     }
     __syncthreads();
