@@ -192,12 +192,40 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
                     const unsigned m = __ballot_sync(0xffffffffu, bit);
                     peers &= bit ? m : ~m;
                 }
-                const int rank = __popc(peers & ((1u << lane) - 1u));
-                int max_rank = active[q] ? rank : 0;
+                // (a) ids shared by >= 4 lanes (spatially coherent data puts whole warps into one cluster):
+                //     one butterfly reduction per such id, lane 0 adds the totals -- cost independent of
+                //     the multiplicity;  (b) the rest goes in rank order, at most 3 rounds.
+                bool pending = active[q];
+                unsigned heavy = __ballot_sync(0xffffffffu, pending && __popc(peers) >= 4);
+                while (heavy) {
+                    const int src = __ffs(heavy) - 1;
+                    const unsigned grp = __shfl_sync(0xffffffffu, peers, src);
+                    const int jj = __shfl_sync(0xffffffffu, best_j[q], src);
+                    const bool mine = (grp >> lane) & 1u;
+                    float v[D];
+#pragma unroll
+                    for (int d = 0; d < D; d++) v[d] = mine ? ((q & 1) ? X[q >> 1][d].y : X[q >> 1][d].x) : 0.f;
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1)
+#pragma unroll
+                        for (int d = 0; d < D; d++) v[d] += __shfl_xor_sync(0xffffffffu, v[d], m);
+                    if (lane == 0) {
+                        float* row = my_acc + jj * ROW;
+#pragma unroll
+                        for (int d = 0; d < D; d++) row[d] += v[d];
+                        row[D] += (float)__popc(grp);
+                    }
+                    if (mine) pending = false;
+                    heavy &= ~grp;
+                    __syncwarp();
+                }
+                const unsigned light = __ballot_sync(0xffffffffu, pending);
+                const int rank = __popc(peers & light & ((1u << lane) - 1u));
+                int max_rank = pending ? rank : 0;
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) max_rank = max(max_rank, __shfl_xor_sync(0xffffffffu, max_rank, m));
                 for (int r = 0; r <= max_rank; r++) {
-                    if (active[q] && rank == r) {
+                    if (pending && rank == r) {
                         float* row = my_acc + best_j[q] * ROW;
 #pragma unroll
                         for (int d = 0; d < D; d++) row[d] += (q & 1) ? X[q >> 1][d].y : X[q >> 1][d].x;

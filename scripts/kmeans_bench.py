@@ -16,12 +16,17 @@ def main():
     ap.add_argument("--k", type=int, default=64)
     ap.add_argument("--fuse", type=int, default=1)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--coherent", type=int, default=0, help="points of one cluster are contiguous in memory (trained scenes are spatially coherent)")
     a = ap.parse_args()
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(7)
     fa = torch.rand(a.N, 6, device=dev, generator=g)
     fb = (torch.rand(a.N, 3, device=dev, generator=g) - 0.5) * 8
     cen = torch.cat([fa[:a.k], fb[:a.k]], 1).contiguous()
+    if a.coherent:
+        own = (torch.arange(a.N, device=dev) * a.k // a.N)
+        fa = (cen[own, :6] + 0.01 * torch.randn(a.N, 6, device=dev, generator=g)).contiguous()
+        fb = (cen[own, 6:] + 0.01 * torch.randn(a.N, 3, device=dev, generator=g)).contiguous()
     ids = torch.empty(a.N, dtype=torch.int64, device=dev)
     s9 = torch.zeros(a.k, 9, device=dev)
     c1 = torch.zeros(a.k, device=dev)
