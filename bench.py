@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-kmeans", action="store_true")
     ap.add_argument("--views-per-step", type=int, default=2,
                     help="views each rank renders per step (gradients accumulate; ONE gradient all-reduce per step)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="side streams the views of a step are spread over (dist.render_views_backward)")
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events in the timed region")
     return ap.parse_args()
 
@@ -169,20 +171,23 @@ def run_ours(a):
         for t in grads:
             t.grad = None
 
-    from opengaussian_b200.dist import allreduce_gradients
+    from opengaussian_b200.dist import render_views_backward
     V = max(1, a.views_per_step)
+    S = max(1, min(a.streams, V))
 
     def frame(i, Gd):
-        """One step: this rank renders V views (fwd + bwd, gradients accumulate in .grad), then the
-        parameter gradients of all ranks are summed once (opengaussian_b200.dist)."""
+        """One step through the product's multi-view entry point (opengaussian_b200.dist):
+        this rank renders V views (fwd + bwd, gradients accumulate in .grad; the views are spread over S
+        streams so one view's binning runs under another's blending), then the parameter gradients of
+        all ranks are summed once."""
         zero_grads()
-        for v in range(V):
+
+        def view(v):
             rast = GaussianRasterizer(settings[(i * V + v) % len(settings)])
             color, radii, depth, alpha = rast(means2D=means2D, **params)
-            torch.autograd.backward((color, depth, alpha), (Gd[0:3], Gd[3:4], Gd[4:5]))
-        if world > 1:
-            allreduce_gradients(grads[:-1])
-        return color, radii
+            return (color, depth, alpha), (Gd[0:3], Gd[3:4], Gd[4:5])
+
+        render_views_backward(view, list(range(V)), grads[:-1], already_split=True, streams=S)
 
     def barrier():
         if world > 1:
@@ -266,18 +271,14 @@ def run_ours(a):
         Gd = G_dev[s]
         loss = (color * Gd[0:3]).sum() + (depth * Gd[3:4]).sum() + (alpha * Gd[4:5]).sum()
         loss.backward()
-        consumed[s].record()
+        consumed[s].record()          # the staged inputs are free again once the backward has used them
         return loss.detach()
 
     def e2e_step(i, nxt):
         """V views from pinned host inputs, one gradient all-reduce, one loss read-back."""
         zero_grads()
-        total = None
-        for v in range(V):
-            l = e2e_view(i * V + v, nxt or v + 1 < V)
-            total = l if total is None else total + l
-        if world > 1:
-            allreduce_gradients(grads[:-1])
+        total = render_views_backward(lambda v: e2e_view(i * V + v, nxt or v + 1 < V), list(range(V)), grads[:-1],
+                                      already_split=True, streams=S)
         return float(total.item())    # D2H read of the step's result
 
     for s in range(2):
@@ -368,7 +369,7 @@ def run_ours(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": a.workload, "gaussians": P, "image": [W, H], "sh_degree": 3, "views_per_rank": len(cams),
-                   "views_per_step_per_rank": V,
+                   "views_per_step_per_rank": V, "streams": S,
                    "gradients": "all inputs (means3D, means2D, opacities, shs, scales, rotations)",
                    "parallelism": f"view-parallel x{world}" + (" + one NCCL grad allreduce per step" if world > 1 else ""),
                    "l2": "inputs larger than L2 (236 MB parameters + 8 rotating views per rank)",

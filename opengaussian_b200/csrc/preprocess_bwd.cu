@@ -28,8 +28,11 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
 #ifndef PB
 #define PB 128   // Gaussians (= threads) per CTA: 25 KB SH slab, several CTAs per SM overlap their load / compute / store phases
 #endif
+#ifndef PB_MINB
+#define PB_MINB 8   // <= 64 registers: twice the resident warps outweighs ~70 B of spills (0.158 -> 0.144 ms)
+#endif
 template <bool STAGE_SH>
-__global__ void __launch_bounds__(PB, 4) preprocess_bwd_kernel(PreprocessBwdArgs a) {
+__global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessBwdArgs a) {
     extern __shared__ float s_sh[];
     __shared__ uint8_t s_vis[PB];
     const int i = blockIdx.x * PB + threadIdx.x;

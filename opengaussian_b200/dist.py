@@ -111,22 +111,68 @@ def gather_ids(local_ids: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([o[:int(s)] for o, s in zip(outs, sizes)])
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device, n):
+    key = (str(device), n)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device) for _ in range(n)]
+    return _SIDE_STREAMS[key]
+
+
 def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.Tensor], group=None,
-                          already_split: bool = False) -> Optional[torch.Tensor]:
+                          already_split: bool = False, streams: int = 1) -> Optional[torch.Tensor]:
     """One view-parallel step: this rank renders ITS views (`render_loss(view) -> scalar loss`),
     backpropagates, and the parameter gradients of all ranks are summed.  Equivalent to one
-    process rendering every view and summing the losses."""
+    process rendering every view and summing the losses.
+
+    ``streams > 1`` (CUDA only) round-robins the rank's views over that many side streams: the views of
+    a step are independent, so the latency-bound binning kernels (sorts, scans) of one view run under
+    the compute-bound blending of another.  Gradients still accumulate in ``.grad`` (autograd orders
+    the accumulation across streams); the caller's stream waits for every side stream before the
+    all-reduce."""
     mine = views if already_split else split_views(views, group)
-    total = None
-    for v in mine:
-        loss = render_loss(v)
-        loss.backward()
-        total = loss.detach() if total is None else total + loss.detach()
     params = list(params)
+    total = None
+
+    def run(v):
+        """render_loss may return a scalar loss, (outputs, grad_outputs) to be back-propagated as is, or
+        an already back-propagated (detached) loss."""
+        res = render_loss(v)
+        if isinstance(res, tuple):
+            torch.autograd.backward(res[0], res[1])
+            return None
+        if res.requires_grad:
+            res.backward()
+        return res.detach()
+
+    use_streams = streams > 1 and len(mine) > 1 and params and params[0].is_cuda
+    if use_streams:
+        dev = params[0].device
+        cur = torch.cuda.current_stream(dev)
+        side = _side_streams(dev, min(streams, len(mine)))
+        parts = []
+        for s in side:
+            s.wait_stream(cur)
+        for i, v in enumerate(mine):
+            s = side[i % len(side)]
+            with torch.cuda.stream(s):
+                part = run(v)
+                if part is not None:
+                    parts.append(part)
+        for s in side:
+            cur.wait_stream(s)
+        for p_ in parts:
+            p_.record_stream(cur)
+            total = p_ if total is None else total + p_
+    else:
+        for v in mine:
+            part = run(v)
+            if part is not None:
+                total = part if total is None else total + part
     allreduce_gradients(params, group)
     r, w = world(group)
-    if w > 1:
-        if total is None:
-            total = torch.zeros((), device=params[0].device)
+    if w > 1 and total is not None:
         dist.all_reduce(total, group=group)
     return total
