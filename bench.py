@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--no-kmeans", action="store_true")
     ap.add_argument("--views-per-step", type=int, default=2,
                     help="views each rank renders per step (gradients accumulate; ONE gradient all-reduce per step)")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=1,
                     help="side streams the views of a step are spread over (dist.render_views_backward)")
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events in the timed region")
     return ap.parse_args()
