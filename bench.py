@@ -269,7 +269,9 @@ def run_ours(a):
                                            3, cd[32:35], False, False)
         color, radii, depth, alpha = GaussianRasterizer(rs)(means2D=means2D, **params)
         Gd = G_dev[s]
-        loss = (color * Gd[0:3]).sum() + (depth * Gd[3:4]).sum() + (alpha * Gd[4:5]).sum()
+        # loss = <render outputs, staged gradient images> (one dot product per output tensor)
+        loss = (torch.dot(color.reshape(-1), Gd[0:3].reshape(-1)) + torch.dot(depth.reshape(-1), Gd[3:4].reshape(-1))
+                + torch.dot(alpha.reshape(-1), Gd[4:5].reshape(-1)))
         loss.backward()
         consumed[s].record()          # the staged inputs are free again once the backward has used them
         return loss.detach()

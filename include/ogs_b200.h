@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define OGS_ABI_VERSION 1
+#define OGS_ABI_VERSION 2
 #define OGS_TILE 16
 #define OGS_MAX_CHANNELS 16 /* 3 colour channels + n_extra <= OGS_MAX_CHANNELS */
 
@@ -67,7 +67,20 @@ typedef struct ogs_raster_inputs {
     const float* rotations; /* [P,4] or NULL (scales+rotations, or cov3D_precomp) */
     const float* cov3D_precomp;  /* [P,6] or NULL */
     const float* extra;     /* [P,n_extra] or NULL when n_extra == 0 */
+    /* ---- raw-parameter mode: the GaussianModel getters of
+     * scene/gaussian_model.py:122-169 folded into preprocess.  act_flags == 0 and shs_rest == NULL:
+     * every tensor is ACTIVATED, as the reference rasterizer receives them. ---- */
+    int32_t act_flags;      /* OGS_ACT_* bits */
+    int32_t reserved_;
+    const float* shs_rest;  /* if != NULL: `shs` is _features_dc [P,1,3] and this is _features_rest [P,M-1,3]
+                               (get_features' torch.cat is never materialised) */
 } ogs_raster_inputs;
+
+#define OGS_ACT_SCALE_EXP 1        /* scales are log-scales: exp() (get_scaling, :123-125) */
+#define OGS_ACT_ROT_NORMALIZE 2    /* rotations are unnormalised: x / max(|x|, 1e-12) (get_rotation, :131-133) */
+#define OGS_ACT_OPACITY_SIGMOID 4  /* opacities are logits: sigmoid() (get_opacity, :155-157) */
+#define OGS_ACT_EXTRA_UNIT_HALF 8  /* extra is raw ins_feat: (normalize(x) + 1) / 2 (get_ins_feat :161-169 and
+                                      gaussian_renderer/__init__.py:127) */
 
 typedef struct ogs_raster_outputs {
     float* color;    /* [3 + n_extra, H, W] planar */
@@ -104,6 +117,7 @@ typedef struct ogs_raster_grads_out {
     float* dL_drotations; /* [P,4] */
     float* dL_dcov3D;     /* [P,6] */
     float* dL_dextra;     /* [P,n_extra] */
+    float* dL_dshs_rest;  /* [P,M-1,3] when shs_rest is used (dL_dshs is then [P,1,3]) */
     void* scratch;        /* ogs_raster_backward_scratch_floats(P, n_extra) floats of caller workspace */
 } ogs_raster_grads_out;
 

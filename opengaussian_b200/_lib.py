@@ -21,7 +21,11 @@ class RasterInputs(C.Structure):
         ("bg", _fp), ("viewmatrix", _fp), ("projmatrix", _fp), ("campos", _fp),
         ("means3D", _fp), ("opacities", _fp), ("shs", _fp), ("colors_precomp", _fp),
         ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp), ("extra", _fp),
+        ("act_flags", C.c_int32), ("reserved_", C.c_int32), ("shs_rest", _fp),
     ]
+
+
+ACT_SCALE_EXP, ACT_ROT_NORMALIZE, ACT_OPACITY_SIGMOID, ACT_EXTRA_UNIT_HALF = 1, 2, 4, 8
 
 
 class RasterOutputs(C.Structure):
@@ -40,7 +44,7 @@ class RasterGradsIn(C.Structure):
 class RasterGradsOut(C.Structure):
     _fields_ = [("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dopacities", _fp), ("dL_dshs", _fp),
                 ("dL_dcolors_precomp", _fp), ("dL_dscales", _fp), ("dL_drotations", _fp),
-                ("dL_dcov3D", _fp), ("dL_dextra", _fp), ("scratch", _fp)]
+                ("dL_dcov3D", _fp), ("dL_dextra", _fp), ("dL_dshs_rest", _fp), ("scratch", _fp)]
 
 
 EXPORTS = {
@@ -86,7 +90,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ogs_abi_version() != 1:
+        if L.ogs_abi_version() != 2:
             raise OgsError("libogs_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

@@ -120,6 +120,12 @@ static int validate_inputs(const ogs_raster_inputs* in) {
         return -1;
     }
     if (in->prefiltered) { set_error("prefiltered=True is not supported"); return -1; }
+    if (in->shs_rest && (!in->shs || in->M < 2)) { set_error("shs_rest needs shs (= _features_dc) and M >= 2"); return -1; }
+    if ((in->act_flags & (OGS_ACT_SCALE_EXP | OGS_ACT_ROT_NORMALIZE)) && !(in->scales && in->rotations)) {
+        set_error("scale/rotation activations need scales and rotations");
+        return -1;
+    }
+    if ((in->act_flags & OGS_ACT_EXTRA_UNIT_HALF) && in->n_extra <= 0) { set_error("extra activation needs n_extra > 0"); return -1; }
     const int gx = (in->W + 15) / 16, gy = (in->H + 15) / 16;
     if ((int64_t)gx * gy > 65535) { set_error("image too large: %d tiles (max 65535)", gx * gy); return -1; }
     if (!in->bg || !in->viewmatrix || !in->projmatrix || !in->campos) { set_error("bg/viewmatrix/projmatrix/campos must be set"); return -1; }
@@ -184,7 +190,8 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     const int gx = (W + 15) / 16, gy = (H + 15) / 16, tiles = gx * gy;
     const bool has_sh = in->shs != nullptr;
 
-    const GeomLayout gl = GeomLayout::make(P, has_sh);
+    const int n_feat_act = (in->act_flags & OGS_ACT_EXTRA_UNIT_HALF) ? in->n_extra : 0;
+    const GeomLayout gl = GeomLayout::make(P, has_sh, n_feat_act);
     const ImgLayout il = ImgLayout::make(W, H);
     memset(st, 0, sizeof *st);
     st->geom = alloc(alloc_user, gl.total, "geom");
@@ -217,6 +224,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
 
         PreprocessArgs pa;
         pa.P = P; pa.D = in->sh_degree; pa.M = in->M; pa.W = W; pa.H = H;
+        pa.act_flags = in->act_flags; pa.n_extra = in->n_extra; pa.shs_rest = in->shs_rest; pa.extra = in->extra;
         pa.means3D = in->means3D; pa.scales = in->scales; pa.rotations = in->rotations;
         pa.cov3D_precomp = in->cov3D_precomp; pa.opacities = in->opacities; pa.shs = in->shs;
         pa.scale_modifier = in->scale_modifier; pa.tanfovx = in->tanfovx; pa.tanfovy = in->tanfovy;
@@ -281,7 +289,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         ba.W = W; ba.H = H; ba.C = C;
         ba.ranges = ranges; ba.point_list = point_list; ba.rec0 = g.rec0; ba.rec1 = g.rec1;
         ba.base = has_sh ? g.rgb : in->colors_precomp;
-        ba.extra = in->extra; ba.bg = in->bg;
+        ba.extra = n_feat_act ? g.feat : in->extra; ba.bg = in->bg;
         ba.out_color = out->color; ba.out_depth = out->depth; ba.out_alpha = out->alpha;
         ba.final_T = final_T; ba.n_contrib = n_contrib;
         prof_begin(PF_BLEND_FWD, s);
@@ -316,20 +324,22 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
     if (P == 0) return 0;
     const int gx = (W + 15) / 16, gy = (H + 15) / 16, tiles = gx * gy;
     const bool has_sh = in->shs != nullptr;
-    const GeomLayout gl = GeomLayout::make(P, has_sh);
+    const int n_feat_act = (in->act_flags & OGS_ACT_EXTRA_UNIT_HALF) ? in->n_extra : 0;
+    const GeomLayout gl = GeomLayout::make(P, has_sh, n_feat_act);
     const ImgLayout il = ImgLayout::make(W, H);
     const BinLayout bl = BinLayout::make(st->num_rendered, tiles);
     const GeomPtrs g = GeomPtrs::from(st->geom, gl);
 
-    const int geom = (go->dL_dmeans3D || go->dL_dmeans2D || go->dL_dopacities || go->dL_dshs || go->dL_dscales ||
-                      go->dL_drotations || go->dL_dcov3D) ? 1 : 0;
+    const int geom = (go->dL_dmeans3D || go->dL_dmeans2D || go->dL_dopacities || go->dL_dshs || go->dL_dshs_rest ||
+                      go->dL_dscales || go->dL_drotations || go->dL_dcov3D) ? 1 : 0;
+    if (go->dL_dshs_rest && !go->dL_dshs) { set_error("dL_dshs_rest needs dL_dshs"); return -1; }
     BlendBwdArgs ba;
     ba.P = P; ba.W = W; ba.H = H; ba.C = C;
     ba.ranges = (const uint2*)((char*)st->binning + bl.ranges);
     ba.point_list = (const uint32_t*)((char*)st->binning + bl.point_list);
     ba.rec0 = g.rec0; ba.rec1 = g.rec1;
     ba.base = has_sh ? g.rgb : in->colors_precomp;
-    ba.extra = in->extra; ba.bg = in->bg;
+    ba.extra = n_feat_act ? g.feat : in->extra; ba.bg = in->bg;
     ba.final_T = (const float*)((char*)st->image + il.final_T);
     ba.n_contrib = (const uint32_t*)((char*)st->image + il.n_contrib);
     ba.dL_dcolor = gin->dL_dcolor; ba.dL_ddepth = gin->dL_ddepth; ba.dL_dalpha = gin->dL_dalpha;
@@ -344,6 +354,8 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
 
     PreprocessBwdArgs pa;
     pa.P = P; pa.D = in->sh_degree; pa.M = in->M; pa.C = C; pa.W = W; pa.H = H;
+    pa.act_flags = in->act_flags; pa.shs_rest = in->shs_rest; pa.extra = in->extra; pa.opacities = in->opacities;
+    pa.dL_dshs_rest = go->dL_dshs_rest;
     pa.means3D = in->means3D; pa.scales = in->scales; pa.rotations = in->rotations;
     pa.cov3D_precomp = in->cov3D_precomp; pa.shs = in->shs;
     pa.scale_modifier = in->scale_modifier; pa.tanfovx = in->tanfovx; pa.tanfovy = in->tanfovy;
@@ -377,7 +389,7 @@ int ogs_raster_export(const ogs_raster_inputs* in, const ogs_raster_state* st, u
     const int P = in->P, W = in->W, H = in->H;
     const int gx = (W + 15) / 16, gy = (H + 15) / 16, tiles = gx * gy;
     const bool has_sh = in->shs != nullptr;
-    const GeomLayout gl = GeomLayout::make(P, has_sh);
+    const GeomLayout gl = GeomLayout::make(P, has_sh, (in->act_flags & OGS_ACT_EXTRA_UNIT_HALF) ? in->n_extra : 0);
     const ImgLayout il = ImgLayout::make(W, H);
     const BinLayout bl = BinLayout::make(st->num_rendered, tiles);
     const GeomPtrs g = GeomPtrs::from(st->geom, gl);

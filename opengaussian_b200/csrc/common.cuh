@@ -48,8 +48,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 // ---- geometry state layout (one caller-owned block, see ogs_raster_state::geom) ----
 struct GeomLayout {
-    size_t rec0, rec1, rgb, clamped, tiles, total;
-    __host__ static GeomLayout make(int P, bool has_sh) {
+    size_t rec0, rec1, rgb, clamped, tiles, feat, total;
+    __host__ static GeomLayout make(int P, bool has_sh, int n_feat_act = 0) {
         GeomLayout g;
         size_t o = 0;
         size_t n = (size_t)(P > 0 ? P : 1);
@@ -58,6 +58,7 @@ struct GeomLayout {
         g.rgb = o; if (has_sh) o = align_up(o + n * 12, 256);
         g.clamped = o; if (has_sh) o = align_up(o + n, 256);
         g.tiles = o; o = align_up(o + n * 4, 256);
+        g.feat = o; if (n_feat_act > 0) o = align_up(o + n * 4 * (size_t)n_feat_act, 256);   // activated extra channels
         g.total = o;
         return g;
     }
@@ -69,6 +70,7 @@ struct GeomPtrs {
     float* rgb;        // [P,3] SH colours (only with shs)
     uint8_t* clamped;  // bit c set: channel c was clamped at 0
     uint32_t* tiles;   // tiles_touched
+    float* feat;       // [P,n_extra] activated extra channels (raw-parameter mode only)
     __host__ static GeomPtrs from(void* base, const GeomLayout& l) {
         char* b = (char*)base;
         GeomPtrs p;
@@ -77,6 +79,7 @@ struct GeomPtrs {
         p.rgb = (float*)(b + l.rgb);
         p.clamped = (uint8_t*)(b + l.clamped);
         p.tiles = (uint32_t*)(b + l.tiles);
+        p.feat = (float*)(b + l.feat);
         return p;
     }
 };
@@ -108,6 +111,8 @@ struct ImgLayout {
 // ---- kernels launchers (defined in the per-family .cu files) ----
 struct PreprocessArgs {
     int P, D, M, W, H;
+    int act_flags, n_extra;         // raw-parameter mode (OGS_ACT_*), extra channel count
+    const float *shs_rest, *extra;  // split SH (see ogs_raster_inputs), raw extra channels
     const float *means3D, *scales, *rotations, *cov3D_precomp, *opacities, *shs;
     float scale_modifier, tanfovx, tanfovy;
     const float *view, *proj, *campos;
@@ -165,6 +170,9 @@ int launch_blend_backward(const BlendBwdArgs& a, cudaStream_t s);
 
 struct PreprocessBwdArgs {
     int P, D, M, C, W, H;
+    int act_flags;
+    const float *shs_rest, *extra, *opacities;
+    float* dL_dshs_rest;
     const float *means3D, *scales, *rotations, *cov3D_precomp, *shs;
     float scale_modifier, tanfovx, tanfovy;
     const float *view, *proj, *campos;

@@ -81,15 +81,20 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
 #pragma unroll
             for (int k = 0; k < 6; k++) c6[k] = a.cov3D_precomp[6 * (size_t)i + k];
         } else {
-            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            if (a.act_flags & OGS_ACT_ROT_NORMALIZE) {   // torch.nn.functional.normalize: x / max(|x|_2, 1e-12)
+                const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+                q.x /= nrm; q.y /= nrm; q.z /= nrm; q.w /= nrm;
+            }
             const float r = q.x, x = q.y, y = q.z, z = q.w;
             float R[3][3];
             R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
             R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
             R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
             const float mod = a.scale_modifier;
-            float s[3] = {mod * a.scales[3 * (size_t)i + 0], mod * a.scales[3 * (size_t)i + 1],
-                          mod * a.scales[3 * (size_t)i + 2]};
+            float s[3] = {a.scales[3 * (size_t)i + 0], a.scales[3 * (size_t)i + 1], a.scales[3 * (size_t)i + 2]};
+            if (a.act_flags & OGS_ACT_SCALE_EXP) { s[0] = expf(s[0]); s[1] = expf(s[1]); s[2] = expf(s[2]); }
+            s[0] = mod * s[0]; s[1] = mod * s[1]; s[2] = mod * s[2];
             float L[3][3];
 #pragma unroll
             for (int ii = 0; ii < 3; ii++)
@@ -151,7 +156,9 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
         radius_out = rad;
         tiles = (uint32_t)((y1 - y0) * (x1 - x0));
         r0 = make_float4(px, py, conA, conB);
-        r1 = make_float4(conC, a.opacities[i], pv2, __int_as_float(rad));
+        float opac = a.opacities[i];
+        if (a.act_flags & OGS_ACT_OPACITY_SIGMOID) opac = 1.0f / (1.0f + expf(-opac));
+        r1 = make_float4(conC, opac, pv2, __int_as_float(rad));
         dkey = __float_as_uint(pv2);
     } while (0);
 
@@ -160,6 +167,41 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
         s_vis[threadIdx.x] = visible;
         __syncthreads();
         const int per = a.M * 3;
+        if (a.shs_rest) {
+            // split SH: row = [_features_dc (3) | _features_rest ((M-1)*3)], two contiguous slabs
+            const int pr = per - 3;
+            const size_t base_dc = (size_t)blockIdx.x * PF * 3, base_r = (size_t)blockIdx.x * PF * pr;
+            const size_t tot_dc = (size_t)P * 3, tot_r = (size_t)P * pr;
+            for (int e = threadIdx.x; e < PF * 3; e += PF) {
+                const int gi = e / 3, k = e - gi * 3;
+                if (s_vis[gi] && base_dc + e < tot_dc) s_sh[gi * (per + 1) + k] = __ldg(a.shs + base_dc + e);
+            }
+            // the slab base is 16-byte aligned (PF * pr * 4 bytes per CTA); a float4 may straddle two rows
+            const float4* src = reinterpret_cast<const float4*>(a.shs_rest + base_r);
+            const int n4 = (PF * pr) / 4;
+            for (int e = threadIdx.x; e < n4; e += PF) {
+                const int f = e * 4;
+                const int g0 = f / pr, g3 = (f + 3) / pr;
+                if ((s_vis[g0] || s_vis[g3 < PF ? g3 : g0]) && base_r + f + 3 < tot_r) {
+                    const float4 q = __ldg(src + e);
+                    const float v4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const int gi = (f + t) / pr, k = (f + t) - gi * pr;
+                        if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = v4[t];
+                    }
+                } else if (base_r + f < tot_r) {   // ragged end of the tensor
+                    for (int t = 0; t < 4 && base_r + f + t < tot_r; t++) {
+                        const int gi = (f + t) / pr, k = (f + t) - gi * pr;
+                        if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + f + t);
+                    }
+                }
+            }
+            for (int e = n4 * 4 + threadIdx.x; e < PF * pr; e += PF) {
+                const int gi = e / pr, k = e - gi * pr;
+                if (s_vis[gi] && base_r + e < tot_r) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + e);
+            }
+        } else {
         const size_t base = (size_t)blockIdx.x * PF * per;
         if ((per & 3) == 0) {
             const float4* src = reinterpret_cast<const float4*>(a.shs + base);
@@ -177,6 +219,7 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
                 const int gi = e / per, k = e - gi * per;
                 if (s_vis[gi]) s_sh[gi * (per + 1) + k] = __ldg(a.shs + base + e);
             }
+        }
         }
         __syncthreads();
         if (visible) {
@@ -214,6 +257,14 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
     }
     if (!active) return;
 
+    if (visible && (a.act_flags & OGS_ACT_EXTRA_UNIT_HALF)) {
+        // (normalize(ins_feat) + 1) / 2 -- scene/gaussian_model.py:161-169 + gaussian_renderer/__init__.py:127
+        float n2 = 0.f;
+        for (int c = 0; c < a.n_extra; c++) { const float v = a.extra[(size_t)i * a.n_extra + c]; n2 += v * v; }
+        const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+        for (int c = 0; c < a.n_extra; c++)
+            a.g.feat[(size_t)i * a.n_extra + c] = (a.extra[(size_t)i * a.n_extra + c] / nrm + 1.0f) / 2.0f;
+    }
     a.radii[i] = radius_out;
     a.g.rec0[i] = r0;
     a.g.rec1[i] = r1;

@@ -43,6 +43,18 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
     if (STAGE_SH) {
         s_vis[threadIdx.x] = vis;
         __syncthreads();
+        if (a.shs_rest) {   // split SH: row = [_features_dc (3) | _features_rest ((M-1)*3)]
+            const int pr = per - 3;
+            const size_t base_dc = (size_t)blockIdx.x * PB * 3, base_r = (size_t)blockIdx.x * PB * pr;
+            for (int e = threadIdx.x; e < PB * 3; e += PB) {
+                const int gi = e / 3, k = e - gi * 3;
+                if (s_vis[gi]) s_sh[gi * (per + 1) + k] = __ldg(a.shs + base_dc + e);
+            }
+            for (int e = threadIdx.x; e < PB * pr; e += PB) {
+                const int gi = e / pr, k = e - gi * pr;
+                if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + e);
+            }
+        } else {
         const size_t base = (size_t)blockIdx.x * PB * per;
         const float4* src = reinterpret_cast<const float4*>(a.shs + base);
         for (int e = threadIdx.x; e < PB / 4 * per; e += PB) {     // PB * per / 4 float4 (per % 4 == 0)
@@ -54,19 +66,36 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
                 d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
             }
         }
+        }
         __syncthreads();
     }
     if (active) preprocess_bwd_body<STAGE_SH>(a, i, STAGE_SH ? s_sh + threadIdx.x * (per + 1) : nullptr, vis);
     if (STAGE_SH && a.dL_dshs) {
         __syncthreads();
-        const size_t base = (size_t)blockIdx.x * PB * per;
-        float4* dst = reinterpret_cast<float4*>(a.dL_dshs + base);
         const int rows = min(PB, a.P - blockIdx.x * PB);
-        for (int e = threadIdx.x; e < rows * per / 4; e += PB) {
-            const int f = e * 4;
-            const int gi = f / per, k = f - gi * per;
-            const float* d = s_sh + gi * (per + 1) + k;
-            dst[e] = make_float4(d[0], d[1], d[2], d[3]);
+        if (a.shs_rest) {
+            const int pr = per - 3;
+            float* dst_dc = a.dL_dshs + (size_t)blockIdx.x * PB * 3;
+            for (int e = threadIdx.x; e < rows * 3; e += PB) {
+                const int gi = e / 3, k = e - gi * 3;
+                dst_dc[e] = s_sh[gi * (per + 1) + k];
+            }
+            if (a.dL_dshs_rest) {
+                float* dst_r = a.dL_dshs_rest + (size_t)blockIdx.x * PB * pr;
+                for (int e = threadIdx.x; e < rows * pr; e += PB) {
+                    const int gi = e / pr, k = e - gi * pr;
+                    dst_r[e] = s_sh[gi * (per + 1) + 3 + k];
+                }
+            }
+        } else {
+            const size_t base = (size_t)blockIdx.x * PB * per;
+            float4* dst = reinterpret_cast<float4*>(a.dL_dshs + base);
+            for (int e = threadIdx.x; e < rows * per / 4; e += PB) {
+                const int f = e * 4;
+                const int gi = f / per, k = f - gi * per;
+                const float* d = s_sh + gi * (per + 1) + k;
+                dst[e] = make_float4(d[0], d[1], d[2], d[3]);
+            }
         }
     }
 }
@@ -82,7 +111,19 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
         for (int c = 0; c < 3; c++) a.dL_dcolors_precomp[3 * (size_t)i + c] = vis ? acc[c] : 0.f;
     }
     if (a.dL_dextra) {
-        for (int c = 3; c < C; c++) a.dL_dextra[(size_t)(C - 3) * i + (c - 3)] = vis ? acc[c] : 0.f;
+        const int F = C - 3;
+        if (vis && (a.act_flags & OGS_ACT_EXTRA_UNIT_HALF)) {
+            // f = (x / n + 1) / 2, n = max(|x|, 1e-12):  dL/dx = (g - u <u, g>) / (2 n),  u = x / n
+            float n2 = 0.f;
+            for (int c = 0; c < F; c++) { const float v = a.extra[(size_t)F * i + c]; n2 += v * v; }
+            const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+            float dotug = 0.f;
+            for (int c = 0; c < F; c++) dotug += (a.extra[(size_t)F * i + c] / nrm) * acc[3 + c];
+            for (int c = 0; c < F; c++)
+                a.dL_dextra[(size_t)F * i + c] = (acc[3 + c] - (a.extra[(size_t)F * i + c] / nrm) * dotug) / (2.0f * nrm);
+        } else {
+            for (int c = 3; c < C; c++) a.dL_dextra[(size_t)F * i + (c - 3)] = vis ? acc[c] : 0.f;
+        }
     }
     if (!a.geom) return;
 
@@ -117,19 +158,28 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
         float c6[6];
         float R[3][3];
         float s[3] = {0.f, 0.f, 0.f};
-        float qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        float qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, qnorm = 1.f;
+        float sact[3] = {0.f, 0.f, 0.f};
         if (a.cov3D_precomp) {
 #pragma unroll
             for (int k = 0; k < 6; k++) c6[k] = a.cov3D_precomp[6 * (size_t)i + k];
         } else {
-            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            if (a.act_flags & OGS_ACT_ROT_NORMALIZE) {
+                qnorm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+                q.x /= qnorm; q.y /= qnorm; q.z /= qnorm; q.w /= qnorm;
+            }
             qr = q.x; qx = q.y; qy = q.z; qz = q.w;
             const float r = qr, x = qx, y = qy, z = qz;
             R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
             R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
             R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
 #pragma unroll
-            for (int k = 0; k < 3; k++) s[k] = a.scale_modifier * a.scales[3 * (size_t)i + k];
+            for (int k = 0; k < 3; k++) {
+                sact[k] = a.scales[3 * (size_t)i + k];
+                if (a.act_flags & OGS_ACT_SCALE_EXP) sact[k] = expf(sact[k]);
+                s[k] = a.scale_modifier * sact[k];
+            }
             float L[3][3];
 #pragma unroll
             for (int ii = 0; ii < 3; ii++)
@@ -301,6 +351,19 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
             drot[1] = 2.f * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] - 2.f * x * dR[1][1] - r * dR[1][2] + z * dR[2][0] + r * dR[2][1] - 2.f * x * dR[2][2]);
             drot[2] = 2.f * (-2.f * y * dR[0][0] + x * dR[0][1] + r * dR[0][2] + x * dR[1][0] + z * dR[1][2] - r * dR[2][0] + z * dR[2][1] - 2.f * y * dR[2][2]);
             drot[3] = 2.f * (-2.f * z * dR[0][0] - r * dR[0][1] + x * dR[0][2] + r * dR[1][0] - 2.f * z * dR[1][1] + y * dR[1][2] + x * dR[2][0] + y * dR[2][1]);
+            if (a.act_flags & OGS_ACT_SCALE_EXP) {         // d exp(x) = exp(x) dx
+#pragma unroll
+                for (int j = 0; j < 3; j++) dscale[j] *= sact[j];
+            }
+            if (a.act_flags & OGS_ACT_ROT_NORMALIZE) {     // q = x / n:  dL/dx = (g - q <q, g>) / n
+                const float dq = r * drot[0] + x * drot[1] + y * drot[2] + z * drot[3];
+                drot[0] = (drot[0] - r * dq) / qnorm; drot[1] = (drot[1] - x * dq) / qnorm;
+                drot[2] = (drot[2] - y * dq) / qnorm; drot[3] = (drot[3] - z * dq) / qnorm;
+            }
+        }
+        if (a.act_flags & OGS_ACT_OPACITY_SIGMOID) {       // o = sigmoid(x): dL/dx = dL/do o (1 - o)
+            const float o = a.g.rec1[i].y;
+            dop *= o * (1.0f - o);
         }
     } else if (a.shs && (STAGE_SH || a.dL_dshs)) {
         float* dsh = STAGE_SH ? s_row : a.dL_dshs + (size_t)i * M * 3;
@@ -335,7 +398,10 @@ int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
     if (a.P <= 0) return 0;
     const int per = a.M * 3;
     const size_t smem = (size_t)PB * (per + 1) * sizeof(float);
-    if (a.geom && a.shs && (per % 4) == 0 && smem <= 100 * 1024) {
+    if (a.shs_rest && !(a.geom && smem <= 100 * 1024)) {
+        if (a.geom) { set_error("preprocess backward: split SH needs the staged path (M=%d too large)", a.M); return -3; }
+    }
+    if (a.geom && a.shs && (a.shs_rest || (per % 4) == 0) && smem <= 100 * 1024) {
         static bool attr_done = false;
         if (!attr_done) {
             cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);

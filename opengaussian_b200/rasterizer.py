@@ -78,11 +78,13 @@ _ALLOC_THUNK = _lib.ALLOC_FN(_Alloc._cb)
 
 
 def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities, shs, colors_precomp, scales,
-                 rotations, cov3D_precomp, extra, n_extra) -> _lib.RasterInputs:
+                 rotations, cov3D_precomp, extra, n_extra, shs_rest=None, act_flags=0) -> _lib.RasterInputs:
     ri = _lib.RasterInputs()
     ri.P = means3D.shape[0]
     ri.sh_degree = int(rs.sh_degree)
-    ri.M = 0 if shs is None else int(shs.shape[1])
+    ri.M = 0 if shs is None else int(shs.shape[1]) + (0 if shs_rest is None else int(shs_rest.shape[1]))
+    ri.act_flags = int(act_flags)
+    ri.shs_rest = _lib.ptr(shs_rest)
     ri.n_extra = n_extra
     ri.W = int(rs.image_width)
     ri.H = int(rs.image_height)
@@ -109,7 +111,7 @@ def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities,
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra,
-                raster_settings, extra_bg=None):
+                raster_settings, extra_bg=None, sh_rest=None, act_flags=0):
         L = _lib.lib()
         rs = raster_settings
         dev = means3D.device
@@ -123,6 +125,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         rotations = _f32c(rotations)
         cov3Ds_precomp = _f32c(cov3Ds_precomp)
         extra = _f32c(extra)
+        sh_rest = _f32c(sh_rest)
+        act_flags = int(act_flags)
+        if sh_rest is not None and sh is None:
+            raise _lib.OgsError("shs_rest needs shs (= _features_dc)")
         P = means3D.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
         n_extra_user = 0 if extra is None else int(extra.shape[1])
@@ -131,6 +137,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             c_tot = next((c for c in _SUPPORTED_C if c >= 3 + n_extra_user), None)
             if c_tot is None:
                 raise _lib.OgsError(f"extra_feats: at most {_SUPPORTED_C[-1] - 3} channels are supported")
+            if c_tot != 3 + n_extra_user and (act_flags & _lib.ACT_EXTRA_UNIT_HALF):
+                raise _lib.OgsError(f"raw extra_feats need 3 + F in {_SUPPORTED_C} (got F = {n_extra_user})")
             if c_tot != 3 + n_extra_user:   # pad with zero channels up to a compiled width
                 extra = torch.cat([extra, extra.new_zeros(P, c_tot - 3 - n_extra_user)], 1).contiguous()
                 n_extra = c_tot - 3
@@ -150,7 +158,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         radii = torch.empty(P, dtype=torch.int32, device=dev)
 
         ri = _fill_inputs(rs, bg_full, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
-                          extra, n_extra)
+                          extra, n_extra, sh_rest, act_flags)
         ro = _lib.RasterOutputs(_lib.ptr(color_all), _lib.ptr(depth), _lib.ptr(alpha), _lib.ptr(radii))
         st = _lib.RasterState()
         alloc = _Alloc(dev)
@@ -166,7 +174,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.n_extra = n_extra
         ctx.n_extra_user = n_extra_user
         ctx.num_rendered = int(st.num_rendered)
-        ctx.save_for_backward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra)
+        ctx.act_flags = act_flags
+        ctx.save_for_backward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra, sh_rest)
         ctx.mark_non_differentiable(radii)
         if n_extra != n_extra_user:
             color_all = color_all[:3 + n_extra_user]
@@ -175,7 +184,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_color_all, _grad_radii, grad_depth, grad_alpha):
         L = _lib.lib()
-        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra = ctx.saved_tensors
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra, sh_rest = ctx.saved_tensors
         rs = ctx.rs
         dev = means3D.device
         P = means3D.shape[0]
@@ -201,27 +210,33 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_rot = out(need[6] and rotations is not None, P, 4)
         g_cov = out(need[7] and cov3Ds_precomp is not None, P, 6)
         g_extra = out(need[8] and extra is not None, P, max(n_extra, 1))
+        need_rest = sh_rest is not None and need[11]
+        if need_rest and g_sh is None:          # the kernel writes both halves of the split SH gradient
+            g_sh = out(True, *sh.shape)
+        g_sh_rest = out(need_rest, *(sh_rest.shape if sh_rest is not None else (0,)))
         scratch = torch.empty(L.ogs_raster_backward_scratch_floats(P, n_extra), dtype=torch.float32, device=dev)
 
         ri = _fill_inputs(rs, ctx.bg_full, means3D, opacities, sh, colors_precomp, scales, rotations,
-                          cov3Ds_precomp, extra, n_extra)
+                          cov3Ds_precomp, extra, n_extra, sh_rest, ctx.act_flags)
         gi = _lib.RasterGradsIn(_lib.ptr(gc), _lib.ptr(gd), _lib.ptr(ga))
         go = _lib.RasterGradsOut(_lib.ptr(g_means3D), _lib.ptr(g_means2D), _lib.ptr(g_opac), _lib.ptr(g_sh),
                                  _lib.ptr(g_colors), _lib.ptr(g_scales), _lib.ptr(g_rot), _lib.ptr(g_cov),
-                                 _lib.ptr(g_extra), _lib.ptr(scratch))
+                                 _lib.ptr(g_extra), _lib.ptr(g_sh_rest), _lib.ptr(scratch))
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = L.ogs_raster_backward(C.byref(ri), C.byref(ctx.state), C.byref(gi), C.byref(go), C.c_void_p(stream))
         _lib.check(rc, "ogs_raster_backward")
         if g_extra is not None and n_extra != ctx.n_extra_user:
             g_extra = g_extra[:, :ctx.n_extra_user].contiguous()
-        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, g_extra, None, None
+        if not need[2]:
+            g_sh = None
+        return g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, g_extra, None, None, g_sh_rest, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, extra_feats=None, extra_bg=None):
+                        raster_settings, extra_feats=None, extra_bg=None, sh_rest=None, act_flags=0):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, extra_feats, raster_settings, extra_bg)
+                                     cov3Ds_precomp, extra_feats, raster_settings, extra_bg, sh_rest, act_flags)
 
 
 class GaussianRasterizer(nn.Module):
@@ -241,6 +256,22 @@ class GaussianRasterizer(nn.Module):
                 rc = L.ogs_mark_visible(pos.shape[0], _lib.ptr(pos), _lib.ptr(view), _lib.ptr(out), C.c_void_p(stream))
             _lib.check(rc, "ogs_mark_visible")
         return out.bool()
+
+    def forward_raw(self, means3D, means2D, opacity_logits, features_dc, features_rest, log_scales, raw_rotations,
+                    raw_ins_feat=None, extra_bg=None):
+        """Raw-parameter entry: takes GaussianModel's PARAMETERS (`_xyz, _opacity, _features_dc,
+        _features_rest, _scaling, _rotation, _ins_feat`) and folds the getters of scene/gaussian_model.py:122-169
+        -- exp, normalize, sigmoid, the get_features cat, and render()'s (normalize(ins_feat) + 1) / 2 -- into the
+        preprocess kernels, forward and backward.  Same return tuple as forward()."""
+        flags = _lib.ACT_SCALE_EXP | _lib.ACT_ROT_NORMALIZE | _lib.ACT_OPACITY_SIGMOID
+        if raw_ins_feat is not None:
+            flags |= _lib.ACT_EXTRA_UNIT_HALF
+        color_all, radii, depth, alpha = rasterize_gaussians(
+            means3D, means2D, features_dc, None, opacity_logits, log_scales, raw_rotations, None, self.raster_settings,
+            raw_ins_feat, extra_bg, features_rest, flags)
+        if raw_ins_feat is None:
+            return color_all, radii, depth, alpha
+        return color_all[:3], radii, depth, alpha, color_all[3:]
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None, extra_feats=None, extra_bg=None):

@@ -103,27 +103,6 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
 
     means3D = xyz
     means2D = screenspace_points
-    opacity = pc.get_opacity
-    scales = rotations = cov3D_precomp = None
-    if pipe.compute_cov3D_python:
-        cov3D_precomp = pc.get_covariance(scaling_modifier)
-    else:
-        scales = pc.get_scaling
-        rotations = pc.get_rotation
-
-    shs = colors_precomp = None
-    if override_color is None:
-        if pipe.convert_SHs_python:
-            from .sh import eval_sh
-            shs_view = pc.get_features.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
-            dir_pp = (pc.get_xyz - viewpoint_camera.camera_center.repeat(pc.get_features.shape[0], 1))
-            dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
-            sh2rgb = eval_sh(pc.active_sh_degree, shs_view, dir_pp_normalized)
-            colors_precomp = torch.clamp_min(sh2rgb + 0.5, 0.0)
-        else:
-            shs = pc.get_features
-    else:
-        colors_precomp = override_color
 
     # probabilistically rescale (same RNG draws as the reference, :121-124)
     prob = torch.rand(1)
@@ -132,6 +111,39 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
     if prob > 0.5 and rescale:
         rescale_factor = torch.rand(1).to(xyz.device)
         rescaled = True
+    one_pass = fused and render_color and render_feat_map and not rescaled
+
+    # Raw-parameter path: when this call is exactly one fused pass over the whole model,
+    # hand the PARAMETERS to the rasterizer and let preprocess apply the getters of
+    # scene/gaussian_model.py:122-169 (exp / normalize / sigmoid, no get_features cat, no ins_feat
+    # normalize) -- forward and backward -- instead of ~10 elementwise kernels and a 192 B/Gaussian copy.
+    needs_activated = (render_cluster and cluster_idx is not None) or \
+        (leaf_cluster_idx is not None and leaf_cluster_idx.numel() > 0)
+    raw_names = ("_xyz", "_opacity", "_scaling", "_rotation", "_features_dc", "_features_rest", "_ins_feat")
+    use_raw = (one_pass and not needs_activated and override_color is None and not pipe.compute_cov3D_python
+               and not pipe.convert_SHs_python and all(hasattr(pc, n) for n in raw_names)
+               and getattr(pipe, "raw_parameter_path", True))
+
+    opacity = scales = rotations = cov3D_precomp = shs = colors_precomp = None
+    if not use_raw:
+        opacity = pc.get_opacity
+        if pipe.compute_cov3D_python:
+            cov3D_precomp = pc.get_covariance(scaling_modifier)
+        else:
+            scales = pc.get_scaling
+            rotations = pc.get_rotation
+        if override_color is None:
+            if pipe.convert_SHs_python:
+                from .sh import eval_sh
+                shs_view = pc.get_features.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
+                dir_pp = (pc.get_xyz - viewpoint_camera.camera_center.repeat(pc.get_features.shape[0], 1))
+                dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+                sh2rgb = eval_sh(pc.active_sh_degree, shs_view, dir_pp_normalized)
+                colors_precomp = torch.clamp_min(sh2rgb + 0.5, 0.0)
+            else:
+                shs = pc.get_features
+        else:
+            colors_precomp = override_color
 
     def sc(s):
         return None if s is None else (s * rescale_factor if rescaled else s)
@@ -139,8 +151,16 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
     rendered_image = radii = rendered_depth = rendered_alpha = None
     rendered_ins_feat = silhouette = None
     bg3 = bg_color.reshape(-1).float()
-    one_pass = fused and render_color and render_feat_map and not rescaled
-    if one_pass:
+    if use_raw:
+        q = getattr(pc, "_ins_feat_q", None)
+        raw_feat = pc._ins_feat if (origin_feat or q is None or len(q) == 0) else q
+        nb = raw_feat.shape[-1]
+        ebg = torch.cat([bg3] * ((nb + 2) // 3))[:nb]
+        rendered_image, radii, rendered_depth, rendered_alpha, rendered_ins_feat = rasterizer.forward_raw(
+            means3D, means2D, pc._opacity, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation,
+            raw_ins_feat=raw_feat, extra_bg=ebg)
+        silhouette = rendered_alpha
+    elif one_pass:
         # ONE launch: RGB + feature channels + depth + alpha; silhouette == alpha (same geometry)
         ins_feat = (pc.get_ins_feat(origin=origin_feat) + 1) / 2
         nb = ins_feat.shape[-1]

@@ -155,3 +155,56 @@ def test_alias_packages_import():
     from opengaussian_b200 import rasterizer
     assert m1.GaussianRasterizer is rasterizer.GaussianRasterizer is m2.GaussianRasterizer
     assert math.isclose(1.0, 1.0)
+
+
+class FakeGaussiansRaw(FakeGaussians):
+    """Parameters laid out as GaussianModel holds them (_features_dc / _features_rest, scene/gaussian_model.py:66-69)."""
+
+    def __init__(self, gs, dev, geom_grad=True):
+        super().__init__(gs, dev, feat_grad=True, geom_grad=geom_grad)
+        f = gs["shs"].to(dev)
+        self._features_dc = f[:, :1].contiguous().requires_grad_(geom_grad)
+        self._features_rest = f[:, 1:].contiguous().requires_grad_(geom_grad)
+        self._rotation = (gs["rotations"] * 1.7).to(dev).requires_grad_(geom_grad)     # NOT unit length
+
+    get_features = property(lambda s: torch.cat((s._features_dc, s._features_rest), dim=1))
+
+
+@pytest.mark.parametrize("geom_grad", [True, False])
+def test_raw_parameter_path_equals_getter_path(geom_grad):
+    """render() on the raw parameters (activations folded into preprocess, split SH) must
+    equal render() on the getters' outputs -- images and the gradients w.r.t. every PARAMETER."""
+    from opengaussian_b200.renderer import render
+    dev = "cuda"
+    gs, cams = synth.make_scene("plumbing_10k_256", n_views=2)
+    cam = _cam(cams[0], dev)
+    bg = torch.tensor([0.2, 0.1, 0.3], device=dev)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    H, W = cam.image_height, cam.image_width
+    G = {k: torch.randn(c, H, W, device=dev, generator=gen) for k, c in (("render", 3), ("ins_feat", 6), ("depth", 1), ("alpha", 1))}
+    names = ["_xyz", "_scaling", "_rotation", "_opacity", "_features_dc", "_features_rest", "_ins_feat"]
+    res = {}
+    for raw in (True, False):
+        pc = FakeGaussiansRaw(gs, dev, geom_grad=geom_grad)
+        pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False,
+                                     raw_parameter_path=raw)
+        out = render(cam, pc, pipe, bg, 100, rescale=False)
+        loss = sum((out[k] * G[k]).sum() for k in G)
+        loss.backward()
+        res[raw] = (out, {n: getattr(pc, n).grad for n in names}, out["viewspace_points"].grad)
+    o1, g1, v1 = res[True]
+    o0, g0, v0 = res[False]
+    same = (o1["radii"] == o0["radii"]).float().mean()
+    assert float(same) >= 0.9995            # exp / sigmoid inside the kernel vs torch: a radius may flip by one
+    for k in ("render", "ins_feat", "depth", "alpha", "silhouette"):
+        d = (o1[k] - o0[k]).abs()
+        assert float(d.mean()) <= 1e-6 and float((d > 1e-4).float().mean()) <= 1e-3, k
+    for n in names:
+        if g0[n] is None:
+            assert g1[n] is None, n
+            continue
+        scale = float(g0[n].abs().max()) + 1e-12
+        bad = ((g1[n] - g0[n]).abs() > 2e-3 * scale).float().mean()
+        assert float(bad) <= 1e-3, (n, float((g1[n] - g0[n]).abs().max()) / scale)
+    if geom_grad:
+        assert float((v1 - v0).abs().max()) <= 2e-3 * float(v0.abs().max()) + 1e-9
