@@ -31,6 +31,29 @@ WORKLOAD = "lerf_1m_1080p"
 N_VIEWS = 8
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """NCCL (and friends) print banners such as 'NCCL version ...' on the C-level stdout; the contract is
+    ONE JSON line there.  Point fd 1 at stderr for the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, line)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -40,7 +63,7 @@ def parse():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kmeans", action="store_true")
-    ap.add_argument("--views-per-step", type=int, default=2,
+    ap.add_argument("--views-per-step", type=int, default=4,
                     help="views each rank renders per step (gradients accumulate; ONE gradient all-reduce per step)")
     ap.add_argument("--streams", type=int, default=1,
                     help="side streams the views of a step are spread over (dist.render_views_backward)")
@@ -146,6 +169,7 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    quiet_stdout()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -388,7 +412,7 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_frame_baseline(a.workload, steps=1, warmup=0)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -459,7 +483,7 @@ def run_reference(a):
            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 if __name__ == "__main__":

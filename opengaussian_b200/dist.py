@@ -46,6 +46,12 @@ def allreduce_gradients(params: Iterable[torch.Tensor], group=None, bucket_bytes
     if w == 1:
         return
     params = [p for p in params if p.requires_grad]
+    flat = _coalesced_grads(params)
+    if flat is not None:          # the rasterizer's backward carves all gradients out of one buffer
+        dist.all_reduce(flat, group=group)
+        if average:
+            flat.div_(w)
+        return
     bucket, size = [], 0
 
     def flush():
@@ -85,6 +91,22 @@ def allreduce_gradients(params: Iterable[torch.Tensor], group=None, bucket_bytes
         bucket.append(p)
         size += nbytes
     flush()
+
+
+def _coalesced_grads(params) -> Optional[torch.Tensor]:
+    """If every .grad is a contiguous fp32 view into ONE storage and together they (almost) tile a span of
+    it, returns that span as a flat tensor (alignment gaps between the slices ride along)."""
+    grads = [p.grad for p in params]
+    if len(grads) < 2 or any(g is None or g.dtype != torch.float32 or not g.is_contiguous() for g in grads):
+        return None
+    st = grads[0].untyped_storage()
+    if any(g.untyped_storage().data_ptr() != st.data_ptr() for g in grads):
+        return None
+    lo = min(g.storage_offset() for g in grads)
+    hi = max(g.storage_offset() + g.numel() for g in grads)
+    if hi - lo > sum(g.numel() for g in grads) + 64 * len(grads):
+        return None
+    return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, lo, (hi - lo,))
 
 
 def shard_kmeans(codebook, group=None):

@@ -198,22 +198,46 @@ class _RasterizeGaussians(torch.autograd.Function):
         gd = _f32c(grad_depth) if grad_depth is not None else None
         ga = _f32c(grad_alpha) if grad_alpha is not None else None
 
-        def out(flag, *shape):
-            return torch.empty(*shape, dtype=torch.float32, device=dev) if flag else None
+        # All parameter gradients are carved out of ONE flat buffer (64-float aligned slices): autograd
+        # adopts the views as .grad, and opengaussian_b200.dist.allreduce_gradients then reduces the whole
+        # buffer with a single NCCL call instead of one per tensor.
+        specs = []
 
-        g_means3D = out(need[0], P, 3)
-        g_means2D = out(need[1], P, 3)
-        g_sh = out(need[2] and sh is not None, *(sh.shape if sh is not None else (0,)))
-        g_colors = out(need[3] and colors_precomp is not None, P, 3)
-        g_opac = out(need[4], *opacities.shape)
-        g_scales = out(need[5] and scales is not None, P, 3)
-        g_rot = out(need[6] and rotations is not None, P, 4)
-        g_cov = out(need[7] and cov3Ds_precomp is not None, P, 6)
-        g_extra = out(need[8] and extra is not None, P, max(n_extra, 1))
+        def want(flag, *shape):
+            if not flag:
+                return None
+            n = 1
+            for d in shape:
+                n *= int(d)
+            specs.append((len(specs), tuple(int(d) for d in shape), n))
+            return len(specs) - 1
+
         need_rest = sh_rest is not None and need[11]
-        if need_rest and g_sh is None:          # the kernel writes both halves of the split SH gradient
-            g_sh = out(True, *sh.shape)
-        g_sh_rest = out(need_rest, *(sh_rest.shape if sh_rest is not None else (0,)))
+        i_means3D = want(need[0], P, 3)
+        i_opac = want(need[4], *opacities.shape)
+        i_sh = want((need[2] or need_rest) and sh is not None, *(sh.shape if sh is not None else (0,)))
+        i_sh_rest = want(need_rest, *(sh_rest.shape if sh_rest is not None else (0,)))
+        i_colors = want(need[3] and colors_precomp is not None, P, 3)
+        i_scales = want(need[5] and scales is not None, P, 3)
+        i_rot = want(need[6] and rotations is not None, P, 4)
+        i_cov = want(need[7] and cov3Ds_precomp is not None, P, 6)
+        i_extra = want(need[8] and extra is not None, P, max(n_extra, 1))
+        i_means2D = want(need[1], P, 3)            # last: it is a per-view statistic, not all-reduced
+        offs, total = [], 0
+        for _, _, n in specs:
+            offs.append(total)
+            total += (n + 63) // 64 * 64
+        flat = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+
+        def view(i):
+            if i is None:
+                return None
+            _, shape, n = specs[i]
+            return flat[offs[i]:offs[i] + n].view(shape)
+
+        g_means3D, g_opac, g_sh, g_sh_rest = view(i_means3D), view(i_opac), view(i_sh), view(i_sh_rest)
+        g_colors, g_scales, g_rot, g_cov = view(i_colors), view(i_scales), view(i_rot), view(i_cov)
+        g_extra, g_means2D = view(i_extra), view(i_means2D)
         scratch = torch.empty(L.ogs_raster_backward_scratch_floats(P, n_extra), dtype=torch.float32, device=dev)
 
         ri = _fill_inputs(rs, ctx.bg_full, means3D, opacities, sh, colors_precomp, scales, rotations,

@@ -365,3 +365,30 @@ def test_full_size_config_properties(scene, fused):
         assert frac_bad == 0.0, k
         assert float(dev.max()) <= 1e-4 * scale, k
         assert bool(torch.isfinite(g1).all())
+
+
+def test_gradients_share_one_flat_buffer():
+    """The backward carves every parameter gradient out of one buffer so that the multi-GPU step needs a
+    single all-reduce (dist._coalesced_grads); accumulating a second view keeps that property."""
+    from opengaussian_b200 import dist as ogdist
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    gs, cam = small_scene(P=500, W=64, H=48, seed=2)
+    c = _cuda(gs)
+    rs = _settings(cam, np.zeros(3, np.float32))
+    leaves = [c[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")]
+    m2 = torch.zeros(500, 3, device="cuda", requires_grad=True)
+    ref = None
+    for _ in range(2):
+        out = GaussianRasterizer(rs)(means3D=leaves[0], means2D=m2, opacities=leaves[1], shs=leaves[2], scales=leaves[3],
+                                     rotations=leaves[4])
+        (out[0].sum() + out[2].sum()).backward()
+        flat = ogdist._coalesced_grads(leaves)
+        assert flat is not None and flat.numel() >= sum(t.numel() for t in leaves)
+        if ref is None:
+            ref = [t.grad.clone() for t in leaves]
+    for t, r in zip(leaves, ref):           # second backward accumulated in place: grad == 2 * first
+        assert torch.allclose(t.grad, 2 * r, rtol=1e-4, atol=1e-6)
+    before = [t.grad.clone() for t in leaves]
+    flat.mul_(0.5)                          # the flat view aliases every gradient
+    for t, b in zip(leaves, before):
+        assert torch.allclose(t.grad, 0.5 * b)
