@@ -342,16 +342,15 @@ def run_ours(a):
             dist.broadcast(cen, 0)
         ids = torch.empty(Nk, dtype=torch.int64, device=dev)
 
-        s9 = torch.zeros(64, 9, device=dev)
-        c1 = torch.zeros(64, device=dev)
+        buf = torch.zeros(64 * 9 + 64, device=dev)      # [sums | counts] packed: one memset, one collective
+        s9 = buf[:64 * 9].view(64, 9)                   # (the layout Quantize_kMeans.cluster_assign uses)
+        c1 = buf[64 * 9:]
 
         def km_pass():
-            s9.zero_()
-            c1.zero_()
+            buf.zero_()
             kmeans_assign(fa, fb, 1.0, cen, ids_out=ids, sums=s9, counts=c1)
             if world > 1:
-                dist.all_reduce(s9)
-                dist.all_reduce(c1)
+                dist.all_reduce(buf)
 
         for _ in range(3):
             km_pass()
