@@ -17,14 +17,23 @@
  *       composites `n_extra` per-Gaussian feature channels (OpenGaussian's ins_feat) in the same
  *       pass, which replaces the 2x3-channel feature passes + silhouette pass of
  *       gaussian_renderer/__init__.py:125-163.
+ *       Raw-parameter mode (act_flags / shs_rest) additionally folds the GaussianModel getters of
+ *       scene/gaussian_model.py:122-169 and the (normalize(ins_feat)+1)/2 of
+ *       gaussian_renderer/__init__.py:127 into the same kernels.
  *   ogs_mark_visible             upstream GaussianRasterizer.markVisible (mark_visible symbol)
- *   ogs_raster_export_keys       debug view of the sorted (tile|depth) keys (upstream binningState)
+ *   ogs_raster_export            debug view of the geometry records and the sorted (tile|depth) keys
+ *                                (upstream geomState / binningState)
  *   ogs_kmeans_assign            scene/kmeans_quantize.py:38-55 (get_dist) + :181-182,:200-201,
  *                                :223-224,:237-238 (argmin) fused with :82-87,:183-187,:202-205
  *                                (one-hot centroid sums and counts)
  *   ogs_kmeans_finalize          scene/kmeans_quantize.py:208-214 (centres = sums / counts, reset)
  *   ogs_kmeans_gather_st         scene/kmeans_quantize.py:273-275 (gather centres, straight-through)
- *   ogs_kmeans_cluster_index     scene/kmeans_quantize.py:89-144 (equalize_cluster_size index lists)
+ *   ogs_kmeans_count             scene/kmeans_quantize.py:89-144 (equalize_cluster_size member counts)
+ *   ogs_mask_mean_forward/backward, ogs_mask_var_forward
+ *                                utils/opengs_utlis.py:240-283 (mask_feature_mean incl. return_var) and
+ *                                :184-201 (pair_mask_feature_mean)
+ *   ogs_cohesion_forward/backward
+ *                                train.py:102-121 (cohesion_loss)
  */
 #ifndef OGS_B200_H
 #define OGS_B200_H

@@ -6,12 +6,8 @@
 
 #include "../../include/ogs_b200.h"
 
-#define OGS_BLOCK 256              // pixels per tile CTA (16x16)
 #ifndef OGS_FWD_PAIRS
 #define OGS_FWD_PAIRS 1            // packed pixel pairs per lane in blend_fwd (1: 8x8 px per warp, 2: 8x16)
-#endif
-#ifndef OGS_BWD_PAIRS
-#define OGS_BWD_PAIRS 1
 #endif
 #define OGS_NUM_SMS 148
 
@@ -184,48 +180,6 @@ struct PreprocessBwdArgs {
 int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s);
 
 #ifdef __CUDACC__
-// Conservative test "can Gaussian (r0 = x,y,A,B ; r1 = C,opacity,..) reach alpha >= 1/255 anywhere in
-// the pixel rectangle [x0,x1] x [y0,y1]?".  alpha >= 1/255 needs q(d) = A dx^2 + 2 B dx dy + C dy^2
-// <= 2 ln(255 opacity); q is convex, so its minimum over the rectangle is 0 if the centre is inside,
-// else the smallest of the four clamped 1-D edge minima.  A small margin keeps the test conservative
-// under fp32 rounding: an entry is dropped only if it would have been skipped by every pixel.
-__device__ __forceinline__ bool ogs_rect_hit(const float4 r0, const float4 r1, float x0, float y0, float x1, float y1) {
-    const float A = r0.z, B = r0.w, C = r1.x;
-    const float o255 = 255.0f * r1.y;
-    if (!(o255 >= 1.0f)) return false;
-    if (!(A > 0.f && C > 0.f)) return true;
-    const float tau2 = 2.0f * __logf(o255);
-    const float dxl = r0.x - x1, dxh = r0.x - x0, dyl = r0.y - y1, dyh = r0.y - y0;
-    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;
-    const float nbc = -B / C, nba = -B / A;
-    float q = 3.0e38f;
-    {
-        const float c = dxl, d = fminf(dyh, fmaxf(dyl, nbc * c));
-        q = fminf(q, A * c * c + 2.f * B * c * d + C * d * d);
-    }
-    {
-        const float c = dxh, d = fminf(dyh, fmaxf(dyl, nbc * c));
-        q = fminf(q, A * c * c + 2.f * B * c * d + C * d * d);
-    }
-    {
-        const float c = dyl, d = fminf(dxh, fmaxf(dxl, nba * c));
-        q = fminf(q, A * d * d + 2.f * B * d * c + C * c * c);
-    }
-    {
-        const float c = dyh, d = fminf(dxh, fmaxf(dxl, nba * c));
-        q = fminf(q, A * d * d + 2.f * B * d * c + C * c * c);
-    }
-    return q <= tau2 * 1.001f + 1e-3f;
-}
-
-// Gaussian exponent at one pixel, with the rounding sequence pinned by explicit intrinsics so that
-// the forward and backward kernels take identical skip / contribute decisions:
-//   adx = (A dx) dx, bdx = B dx  (shared by the pixels of a column), power = -(B dx) dy - 0.5 (adx + (C dy) dy).
-__device__ __forceinline__ float ogs_power(float adx, float bdx, float Cc, float dy) {
-    const float q = __fmaf_rn(__fmul_rn(Cc, dy), dy, adx);
-    return __fmaf_rn(-bdx, dy, __fmul_rn(-0.5f, q));
-}
-
 // ---- blend kernels: staged (pre-scaled) Gaussian records and packed two-pixel arithmetic ----
 // The blend kernels stage each list entry in shared memory with the conic pre-multiplied so that
 // the exponent comes out directly in the log2 domain (one MUFU.EX2, no range fix-up):
@@ -257,8 +211,11 @@ __device__ __forceinline__ float2 ogs_pair_power(float adx, float bdx, float Cs,
     const float2 q = __ffma2_rn(t, dy, s2(adx));
     return __ffma2_rn(s2(bdx), dy, q);
 }
-// ogs_rect_hit on a staged record: alpha >= 1/255 somewhere in the rectangle needs
-// q'(d) = a dx^2 + 2 hb dx dy + c dy^2 <= log2(255 opacity) with a = -A', hb = -B'/2, c = -C'.
+// Conservative test on a staged record: "can this Gaussian reach alpha >= 1/255 anywhere in the pixel
+// rectangle [x0,x1] x [y0,y1]?"  That needs q'(d) = a dx^2 + 2 hb dx dy + c dy^2 <= log2(255 opacity)
+// with a = -A', hb = -B'/2, c = -C'.  q' is convex, so its minimum over the rectangle is 0 if the centre
+// is inside, else the smallest of the four clamped 1-D edge minima.  A small margin keeps the test
+// conservative under fp32 rounding: an entry is dropped only if every pixel would have skipped it.
 __device__ __forceinline__ bool ogs_rect_hit_s(const float4 sa, const float2 sb, float x0, float y0, float x1, float y1) {
     const float A = -sa.z, B = -0.5f * sa.w, C = -sb.x;
     const float o255 = 255.0f * sb.y;

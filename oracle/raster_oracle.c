@@ -8,7 +8,9 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  The product path
  * (opengaussian_b200/) never links, imports or calls anything in oracle/.
  *
- * PARITY UNPINNED: the rasterizer's CUDA source is a third-party dependency that is NOT
+ * PARITY UNPINNED for binning and blending (PARTIALLY PINNED for preprocess: SH colours, 3D covariance and
+ * camera conventions are checked against golden vectors produced by the reference's own Python code,
+ * tests/golden/make_raster_golden.py): the rasterizer's CUDA source is a third-party dependency that is NOT
  * present under /root/reference (submodules/ashawkey-diff-gaussian-rasterization.zip is
  * listed in .MISSING_LARGE_BLOBS; only pin: the commented
  * `ashawkey-diff-gaussian-rasterization==0.0.0` at environment.yml:118).  The reference
