@@ -368,6 +368,11 @@ def run_ours(a):
         km = {"metric": "kmeans assign+centroid-sum pass, k=64 D=9", "points": Nk * world, "ms_per_pass": kms,
               "gpts_per_s": Nk * world / kms / 1e6, "hbm_frac": (Nk * 44 / (kms / 1e3) / 1e9) / load_peaks()[0]}
 
+    # ---- Stage-1 training step (BASELINE config 3): fused render() + mask statistics + Stage-1 losses ----
+    stage1 = None
+    if not a.no_kmeans and world == 1:
+        stage1 = stage1_step(dev, e0, e1)
+
     # ---- roofline of the dominant kernel ----
     peak, peak_src = load_peaks()
     alg = algorithmic_bytes(P, P_vis, N_r, H, W, 3, 3, tile_bits)
@@ -408,12 +413,56 @@ def run_ours(a):
     }
     if km:
         out["kmeans"] = km
+    if stage1:
+        out["stage1_step"] = stage1
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_frame_baseline(a.workload, steps=1, warmup=0)
     if rank == 0:
         emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stage1_step(dev, e0, e1, iters=10):
+    """OpenGaussian's own training step (stage 1, train.py:352-456) on the synthetic ScanNet-like scene of
+    BASELINE config 3: ONE fused render (RGB + 6 feature channels + depth + alpha, raw parameters), per-mask
+    feature means over 120 SAM-like masks, cohesion + separation losses, backward to `_ins_feat`."""
+    import types
+    import torch
+    from opengaussian_b200 import synth
+    from opengaussian_b200.mask_stats import cohesion_loss, mask_feature_mean, separation_loss
+    from opengaussian_b200.renderer import render
+    name = "scannet_1m_1296x968"
+    gs, cams = synth.make_scene(name, n_views=4)
+    pc = synth.SynthModel(gs, dev, stage0=False)
+    pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
+    cam_ns = [types.SimpleNamespace(FoVx=c.FoVx, FoVy=c.FoVy, image_height=c.image_height, image_width=c.image_width,
+                                    world_view_transform=c.world_view_transform.to(dev),
+                                    full_proj_transform=c.full_proj_transform.to(dev),
+                                    camera_center=c.camera_center.to(dev), bClusterOccur=None) for c in cams]
+    H, W = cams[0].image_height, cams[0].image_width
+    masks = synth.sam_like_masks(120, H, W, 4).to(dev)
+    bg = torch.zeros(3, device=dev)
+
+    def step(i):
+        pc._ins_feat.grad = None
+        out = render(cam_ns[i % len(cam_ns)], pc, pipe, bg, 1000, rescale=False)
+        mean = mask_feature_mean(out["ins_feat"], masks, image_mask=out["silhouette"])
+        loss = separation_loss(mean, 1000) + 0.1 * cohesion_loss(out["ins_feat"], masks, mean)
+        loss.backward()
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(iters):
+        step(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"metric": "Stage-1 training steps/s (fused render + mask means + cohesion/separation losses, fwd+bwd)",
+            "workload": name, "masks": 120, "ms_per_step": ms, "steps_per_s": 1000.0 / ms,
+            "note": "the reference does 4 forward + 2 backward rasterizations and [M,6,H,W] mask tensors per step"}
 
 
 # --------------------------------------------------------------------------------------------

@@ -159,3 +159,49 @@ def make_scene(name: str, n_views: int = 8, seed: int = 0, P: int = None):
     gs = make_gaussians(P or P0, kind, seed, scale_mult=scale_mult)
     cams = orbit_cameras(n_views, rad, W, H, fovx, height)
     return gs, cams
+
+
+class SynthModel:
+    """The part of GaussianModel that render() consumes, on synthetic parameters: the PARAMETER tensors as
+    scene/gaussian_model.py:66-74 holds them (`_xyz, _scaling` (log), `_rotation` (unnormalised), `_opacity`
+    (logit), `_features_dc`, `_features_rest`, `_ins_feat`) and the getters of :122-169.  Used by the tests
+    and the Stage-1 leg of bench.py; stage0=True makes every parameter trainable, otherwise only `_ins_feat`
+    (OpenGaussian detaches the geometry from stage 1 on, train.py:431-436)."""
+
+    def __init__(self, gs, device, stage0: bool = False):
+        t = lambda x: x.to(device)  # noqa: E731
+        self._xyz = t(gs["means3D"]).requires_grad_(stage0)
+        self._scaling = t(torch.log(gs["scales"])).requires_grad_(stage0)
+        self._rotation = t(gs["rotations"] * 1.3).requires_grad_(stage0)
+        self._opacity = t(torch.logit(gs["opacities"].clamp(1e-4, 1 - 1e-4))).requires_grad_(stage0)
+        self._features_dc = t(gs["shs"][:, :1].contiguous()).requires_grad_(stage0)
+        self._features_rest = t(gs["shs"][:, 1:].contiguous()).requires_grad_(stage0)
+        self._ins_feat = t(gs["ins_feat"] * 2 - 1).requires_grad_(True)
+        self._ins_feat_q = None
+        self.active_sh_degree = int(gs.get("sh_degree", 3))
+        self.max_sh_degree = 3
+
+    def parameters(self):
+        return [self._xyz, self._scaling, self._rotation, self._opacity, self._features_dc, self._features_rest,
+                self._ins_feat]
+
+    get_xyz = property(lambda s: s._xyz)
+    get_scaling = property(lambda s: torch.exp(s._scaling))
+    get_rotation = property(lambda s: torch.nn.functional.normalize(s._rotation))
+    get_opacity = property(lambda s: torch.sigmoid(s._opacity))
+    get_features = property(lambda s: torch.cat((s._features_dc, s._features_rest), dim=1))
+
+    def get_ins_feat(self, origin=False):
+        f = self._ins_feat if (origin or self._ins_feat_q is None) else self._ins_feat_q
+        return torch.nn.functional.normalize(f, dim=1)
+
+
+def sam_like_masks(M: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
+    """[M,H,W] bool: a partition-like set of compact regions (rectangles painted in order), mask 0 = rest."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.zeros(H, W, dtype=torch.int64)
+    for m in range(1, M):
+        y0, x0 = int(torch.randint(0, H - 8, (1,), generator=g)), int(torch.randint(0, W - 8, (1,), generator=g))
+        h, w = int(torch.randint(8, H // 3, (1,), generator=g)), int(torch.randint(8, W // 3, (1,), generator=g))
+        ids[y0:y0 + h, x0:x0 + w] = m
+    return torch.stack([(ids == m) for m in range(M)])

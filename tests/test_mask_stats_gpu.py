@@ -52,13 +52,8 @@ def test_stage1_loss_vs_reference_golden(name):
 
 
 def _sam_like_masks(M, H, W, seed):
-    g = torch.Generator().manual_seed(seed)
-    ids = torch.zeros(H, W, dtype=torch.int64)
-    for m in range(1, M):        # overlapping rectangles painted in order: a partition into compact regions
-        y0, x0 = int(torch.randint(0, H - 8, (1,), generator=g)), int(torch.randint(0, W - 8, (1,), generator=g))
-        h, w = int(torch.randint(8, H // 3, (1,), generator=g)), int(torch.randint(8, W // 3, (1,), generator=g))
-        ids[y0:y0 + h, x0:x0 + w] = m
-    return torch.stack([(ids == m) for m in range(M)])
+    from opengaussian_b200 import synth
+    return synth.sam_like_masks(M, H, W, seed)
 
 
 def test_stage1_loss_vs_oracle_scannet_size():
