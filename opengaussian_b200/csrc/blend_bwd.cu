@@ -29,7 +29,9 @@
 
 namespace ogs {
 
+#ifndef BB
 #define BB 64            // Gaussians per backward batch
+#endif
 
 template <int CUR, int M>
 struct HalvingReduce {

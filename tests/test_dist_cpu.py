@@ -126,3 +126,25 @@ def test_sharded_kmeans_and_grad_allreduce_world2():
     assert np.allclose(res["g3"], np.full(2, 3.0, np.float32))           # rank 0 rendered views 0, 2, 4
     w_sum = sum((np.arange(6) * (i + 1)).sum() + 4 * i for i in v) + 3 * 2
     assert abs(res["total"] - w_sum) < 1e-3
+
+
+def test_coalesced_gradient_view_cpu():
+    """dist._coalesced_grads: gradients that are 64-float aligned views into one buffer (what the rasterizer's
+    backward hands to autograd) are recognised and aliased by ONE flat tensor; anything else is refused."""
+    import torch
+    from opengaussian_b200 import dist as ogdist
+    flat = torch.arange(64 * 5, dtype=torch.float32)
+    a, b, c = torch.zeros(10, 3), torch.zeros(7, 4), torch.zeros(5)
+    for t in (a, b, c):
+        t.requires_grad_(True)
+    a.grad = flat[0:30].view(10, 3)
+    b.grad = flat[64:92].view(7, 4)
+    c.grad = flat[128:133]
+    v = ogdist._coalesced_grads([a, b, c])
+    assert v is not None and v.numel() == 133
+    v.mul_(2.0)
+    assert float(a.grad[0, 1]) == 2.0 and float(b.grad[0, 0]) == 128.0 and float(c.grad[4]) == 264.0
+    c.grad = torch.zeros(5)                       # a gradient living elsewhere: no coalescing
+    assert ogdist._coalesced_grads([a, b, c]) is None
+    c.grad = None
+    assert ogdist._coalesced_grads([a, b, c]) is None
