@@ -94,27 +94,33 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
         self.ok = False
 
-    def run(self):
+    def prepare(self):
+        """NVML initialisation takes driver locks for ~100 ms: do it BEFORE the timed region, never inside."""
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
-                     0x4: "sw_power_cap"}
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
             self.ok = True
-            while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for bit, nm in names.items():
-                        if r & bit:
-                            self.reasons.add(nm)
-                except Exception:
-                    pass
-                time.sleep(0.2)
         except Exception:
             self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def result(self):
         if not self.ok or not self.sm:
@@ -232,10 +238,14 @@ def run_ours(a):
     tile_bits = max(1, (tiles - 1).bit_length())
 
     # ---- device-resident timing ----
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.prepare()
     for i in range(a.warmup):
         frame(i, G)
     barrier()
-    sampler = ClockSampler(physical_gpu_index(local))
+    import gc
+    gc.collect()
+    gc.disable()          # no cyclic-GC pause inside the timed regions
     sampler.start()
     _lib.profile_enable(not a.no_profile)
     _lib.profile_read()

@@ -84,11 +84,8 @@ int blend_bwd_stride(int C, int geom) { return geom ? C + 7 : C; }
 // PAIRS packed pixel pairs per lane: the warp's block is 8 x (8 * PAIRS) pixels and a 16x16 tile takes
 // 4 / PAIRS warps.  More pixels per lane amortise the cross-lane reduction and the per-entry loop
 // overhead (about half of the instructions at PAIRS = 1) at the price of coarser culling.
-#ifndef OGS_BWD_MINB
-#define OGS_BWD_MINB 1
-#endif
 template <int C, bool GEOM, int PAIRS>
-__global__ void __launch_bounds__(128 / PAIRS, (C <= 4 && PAIRS == 2) ? OGS_BWD_MINB : 1) blend_bwd_kernel(BlendBwdArgs a) {
+__global__ void __launch_bounds__(128 / PAIRS) blend_bwd_kernel(BlendBwdArgs a) {
     constexpr int BWD_THREADS = 128 / PAIRS, BWD_WARPS = 4 / PAIRS, NPX = 2 * PAIRS;
     constexpr int V = GEOM ? C + 7 : C;
     constexpr int CH = (C + 1 + 3) & ~3;  // colours + depth, padded to float4
