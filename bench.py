@@ -375,7 +375,21 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         kms = float(t_ms)
+        km_cpu = None
+        if rank == 0 and world == 1 and not a.no_cpu_baseline:
+            # CPU port (oracle/kmeans_oracle.c, scalar C, 1 thread) on BASELINE config 1's 200 k points
+            from oracle import kmeans as okm
+            n_s = 200_000
+            ca, cb, cc = fa[:n_s].cpu().numpy(), fb[:n_s].cpu().numpy(), cen.cpu().numpy()
+            okm.assign(ca[:1000], cb[:1000], 1.0, cc)
+            t0 = time.perf_counter()
+            ids_cpu = okm.assign(ca, cb, 1.0, cc)
+            okm.accumulate(ca, cb, 1.0, 64, ids_cpu)
+            dt = time.perf_counter() - t0
+            km_cpu = {"gpts_per_s": n_s / dt / 1e9, "cores": 1, "kind": "port",
+                      "sample": f"{n_s} points, one assign + centroid-sum pass through oracle/kmeans_oracle.c", "seconds": dt}
         km = {"metric": "kmeans assign+centroid-sum pass, k=64 D=9", "points": Nk * world, "ms_per_pass": kms,
+              "cpu_baseline": km_cpu,
               "gpts_per_s": Nk * world / kms / 1e6, "hbm_frac": (Nk * 44 / (kms / 1e3) / 1e9) / load_peaks()[0]}
 
     # ---- Stage-1 training step (BASELINE config 3): fused render() + mask statistics + Stage-1 losses ----
@@ -486,7 +500,12 @@ def cpu_frame_baseline(workload, steps, warmup):
     gs = synth.make_gaussians(P0, kind, 0, scale_mult=scale_mult)
     cams = synth.orbit_cameras(N_VIEWS, rad, W, H, fovx, height)
     g = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in gs.items()}
-    cores = int(lib().ogs_oracle_set_threads(0))
+    # every host thread this process may run on (torchrun exports OMP_NUM_THREADS=1: override it)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    cores = int(lib().ogs_oracle_set_threads(avail))
     rng = np.random.default_rng(0)
     gc = rng.standard_normal((3, H, W)).astype(np.float32)
     gd = rng.standard_normal((H, W)).astype(np.float32)
