@@ -310,25 +310,42 @@ def run_ours(a):
         consumed[s].record()          # the staged inputs are free again once the backward has used them
         return loss.detach()
 
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses = []
+
     def e2e_step(i, nxt):
-        """V views from pinned host inputs, one gradient all-reduce, one loss read-back."""
+        """V views from pinned host inputs, one gradient all-reduce, and the step's loss copied to pinned
+        host memory.  The copy is asynchronous; the host reads it one step later (read_loss), so that the
+        read-back of step i does not drain the GPU before step i+1 is queued -- every step's loss is still
+        read inside the timed region."""
         zero_grads()
         total = render_views_backward(lambda v: e2e_view(i * V + v, nxt or v + 1 < V), list(range(V)), grads[:-1],
                                       already_split=True, streams=S)
-        return float(total.item())    # D2H read of the step's result
+        loss_host[i % 2].copy_(total.reshape(1), non_blocking=True)
+        loss_ready[i % 2].record()
+
+    def read_loss(i):
+        loss_ready[i % 2].synchronize()
+        losses.append(float(loss_host[i % 2][0]))     # D2H result of step i, on the host
 
     for s in range(2):
         consumed[s].record()
     stage(0)
     for i in range(3):
         e2e_step(i, True)
+        read_loss(i)
     barrier()
     t0 = time.perf_counter()
     e0.record()
     for i in range(3, 3 + a.steps):
         e2e_step(i, i + 1 < 3 + a.steps)
+        if i > 3:
+            read_loss(i - 1)
+    read_loss(3 + a.steps - 1)
     e1.record()
     torch.cuda.synchronize()
+    assert len(losses) == 3 + a.steps and all(x == x for x in losses)    # every step's loss arrived, none is NaN
     ms_e2e = e0.elapsed_time(e1)
     wall_e2e = (time.perf_counter() - t0) * 1000.0
     barrier()
