@@ -44,7 +44,8 @@ class RasterGradsIn(C.Structure):
 class RasterGradsOut(C.Structure):
     _fields_ = [("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dopacities", _fp), ("dL_dshs", _fp),
                 ("dL_dcolors_precomp", _fp), ("dL_dscales", _fp), ("dL_drotations", _fp),
-                ("dL_dcov3D", _fp), ("dL_dextra", _fp), ("dL_dshs_rest", _fp), ("scratch", _fp)]
+                ("dL_dcov3D", _fp), ("dL_dextra", _fp), ("dL_dshs_rest", _fp), ("scratch", _fp),
+                ("accumulate", C.c_int32), ("reserved_", C.c_int32)]
 
 
 EXPORTS = {

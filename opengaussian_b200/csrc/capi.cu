@@ -355,7 +355,7 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
     PreprocessBwdArgs pa;
     pa.P = P; pa.D = in->sh_degree; pa.M = in->M; pa.C = C; pa.W = W; pa.H = H;
     pa.act_flags = in->act_flags; pa.shs_rest = in->shs_rest; pa.extra = in->extra; pa.opacities = in->opacities;
-    pa.dL_dshs_rest = go->dL_dshs_rest;
+    pa.dL_dshs_rest = go->dL_dshs_rest; pa.accumulate = go->accumulate;
     pa.means3D = in->means3D; pa.scales = in->scales; pa.rotations = in->rotations;
     pa.cov3D_precomp = in->cov3D_precomp; pa.shs = in->shs;
     pa.scale_modifier = in->scale_modifier; pa.tanfovx = in->tanfovx; pa.tanfovy = in->tanfovy;

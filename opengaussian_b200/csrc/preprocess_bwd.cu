@@ -19,6 +19,10 @@ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
                                  0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                  -0.5900435899266435f};
 
+// out = v, or out += v in accumulate mode (the caller hands the parameter's existing .grad: summing the
+// views of a step then costs one read of the old gradient here instead of a separate read-read-write pass)
+__device__ __forceinline__ void put(float* p, float v, bool accum) { *p = accum ? *p + v : v; }
+
 // STAGE_SH: the block's SH slab (visible rows only) is loaded with coalesced 16-byte loads into a
 // padded shared-memory layout, each thread overwrites its row in place with dL/dsh, and the slab
 // is written back coalesced -- instead of 48 strided 4-byte accesses per thread in each direction.
@@ -73,18 +77,21 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
     if (STAGE_SH && a.dL_dshs) {
         __syncthreads();
         const int rows = min(PB, a.P - blockIdx.x * PB);
+        const bool ac = a.accumulate;
         if (a.shs_rest) {
             const int pr = per - 3;
             float* dst_dc = a.dL_dshs + (size_t)blockIdx.x * PB * 3;
             for (int e = threadIdx.x; e < rows * 3; e += PB) {
                 const int gi = e / 3, k = e - gi * 3;
-                dst_dc[e] = s_sh[gi * (per + 1) + k];
+                if (!ac) dst_dc[e] = s_sh[gi * (per + 1) + k];
+                else if (s_vis[gi]) dst_dc[e] += s_sh[gi * (per + 1) + k];
             }
             if (a.dL_dshs_rest) {
                 float* dst_r = a.dL_dshs_rest + (size_t)blockIdx.x * PB * pr;
                 for (int e = threadIdx.x; e < rows * pr; e += PB) {
                     const int gi = e / pr, k = e - gi * pr;
-                    dst_r[e] = s_sh[gi * (per + 1) + 3 + k];
+                    if (!ac) dst_r[e] = s_sh[gi * (per + 1) + 3 + k];
+                    else if (s_vis[gi]) dst_r[e] += s_sh[gi * (per + 1) + 3 + k];
                 }
             }
         } else {
@@ -94,7 +101,11 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
                 const int f = e * 4;
                 const int gi = f / per, k = f - gi * per;
                 const float* d = s_sh + gi * (per + 1) + k;
-                dst[e] = make_float4(d[0], d[1], d[2], d[3]);
+                if (!ac) dst[e] = make_float4(d[0], d[1], d[2], d[3]);
+                else if (s_vis[gi]) {
+                    const float4 o = dst[e];
+                    dst[e] = make_float4(o.x + d[0], o.y + d[1], o.z + d[2], o.w + d[3]);
+                }
             }
         }
     }
@@ -108,7 +119,8 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
     // colour / feature gradients pass straight through
     if (a.dL_dcolors_precomp) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) a.dL_dcolors_precomp[3 * (size_t)i + c] = vis ? acc[c] : 0.f;
+        if (vis || !a.accumulate)
+            for (int c = 0; c < 3; c++) put(a.dL_dcolors_precomp + 3 * (size_t)i + c, vis ? acc[c] : 0.f, a.accumulate);
     }
     if (a.dL_dextra) {
         const int F = C - 3;
@@ -120,9 +132,10 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
             float dotug = 0.f;
             for (int c = 0; c < F; c++) dotug += (a.extra[(size_t)F * i + c] / nrm) * acc[3 + c];
             for (int c = 0; c < F; c++)
-                a.dL_dextra[(size_t)F * i + c] = (acc[3 + c] - (a.extra[(size_t)F * i + c] / nrm) * dotug) / (2.0f * nrm);
+                put(a.dL_dextra + (size_t)F * i + c, (acc[3 + c] - (a.extra[(size_t)F * i + c] / nrm) * dotug) / (2.0f * nrm), a.accumulate);
         } else {
-            for (int c = 3; c < C; c++) a.dL_dextra[(size_t)F * i + (c - 3)] = vis ? acc[c] : 0.f;
+            if (vis || !a.accumulate)
+                for (int c = 3; c < C; c++) put(a.dL_dextra + (size_t)F * i + (c - 3), vis ? acc[c] : 0.f, a.accumulate);
         }
     }
     if (!a.geom) return;
@@ -370,27 +383,29 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
         for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
     }
 
+    if (a.accumulate && !vis) return;          // nothing to add
+    const bool ac = a.accumulate;
     if (a.dL_dmeans3D) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) a.dL_dmeans3D[3 * (size_t)i + k] = dmean[k];
+        for (int k = 0; k < 3; k++) put(a.dL_dmeans3D + 3 * (size_t)i + k, dmean[k], ac);
     }
     if (a.dL_dmeans2D) {
-        a.dL_dmeans2D[3 * (size_t)i + 0] = dm2x;
-        a.dL_dmeans2D[3 * (size_t)i + 1] = dm2y;
-        a.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
+        put(a.dL_dmeans2D + 3 * (size_t)i + 0, dm2x, ac);
+        put(a.dL_dmeans2D + 3 * (size_t)i + 1, dm2y, ac);
+        if (!ac) a.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
     }
-    if (a.dL_dopacities) a.dL_dopacities[i] = dop;
+    if (a.dL_dopacities) put(a.dL_dopacities + i, dop, ac);
     if (a.dL_dscales) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) a.dL_dscales[3 * (size_t)i + k] = dscale[k];
+        for (int k = 0; k < 3; k++) put(a.dL_dscales + 3 * (size_t)i + k, dscale[k], ac);
     }
     if (a.dL_drotations) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) a.dL_drotations[4 * (size_t)i + k] = drot[k];
+        for (int k = 0; k < 4; k++) put(a.dL_drotations + 4 * (size_t)i + k, drot[k], ac);
     }
     if (a.dL_dcov3D) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)i + k] = dc6[k];
+        for (int k = 0; k < 6; k++) put(a.dL_dcov3D + 6 * (size_t)i + k, dc6[k], ac);
     }
 }
 
@@ -401,7 +416,12 @@ int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
     if (a.shs_rest && !(a.geom && smem <= 100 * 1024)) {
         if (a.geom) { set_error("preprocess backward: split SH needs the staged path (M=%d too large)", a.M); return -3; }
     }
-    if (a.geom && a.shs && (a.shs_rest || (per % 4) == 0) && smem <= 100 * 1024) {
+    const bool staged = a.geom && a.shs && (a.shs_rest || (per % 4) == 0) && smem <= 100 * 1024;
+    if (a.accumulate && a.geom && a.shs && a.dL_dshs && !staged) {
+        set_error("preprocess backward: accumulate mode needs the staged SH path (M=%d)", a.M);
+        return -3;
+    }
+    if (staged) {
         static bool attr_done = false;
         if (!attr_done) {
             cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);

@@ -144,7 +144,8 @@ def _side_streams(device, n):
 
 
 def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.Tensor], group=None,
-                          already_split: bool = False, streams: int = 1) -> Optional[torch.Tensor]:
+                          already_split: bool = False, streams: int = 1,
+                          fuse_accumulate: bool = True) -> Optional[torch.Tensor]:
     """One view-parallel step: this rank renders ITS views (`render_loss(view) -> scalar loss`),
     backpropagates, and the parameter gradients of all ranks are summed.  Equivalent to one
     process rendering every view and summing the losses.
@@ -153,7 +154,11 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
     Measured on B200 (1 M Gaussians, 1080p): +3 % at best -- the binning kernels' large CTAs do not get
     scheduled under a machine full of blend CTAs -- and occasional multi-millisecond allocator stalls,
     so the default stays 1.  Gradients still accumulate in ``.grad`` (autograd orders the accumulation
-    across streams); the caller's stream waits for every side stream before the all-reduce."""
+    across streams); the caller's stream waits for every side stream before the all-reduce.
+    ``fuse_accumulate`` lets the rasterizer's backward add the 2nd..Vth view's gradients straight into the
+    parameters' existing ``.grad`` inside its kernel (rasterizer.fuse_grad_accumulation) when the parameters
+    are fed to the rasterizer directly (leaf inputs, e.g. the raw-parameter path)."""
+    from .rasterizer import fuse_grad_accumulation
     mine = views if already_split else split_views(views, group)
     params = list(params)
     total = None
@@ -190,7 +195,8 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
             total = p_ if total is None else total + p_
     else:
         for v in mine:
-            part = run(v)
+            with fuse_grad_accumulation(fuse_accumulate):
+                part = run(v)
             if part is not None:
                 total = part if total is None else total + part
     allreduce_gradients(params, group)

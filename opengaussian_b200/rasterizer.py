@@ -108,6 +108,39 @@ def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities,
     return ri
 
 
+_FUSE_ACCUMULATE = False
+
+
+class fuse_grad_accumulation:
+    """Context manager: while active, a backward whose differentiable inputs are ALL leaves that already
+    hold a matching fp32 .grad adds its gradients straight into those tensors inside the preprocess-
+    backward kernel and hands autograd `None` for them -- instead of writing fresh gradients that
+    AccumulateGrad then adds in a separate read-read-write pass (0.08 ms per view at 1 M Gaussians).
+    Used by opengaussian_b200.dist.render_views_backward for the 2nd..Vth view of a step.  Gradient hooks
+    on those leaves do not see the fused contribution; anything that does not qualify falls back to the
+    normal path."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global _FUSE_ACCUMULATE
+        self.prev = _FUSE_ACCUMULATE
+        _FUSE_ACCUMULATE = self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _FUSE_ACCUMULATE
+        _FUSE_ACCUMULATE = self.prev
+        return False
+
+
+def _fusable_grad(t, shape):
+    g = t.grad
+    return (t.is_leaf and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == t.device
+            and tuple(g.shape) == tuple(shape))
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra,
@@ -115,6 +148,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         L = _lib.lib()
         rs = raster_settings
         dev = means3D.device
+        means2D_in = means2D
         if dev.type != "cuda":
             raise _lib.OgsError("GaussianRasterizer needs CUDA tensors (there is no CPU fallback)")
         means3D = _f32c(means3D)
@@ -175,6 +209,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.n_extra_user = n_extra_user
         ctx.num_rendered = int(st.num_rendered)
         ctx.act_flags = act_flags
+        ctx.inputs_ref = (means3D, means2D_in)
         ctx.save_for_backward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra, sh_rest)
         ctx.mark_non_differentiable(radii)
         if n_extra != n_extra_user:
@@ -238,6 +273,25 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_means3D, g_opac, g_sh, g_sh_rest = view(i_means3D), view(i_opac), view(i_sh), view(i_sh_rest)
         g_colors, g_scales, g_rot, g_cov = view(i_colors), view(i_scales), view(i_rot), view(i_cov)
         g_extra, g_means2D = view(i_extra), view(i_means2D)
+        # fused accumulation (see fuse_grad_accumulation): every requested gradient goes into the leaf's .grad
+        accumulate = 0
+        if _FUSE_ACCUMULATE and n_extra == ctx.n_extra_user:
+            pairs = [(ctx.inputs_ref[0], g_means3D), (ctx.inputs_ref[1], g_means2D), (sh, g_sh), (colors_precomp, g_colors),
+                     (opacities, g_opac), (scales, g_scales), (rotations, g_rot), (cov3Ds_precomp, g_cov),
+                     (extra, g_extra), (sh_rest, g_sh_rest)]
+            wanted = [(t, g) for t, g in pairs if g is not None]
+            if wanted and all(_fusable_grad(t, g.shape) for t, g in wanted) and (need[2] or g_sh is None):
+                accumulate = 1
+                g_means3D = ctx.inputs_ref[0].grad if g_means3D is not None else None
+                g_means2D = ctx.inputs_ref[1].grad if g_means2D is not None else None
+                g_sh = sh.grad if g_sh is not None else None
+                g_colors = colors_precomp.grad if g_colors is not None else None
+                g_opac = opacities.grad if g_opac is not None else None
+                g_scales = scales.grad if g_scales is not None else None
+                g_rot = rotations.grad if g_rot is not None else None
+                g_cov = cov3Ds_precomp.grad if g_cov is not None else None
+                g_extra = extra.grad if g_extra is not None else None
+                g_sh_rest = sh_rest.grad if g_sh_rest is not None else None
         scratch = torch.empty(L.ogs_raster_backward_scratch_floats(P, n_extra), dtype=torch.float32, device=dev)
 
         ri = _fill_inputs(rs, ctx.bg_full, means3D, opacities, sh, colors_precomp, scales, rotations,
@@ -245,11 +299,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         gi = _lib.RasterGradsIn(_lib.ptr(gc), _lib.ptr(gd), _lib.ptr(ga))
         go = _lib.RasterGradsOut(_lib.ptr(g_means3D), _lib.ptr(g_means2D), _lib.ptr(g_opac), _lib.ptr(g_sh),
                                  _lib.ptr(g_colors), _lib.ptr(g_scales), _lib.ptr(g_rot), _lib.ptr(g_cov),
-                                 _lib.ptr(g_extra), _lib.ptr(g_sh_rest), _lib.ptr(scratch))
+                                 _lib.ptr(g_extra), _lib.ptr(g_sh_rest), _lib.ptr(scratch), accumulate, 0)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = L.ogs_raster_backward(C.byref(ri), C.byref(ctx.state), C.byref(gi), C.byref(go), C.c_void_p(stream))
         _lib.check(rc, "ogs_raster_backward")
+        if accumulate:       # already added into the leaves' .grad
+            return (None,) * 13
         if g_extra is not None and n_extra != ctx.n_extra_user:
             g_extra = g_extra[:, :ctx.n_extra_user].contiguous()
         if not need[2]:

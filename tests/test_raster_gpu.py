@@ -392,3 +392,30 @@ def test_gradients_share_one_flat_buffer():
     flat.mul_(0.5)                          # the flat view aliases every gradient
     for t, b in zip(leaves, before):
         assert torch.allclose(t.grad, 0.5 * b)
+
+
+def test_fused_gradient_accumulation_equals_autograd():
+    """rasterizer.fuse_grad_accumulation: adding the 2nd..Vth view's gradients inside the kernel gives the
+    same sums as autograd's AccumulateGrad, and .grad stays one flat buffer."""
+    from opengaussian_b200 import dist as ogdist
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    gs, _ = small_scene(P=800, W=80, H=64, seed=4)
+    from opengaussian_b200 import synth
+    cams = synth.orbit_cameras(3, 3.5, 80, 64, 0.9, 0.8)
+    c = _cuda(gs)
+    res = {}
+    for fuse in (False, True):
+        leaves = [c[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")]
+        m2 = torch.zeros(800, 3, device="cuda", requires_grad=True)
+
+        def view(cam):
+            rs = _settings(cam, np.zeros(3, np.float32))._replace(debug=False)
+            out = GaussianRasterizer(rs)(means3D=leaves[0], means2D=m2, opacities=leaves[1], shs=leaves[2],
+                                         scales=leaves[3], rotations=leaves[4])
+            return (out[0] * out[0]).sum() + out[2].sum() + out[3].sum()
+
+        ogdist.render_views_backward(view, cams, leaves + [m2], already_split=True, fuse_accumulate=fuse)
+        assert ogdist._coalesced_grads(leaves) is not None
+        res[fuse] = [t.grad.clone() for t in leaves + [m2]]
+    for a, b in zip(res[True], res[False]):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-9
