@@ -19,9 +19,10 @@
 // ([c_0..c_D-1, cn], padded to float4s, broadcast LDS.128) is reused by all four points.
 //
 // Fusion: the centroid sums are accumulated in the SAME pass that assigns.  Each warp owns a
-// private [k][D+1] accumulator in shared memory; lanes with equal ids are serialised by their rank
-// inside the peer group (ballot per id bit), so every update is a plain LDS/FADD/STS (no shared or
-// global atomics) and the result is deterministic.  Block partials go to a [grid][k][D+1] scratch
+// private [k][D+1] accumulator in shared memory; lanes with equal ids (peer groups from one ballot per
+// id bit) are summed by pointer jumping over shuffles and only the group's lowest lane updates the
+// group's row, so every update is a plain LDS/FADD/STS (no shared or global atomics) and the result is
+// deterministic.  Block partials go to a [grid][k][D+1] scratch
 // that a second tiny kernel reduces in fixed order.
 // HBM-bound at the fine level (k <= 10), FP32-bound at the coarse level (k = 64, D = 9).
 #include "common.cuh"
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
         for (int q = 0; q < KM_PPT; q++)
             if (active[q]) ids_out[base + 32 * q] = id_offset + best_j[q];
         if (partials) {
-            // conflict-free, atomic-free accumulate: lanes sharing an id go in rank order
+            // conflict-free, atomic-free accumulate
 #pragma unroll
             for (int q = 0; q < KM_PPT; q++) {
                 unsigned peers = __ballot_sync(0xffffffffu, active[q]);
@@ -192,47 +193,35 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
                     const unsigned m = __ballot_sync(0xffffffffu, bit);
                     peers &= bit ? m : ~m;
                 }
-                // (a) ids shared by >= 4 lanes (spatially coherent data puts whole warps into one cluster):
-                //     one butterfly reduction per such id, lane 0 adds the totals -- cost independent of
-                //     the multiplicity;  (b) the rest goes in rank order, at most 3 rounds.
-                bool pending = active[q];
-                unsigned heavy = __ballot_sync(0xffffffffu, pending && __popc(peers) >= 4);
-                while (heavy) {
-                    const int src = __ffs(heavy) - 1;
-                    const unsigned grp = __shfl_sync(0xffffffffu, peers, src);
-                    const int jj = __shfl_sync(0xffffffffu, best_j[q], src);
-                    const bool mine = (grp >> lane) & 1u;
-                    float v[D];
+                // Segmented sum by pointer jumping: every lane links to the next higher lane with the same id;
+                // after ceil(log2(multiplicity)) rounds of  v += v[next]; next = next[next]  the lowest lane of
+                // each group holds the group's sums and is the only one to touch the group's row -- plain
+                // LDS/FADD/STS, no conflicts, a fixed summation order, and the cost grows with log2 of the
+                // multiplicity (spatially coherent data puts whole warps into one cluster).
+                const unsigned above = peers & ~((2u << lane) - 1u);
+                int nxt = (active[q] && above) ? __ffs(above) - 1 : -1;
+                const bool leader = active[q] && (peers & ((1u << lane) - 1u)) == 0u;
+                const int mult = __reduce_max_sync(0xffffffffu, active[q] ? __popc(peers) : 0);
+                float v[D];
 #pragma unroll
-                    for (int d = 0; d < D; d++) v[d] = mine ? ((q & 1) ? X[q >> 1][d].y : X[q >> 1][d].x) : 0.f;
+                for (int d = 0; d < D; d++) v[d] = active[q] ? ((q & 1) ? X[q >> 1][d].y : X[q >> 1][d].x) : 0.f;
+                for (int span = 1; span < mult; span <<= 1) {
+                    const int src = nxt >= 0 ? nxt : lane;
 #pragma unroll
-                    for (int m = 16; m >= 1; m >>= 1)
-#pragma unroll
-                        for (int d = 0; d < D; d++) v[d] += __shfl_xor_sync(0xffffffffu, v[d], m);
-                    if (lane == 0) {
-                        float* row = my_acc + jj * ROW;
-#pragma unroll
-                        for (int d = 0; d < D; d++) row[d] += v[d];
-                        row[D] += (float)__popc(grp);
+                    for (int d = 0; d < D; d++) {
+                        const float o = __shfl_sync(0xffffffffu, v[d], src);
+                        if (nxt >= 0) v[d] += o;
                     }
-                    if (mine) pending = false;
-                    heavy &= ~grp;
-                    __syncwarp();
+                    const int n2 = __shfl_sync(0xffffffffu, nxt, src);
+                    nxt = nxt >= 0 ? n2 : -1;
                 }
-                const unsigned light = __ballot_sync(0xffffffffu, pending);
-                const int rank = __popc(peers & light & ((1u << lane) - 1u));
-                int max_rank = pending ? rank : 0;
+                if (leader) {
+                    float* row = my_acc + best_j[q] * ROW;
 #pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) max_rank = max(max_rank, __shfl_xor_sync(0xffffffffu, max_rank, m));
-                for (int r = 0; r <= max_rank; r++) {
-                    if (pending && rank == r) {
-                        float* row = my_acc + best_j[q] * ROW;
-#pragma unroll
-                        for (int d = 0; d < D; d++) row[d] += (q & 1) ? X[q >> 1][d].y : X[q >> 1][d].x;
-                        row[D] += 1.0f;
-                    }
-                    __syncwarp();
+                    for (int d = 0; d < D; d++) row[d] += v[d];
+                    row[D] += (float)__popc(peers);
                 }
+                __syncwarp();
             }
         }
         if (staged) __syncthreads();   // everyone is done with s_pts[buf] before it is refilled two tiles from now
