@@ -29,9 +29,14 @@
 
 namespace ogs {
 
+#ifndef KM_THREADS
 #define KM_THREADS 256
+#endif
+#define KM_WARPS (KM_THREADS / 32)
 #define KM_MAX_D 16
-#define KM_PPT 4                              // points per thread (two packed pairs)
+#ifndef KM_PPT
+#define KM_PPT 4                              // points per thread (packed pairs)
+#endif
 #define KM_CTA_POINTS (KM_THREADS * KM_PPT)   // 1024
 
 // ---- TMA bulk copy (global -> shared, completion on an mbarrier) ----
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
     const int tile_floats = KM_CTA_POINTS * D;            // a rows then b rows of one tile
     float* s_pts = smem;                                  // [2][tile_floats]
     float* s_c = smem + 2 * (size_t)tile_floats;          // [k][DP]
-    float* s_acc = s_c + (size_t)k * DP;                  // [8][k][D+1] (only when partials)
+    float* s_acc = s_c + (size_t)k * DP;                  // [KM_WARPS][k][D+1] (only when partials)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int j = threadIdx.x; j < k; j += KM_THREADS) {
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
         for (int d = D + 1; d < DP; d++) s_c[j * DP + d] = 0.f;
     }
     if (partials)
-        for (int e = threadIdx.x; e < 8 * k * ROW; e += KM_THREADS) s_acc[e] = 0.f;
+        for (int e = threadIdx.x; e < KM_WARPS * k * ROW; e += KM_THREADS) s_acc[e] = 0.f;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
         for (int e = threadIdx.x; e < k * ROW; e += KM_THREADS) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; w++) s += s_acc[(size_t)w * k * ROW + e];
+            for (int w = 0; w < KM_WARPS; w++) s += s_acc[(size_t)w * k * ROW + e];
             out[e] = s;
         }
     }
@@ -256,7 +261,7 @@ static int launch_assign_d(int64_t N, const float* a, int Da, const float* b, in
                            int64_t id_offset, int64_t* ids_out, float* sums, float* counts, cudaStream_t s) {
     const bool fuse = (sums != nullptr) || (counts != nullptr);
     size_t smem = (size_t)2 * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
-    if (fuse) smem += (size_t)8 * k * (D + 1) * sizeof(float);
+    if (fuse) smem += (size_t)KM_WARPS * k * (D + 1) * sizeof(float);
     if (smem > 220 * 1024) { set_error("kmeans_assign: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
