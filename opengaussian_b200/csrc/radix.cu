@@ -8,7 +8,7 @@
 //   1. rs_hist_kernel: digit histograms of ALL passes in one sweep over the keys;
 //   2. rs_pass_kernel ("onesweep"): a CTA takes a 4096-item tile through a ticket counter (so that
 //      tile t only ever waits on tiles < t that have already started), ranks its keys stably
-//      (__match_any_sync peer groups + per-warp digit counters), publishes its digit counts and
+//      (peer groups from one ballot per digit bit + per-warp digit counters), publishes its digit counts and
 //      resolves its global digit offsets by decoupled look-back over the preceding tiles' published
 //      (aggregate | inclusive) words, reorders keys/values by local rank in shared memory and writes
 //      each digit run with coalesced stores.
