@@ -128,8 +128,9 @@ typedef struct ogs_raster_grads_out {
     float* dL_dextra;     /* [P,n_extra] */
     float* dL_dshs_rest;  /* [P,M-1,3] when shs_rest is used (dL_dshs is then [P,1,3]) */
     void* scratch;        /* ogs_raster_backward_scratch_floats(P, n_extra) floats of caller workspace */
-    int32_t accumulate;   /* != 0: the outputs hold gradients of earlier views and are ADDED to (summing the views
-                             of a step costs one read of the old gradient instead of a separate add pass) */
+    int32_t accumulate;   /* bit 0: the parameter-gradient outputs hold the gradients of earlier views and are ADDED to
+                             (summing the views of a step costs one read of the old gradient instead of a separate
+                             add pass); bit 1: dL_dmeans2D is added to as well (otherwise it is written) */
     int32_t reserved_;
 } ogs_raster_grads_out;
 

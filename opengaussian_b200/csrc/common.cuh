@@ -167,7 +167,7 @@ int launch_blend_backward(const BlendBwdArgs& a, cudaStream_t s);
 struct PreprocessBwdArgs {
     int P, D, M, C, W, H;
     int act_flags;
-    int accumulate;                 // != 0: every gradient output is ADDED to (invisible Gaussians are skipped)
+    int accumulate;                 // bit 0: parameter gradients are ADDED to (invisible Gaussians skipped); bit 1: dL_dmeans2D too
     const float *shs_rest, *extra, *opacities;
     float* dL_dshs_rest;
     const float *means3D, *scales, *rotations, *cov3D_precomp, *shs;

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
     if (STAGE_SH && a.dL_dshs) {
         __syncthreads();
         const int rows = min(PB, a.P - blockIdx.x * PB);
-        const bool ac = a.accumulate;
+        const bool ac = (a.accumulate & 1) != 0;
         if (a.shs_rest) {
             const int pr = per - 3;
             float* dst_dc = a.dL_dshs + (size_t)blockIdx.x * PB * 3;
@@ -119,8 +119,8 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
     // colour / feature gradients pass straight through
     if (a.dL_dcolors_precomp) {
 #pragma unroll
-        if (vis || !a.accumulate)
-            for (int c = 0; c < 3; c++) put(a.dL_dcolors_precomp + 3 * (size_t)i + c, vis ? acc[c] : 0.f, a.accumulate);
+        if (vis || !(a.accumulate & 1))
+            for (int c = 0; c < 3; c++) put(a.dL_dcolors_precomp + 3 * (size_t)i + c, vis ? acc[c] : 0.f, (a.accumulate & 1) != 0);
     }
     if (a.dL_dextra) {
         const int F = C - 3;
@@ -132,10 +132,10 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
             float dotug = 0.f;
             for (int c = 0; c < F; c++) dotug += (a.extra[(size_t)F * i + c] / nrm) * acc[3 + c];
             for (int c = 0; c < F; c++)
-                put(a.dL_dextra + (size_t)F * i + c, (acc[3 + c] - (a.extra[(size_t)F * i + c] / nrm) * dotug) / (2.0f * nrm), a.accumulate);
+                put(a.dL_dextra + (size_t)F * i + c, (acc[3 + c] - (a.extra[(size_t)F * i + c] / nrm) * dotug) / (2.0f * nrm), (a.accumulate & 1) != 0);
         } else {
-            if (vis || !a.accumulate)
-                for (int c = 3; c < C; c++) put(a.dL_dextra + (size_t)F * i + (c - 3), vis ? acc[c] : 0.f, a.accumulate);
+            if (vis || !(a.accumulate & 1))
+                for (int c = 3; c < C; c++) put(a.dL_dextra + (size_t)F * i + (c - 3), vis ? acc[c] : 0.f, (a.accumulate & 1) != 0);
         }
     }
     if (!a.geom) return;
@@ -383,16 +383,20 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
         for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
     }
 
-    if (a.accumulate && !vis) return;          // nothing to add
-    const bool ac = a.accumulate;
+    // accumulate bit 0: the parameter gradients are added to; bit 1: dL_dmeans2D too (it is a per-view statistic
+    // -- render() feeds a fresh tensor every call -- so it usually is NOT accumulated)
+    const bool ac = (a.accumulate & 1) != 0, ac2 = (a.accumulate & 2) != 0;
+    if (a.dL_dmeans2D) {
+        if (vis || !ac2) {
+            put(a.dL_dmeans2D + 3 * (size_t)i + 0, dm2x, ac2);
+            put(a.dL_dmeans2D + 3 * (size_t)i + 1, dm2y, ac2);
+            if (!ac2) a.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
+        }
+    }
+    if (ac && !vis) return;                    // nothing to add
     if (a.dL_dmeans3D) {
 #pragma unroll
         for (int k = 0; k < 3; k++) put(a.dL_dmeans3D + 3 * (size_t)i + k, dmean[k], ac);
-    }
-    if (a.dL_dmeans2D) {
-        put(a.dL_dmeans2D + 3 * (size_t)i + 0, dm2x, ac);
-        put(a.dL_dmeans2D + 3 * (size_t)i + 1, dm2y, ac);
-        if (!ac) a.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
     }
     if (a.dL_dopacities) put(a.dL_dopacities + i, dop, ac);
     if (a.dL_dscales) {
@@ -417,7 +421,7 @@ int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
         if (a.geom) { set_error("preprocess backward: split SH needs the staged path (M=%d too large)", a.M); return -3; }
     }
     const bool staged = a.geom && a.shs && (a.shs_rest || (per % 4) == 0) && smem <= 100 * 1024;
-    if (a.accumulate && a.geom && a.shs && a.dL_dshs && !staged) {
+    if ((a.accumulate & 1) && a.geom && a.shs && a.dL_dshs && !staged) {
         set_error("preprocess backward: accumulate mode needs the staged SH path (M=%d)", a.M);
         return -3;
     }

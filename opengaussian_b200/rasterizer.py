@@ -276,14 +276,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         # fused accumulation (see fuse_grad_accumulation): every requested gradient goes into the leaf's .grad
         accumulate = 0
         if _FUSE_ACCUMULATE and n_extra == ctx.n_extra_user:
-            pairs = [(ctx.inputs_ref[0], g_means3D), (ctx.inputs_ref[1], g_means2D), (sh, g_sh), (colors_precomp, g_colors),
+            pairs = [(ctx.inputs_ref[0], g_means3D), (sh, g_sh), (colors_precomp, g_colors),
                      (opacities, g_opac), (scales, g_scales), (rotations, g_rot), (cov3Ds_precomp, g_cov),
                      (extra, g_extra), (sh_rest, g_sh_rest)]
             wanted = [(t, g) for t, g in pairs if g is not None]
             if wanted and all(_fusable_grad(t, g.shape) for t, g in wanted) and (need[2] or g_sh is None):
-                accumulate = 1
+                accumulate = 1          # bit 0: the parameter gradients
                 g_means3D = ctx.inputs_ref[0].grad if g_means3D is not None else None
-                g_means2D = ctx.inputs_ref[1].grad if g_means2D is not None else None
                 g_sh = sh.grad if g_sh is not None else None
                 g_colors = colors_precomp.grad if g_colors is not None else None
                 g_opac = opacities.grad if g_opac is not None else None
@@ -292,6 +291,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                 g_cov = cov3Ds_precomp.grad if g_cov is not None else None
                 g_extra = extra.grad if g_extra is not None else None
                 g_sh_rest = sh_rest.grad if g_sh_rest is not None else None
+                # bit 1: means2D as well -- only when it is a shared leaf; render() feeds a fresh tensor per view,
+                # whose gradient (a per-view densification statistic) is then returned to autograd as usual
+                if g_means2D is not None and _fusable_grad(ctx.inputs_ref[1], g_means2D.shape):
+                    accumulate |= 2
+                    g_means2D = ctx.inputs_ref[1].grad
         scratch = torch.empty(L.ogs_raster_backward_scratch_floats(P, n_extra), dtype=torch.float32, device=dev)
 
         ri = _fill_inputs(rs, ctx.bg_full, means3D, opacities, sh, colors_precomp, scales, rotations,
@@ -304,8 +308,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         with torch.cuda.device(dev):
             rc = L.ogs_raster_backward(C.byref(ri), C.byref(ctx.state), C.byref(gi), C.byref(go), C.c_void_p(stream))
         _lib.check(rc, "ogs_raster_backward")
-        if accumulate:       # already added into the leaves' .grad
-            return (None,) * 13
+        if accumulate:       # already added into the leaves' .grad (means2D unless it was fused too)
+            return (None, None if (accumulate & 2) else g_means2D) + (None,) * 11
         if g_extra is not None and n_extra != ctx.n_extra_user:
             g_extra = g_extra[:, :ctx.n_extra_user].contiguous()
         if not need[2]:

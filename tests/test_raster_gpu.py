@@ -419,18 +419,25 @@ def test_fused_gradient_accumulation_equals_autograd():
     cams = synth.orbit_cameras(3, 3.5, 80, 64, 0.9, 0.8)
     c = _cuda(gs)
     res = {}
-    for fuse in (False, True):
-        leaves = [c[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")]
-        m2 = torch.zeros(800, 3, device="cuda", requires_grad=True)
+    for fresh_m2 in (False, True):      # True: a fresh non-leaf screen-space tensor per view, as render() makes it
+        for fuse in (False, True):
+            leaves = [c[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")]
+            m2 = torch.zeros(800, 3, device="cuda", requires_grad=True)
+            per_view = []
 
-        def view(cam):
-            rs = _settings(cam, np.zeros(3, np.float32))._replace(debug=False)
-            out = GaussianRasterizer(rs)(means3D=leaves[0], means2D=m2, opacities=leaves[1], shs=leaves[2],
-                                         scales=leaves[3], rotations=leaves[4])
-            return (out[0] * out[0]).sum() + out[2].sum() + out[3].sum()
+            def view(cam):
+                rs = _settings(cam, np.zeros(3, np.float32))._replace(debug=False)
+                sp = m2 + 0 if fresh_m2 else m2
+                if fresh_m2:
+                    sp.retain_grad()
+                    per_view.append(sp)
+                out = GaussianRasterizer(rs)(means3D=leaves[0], means2D=sp, opacities=leaves[1], shs=leaves[2],
+                                             scales=leaves[3], rotations=leaves[4])
+                return (out[0] * out[0]).sum() + out[2].sum() + out[3].sum()
 
-        ogdist.render_views_backward(view, cams, leaves + [m2], already_split=True, fuse_accumulate=fuse)
-        assert ogdist._coalesced_grads(leaves) is not None
-        res[fuse] = [t.grad.clone() for t in leaves + [m2]]
-    for a, b in zip(res[True], res[False]):
-        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-9
+            ogdist.render_views_backward(view, cams, leaves + [m2], already_split=True, fuse_accumulate=fuse)
+            assert ogdist._coalesced_grads(leaves) is not None
+            res[(fresh_m2, fuse)] = [t.grad.clone() for t in leaves + [m2]] + [sp.grad.clone() for sp in per_view]
+        assert len(res[(fresh_m2, True)]) == len(res[(fresh_m2, False)])
+        for a, b in zip(res[(fresh_m2, True)], res[(fresh_m2, False)]):
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-9
