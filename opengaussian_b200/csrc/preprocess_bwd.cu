@@ -21,7 +21,12 @@ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 
 // out = v, or out += v in accumulate mode (the caller hands the parameter's existing .grad: summing the
 // views of a step then costs one read of the old gradient here instead of a separate read-read-write pass)
-__device__ __forceinline__ void put(float* p, float v, bool accum) { *p = accum ? *p + v : v; }
+// In accumulate mode the add is a fire-and-forget red.global (every address has exactly ONE writer, so the result
+// is deterministic): no dependent load at the tail of the thread.
+__device__ __forceinline__ void put(float* p, float v, bool accum) {
+    if (accum) atomicAdd(p, v);
+    else *p = v;
+}
 
 // STAGE_SH: the block's SH slab (visible rows only) is loaded with coalesced 16-byte loads into a
 // padded shared-memory layout, each thread overwrites its row in place with dL/dsh, and the slab
@@ -84,14 +89,14 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
             for (int e = threadIdx.x; e < rows * 3; e += PB) {
                 const int gi = e / 3, k = e - gi * 3;
                 if (!ac) dst_dc[e] = s_sh[gi * (per + 1) + k];
-                else if (s_vis[gi]) dst_dc[e] += s_sh[gi * (per + 1) + k];
+                else if (s_vis[gi]) atomicAdd(dst_dc + e, s_sh[gi * (per + 1) + k]);
             }
             if (a.dL_dshs_rest) {
                 float* dst_r = a.dL_dshs_rest + (size_t)blockIdx.x * PB * pr;
                 for (int e = threadIdx.x; e < rows * pr; e += PB) {
                     const int gi = e / pr, k = e - gi * pr;
                     if (!ac) dst_r[e] = s_sh[gi * (per + 1) + 3 + k];
-                    else if (s_vis[gi]) dst_r[e] += s_sh[gi * (per + 1) + 3 + k];
+                    else if (s_vis[gi]) atomicAdd(dst_r + e, s_sh[gi * (per + 1) + 3 + k]);
                 }
             }
         } else {
@@ -102,10 +107,7 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
                 const int gi = f / per, k = f - gi * per;
                 const float* d = s_sh + gi * (per + 1) + k;
                 if (!ac) dst[e] = make_float4(d[0], d[1], d[2], d[3]);
-                else if (s_vis[gi]) {
-                    const float4 o = dst[e];
-                    dst[e] = make_float4(o.x + d[0], o.y + d[1], o.z + d[2], o.w + d[3]);
-                }
+                else if (s_vis[gi]) atomicAdd(dst + e, make_float4(d[0], d[1], d[2], d[3]));   // red.global.add.v4.f32
             }
         }
     }
