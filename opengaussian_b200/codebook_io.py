@@ -103,3 +103,24 @@ def load_code_book(base_path):
 def ids_bits(n_points: int) -> int:
     """Bits per id in kmeans_inds.bin: ceil(log2(#points)) -- the reference sizes them by the number of POINTS."""
     return int(math.ceil(math.log2(n_points)))
+
+
+CLUSTER_LANG_KEYS = ("leaf_feat", "leaf_score", "occu_count", "leaf_ind")
+
+
+def save_cluster_lang(model_path, per_leaf_feat, leaf_ave_score, leaf_occu_count, cluster_indices):
+    """`cluster_lang.npz` of Stage 3 (reference train.py:951-954): leaf_feat [k1*k2, 512], leaf_score [k1*k2],
+    occu_count [k1*k2], leaf_ind [num_pts]; uncompressed `np.savez`, dtypes kept as they are."""
+    arrays = [t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+              for t in (per_leaf_feat, leaf_ave_score, leaf_occu_count, cluster_indices)]
+    np.savez(os.path.join(model_path, "cluster_lang.npz"), **dict(zip(CLUSTER_LANG_KEYS, arrays)))
+
+
+def load_cluster_lang(model_path, device="cuda", min_occurrence=5):
+    """What render_lerf_by_text.py:56-62 / scripts/eval_scannet.py:135 read back: (leaf_feat, leaf_score,
+    occu_count, leaf_ind) on `device`; features of leaves seen fewer than `min_occurrence` times are zeroed (:62)."""
+    saved = np.load(os.path.join(model_path, "cluster_lang.npz"))
+    feat, score, occu, ind = (torch.from_numpy(saved[k + ".npy"]).to(device) for k in CLUSTER_LANG_KEYS)
+    if min_occurrence:
+        feat[occu < min_occurrence] *= 0.0
+    return feat, score, occu, ind

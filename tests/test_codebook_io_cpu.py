@@ -73,3 +73,21 @@ def test_two_parameters_share_one_bit_string():
         assert np.array_equal(raw, np.packbits(bits, bitorder="big"))
         _, first = cio.load_code_book(sub)
         assert np.array_equal(first, a.numpy())
+
+
+def test_cluster_lang_file(tmp_path):
+    import numpy as np
+    import torch
+    from opengaussian_b200 import codebook_io as cio
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(20, 512, generator=g)
+    score = torch.rand(20, generator=g)
+    occu = torch.randint(0, 12, (20,), generator=g).float()
+    ind = torch.randint(0, 20, (1000,), generator=g)
+    cio.save_cluster_lang(str(tmp_path), feat, score, occu, ind)
+    raw = np.load(str(tmp_path / "cluster_lang.npz"))            # the reference's readers use these member names
+    assert sorted(raw.files) == sorted(cio.CLUSTER_LANG_KEYS)
+    assert np.array_equal(raw["leaf_feat.npy"], feat.numpy()) and raw["leaf_ind"].dtype == np.int64
+    f2, s2, o2, i2 = cio.load_cluster_lang(str(tmp_path), device="cpu")
+    assert torch.equal(i2, ind) and torch.equal(s2, score) and torch.equal(o2, occu)
+    assert torch.equal(f2[occu >= 5], feat[occu >= 5]) and not f2[occu < 5].any()
