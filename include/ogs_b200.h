@@ -29,6 +29,9 @@
  *   ogs_kmeans_finalize          scene/kmeans_quantize.py:208-214 (centres = sums / counts, reset)
  *   ogs_kmeans_gather_st         scene/kmeans_quantize.py:273-275 (gather centres, straight-through)
  *   ogs_kmeans_count             scene/kmeans_quantize.py:89-144 (equalize_cluster_size member counts)
+ *   ogs_mask_pair_counts         utils/opengs_utlis.py:90-123 (calculate_iou)
+ *   ogs_adam_step                train.py:609 (gaussians.optimizer.step(), the torch.optim.Adam of
+ *                                scene/gaussian_model.py:215-230)
  *   ogs_mask_mean_forward/backward, ogs_mask_var_forward
  *                                utils/opengs_utlis.py:240-283 (mask_feature_mean incl. return_var) and
  *                                :184-201 (pair_mask_feature_mean)
@@ -139,9 +142,9 @@ const char* ogs_last_error(void);
 
 /* Optional device timing of the kernel families (CUDA events recorded on the launching stream).
  * Families: 0 preprocess_fwd, 1 depth_sort_scan, 2 emit, 3 tile_sort, 4 tile_ranges, 5 blend_fwd,
- * 6 blend_bwd, 7 preprocess_bwd, 8 kmeans_assign, 9 mask_stats.  ogs_profile_read synchronises the recorded
+ * 6 blend_bwd, 7 preprocess_bwd, 8 kmeans_assign, 9 mask_stats, 10 adam.  ogs_profile_read synchronises the recorded
  * events, writes the summed milliseconds and launch counts of the first n families and resets. */
-#define OGS_PROFILE_FAMILIES 10
+#define OGS_PROFILE_FAMILIES 11
 void ogs_profile_enable(int on);
 int ogs_profile_read(float* ms_out_host, int32_t* launches_out_host, int32_t n);
 
@@ -211,6 +214,38 @@ int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, co
 int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
                           const float* mean, const float* coef, float* dfeat, float* dmean,
                           void* stream);
+
+/* ---- pairwise mask intersections: utils/opengs_utlis.py::calculate_iou (:90-123) ----
+ * masks1 [n1,H*W], masks2 [n2,H*W] bytes (torch.bool storage, non-zero = inside), device pointers.
+ * Writes inter int32 [n2,n1] = |masks2[j] & masks1[i]| and counts int32 [n1+n2] = pixel count of every row
+ * (masks1 rows first); the union is counts[i] + counts[n1+j] - inter[j][i].  scratch: device buffer of
+ * ogs_mask_iou_scratch_bytes(n1, n2, H*W) bytes (the bit-packed rows).  Outputs are zeroed by the call. */
+int64_t ogs_mask_iou_scratch_bytes(int32_t n1, int32_t n2, int64_t HW);
+int ogs_mask_pair_counts(int32_t n1, int32_t n2, int64_t HW, const uint8_t* masks1, const uint8_t* masks2,
+                         void* scratch, int32_t* inter, int32_t* counts, void* stream);
+
+/* ---- optimiser step: gaussians.optimizer.step() (train.py:609) for torch.optim.Adam(l, lr=0.0, eps=1e-15)
+ * (scene/gaussian_model.py:215-230) -- all parameter tensors in one launch ----
+ * One entry per parameter tensor (float32, contiguous, device pointers).  step_size = lr / (1 - beta1^t) and
+ * bias_correction2_sqrt = sqrt(1 - beta2^t) for the tensor's step count t AFTER the increment, as
+ * torch/optim/adam.py::_single_tensor_adam computes them; no weight decay, no amsgrad.  `tensors` is a HOST
+ * array; grad_scale multiplies every gradient on load (1 for the reference's semantics). */
+typedef struct ogs_adam_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n;
+    float step_size;
+    float bias_correction2_sqrt;
+    float beta1;
+    float beta2;
+    float one_minus_beta1;           /* computed in double on the host, like torch's Python scalars */
+    float one_minus_beta2;
+    float eps;
+    float reserved_;
+} ogs_adam_tensor;
+int ogs_adam_step(int32_t n_tensors, const ogs_adam_tensor* tensors, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

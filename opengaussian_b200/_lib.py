@@ -48,6 +48,13 @@ class RasterGradsOut(C.Structure):
                 ("accumulate", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", _fp), ("grad", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("n", C.c_int64),
+                ("step_size", C.c_float), ("bias_correction2_sqrt", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float), ("eps", C.c_float),
+                ("reserved_", C.c_float)]
+
+
 EXPORTS = {
     "ogs_abi_version": (C.c_int, []),
     "ogs_last_error": (C.c_char_p, []),
@@ -70,6 +77,9 @@ EXPORTS = {
     "ogs_mask_var_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "ogs_cohesion_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "ogs_cohesion_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_adam_step": (C.c_int, [C.c_int32, C.c_void_p, C.c_float, C.c_void_p]),
+    "ogs_mask_iou_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int64]),
+    "ogs_mask_pair_counts": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
 }
 
 _LIB = None
@@ -106,7 +116,7 @@ def check(rc: int, what: str):
 
 
 PROFILE_FAMILIES = ("preprocess_fwd", "depth_sort_scan", "emit", "tile_sort", "tile_ranges", "blend_fwd",
-                    "blend_bwd", "preprocess_bwd", "kmeans_assign", "mask_stats")
+                    "blend_bwd", "preprocess_bwd", "kmeans_assign", "mask_stats", "adam")
 
 
 def profile_enable(on: bool):

@@ -26,6 +26,8 @@ UNITS = {
     "preprocess_bwd.cu": [],
     "kmeans.cu": [],
     "mask_stats.cu": [],
+    "mask_iou.cu": [],
+    "adam.cu": [],
     "capi.cu": [],
 }
 

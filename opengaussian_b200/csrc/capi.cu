@@ -518,4 +518,35 @@ int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, c
     return 0;
 }
 
+int64_t ogs_mask_iou_scratch_bytes(int32_t n1, int32_t n2, int64_t HW) {
+    if (n1 < 0 || n2 < 0 || HW < 0) return -1;
+    return mask_iou_scratch_bytes(n1, n2, HW);
+}
+
+int ogs_mask_pair_counts(int32_t n1, int32_t n2, int64_t HW, const uint8_t* masks1, const uint8_t* masks2,
+                         void* scratch, int32_t* inter, int32_t* counts, void* stream_) {
+    if (n1 < 0 || n2 < 0 || HW < 0 || (HW > 0 && ((n1 > 0 && !masks1) || (n2 > 0 && !masks2))) ||
+        (n1 + n2 > 0 && !counts) || (n1 > 0 && n2 > 0 && !inter) || (n1 + n2 > 0 && HW > 0 && !scratch)) {
+        set_error("mask_pair_counts: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_mask_pair_counts(n1, n2, HW, masks1, masks2, (uint32_t*)scratch, inter, counts, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("mask_pair_counts", 0, s);
+    return 0;
+}
+
+int ogs_adam_step(int32_t n_tensors, const ogs_adam_tensor* tensors, float grad_scale, void* stream_) {
+    if (n_tensors < 0 || (n_tensors > 0 && !tensors)) { set_error("adam_step: bad arguments"); return -1; }
+    if (n_tensors == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_ADAM, s);
+    int rc = launch_adam_step(n_tensors, tensors, grad_scale, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("adam_step", 0, s);
+    return 0;
+}
+
 }  // extern "C"

@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns (int)e
 
 // ---- optional per-family device timing (CUDA events on the launching stream) ----
 enum ProfFamily { PF_PREPROCESS_FWD = 0, PF_DEPTH_SORT_SCAN, PF_EMIT, PF_TILE_SORT, PF_RANGES, PF_BLEND_FWD,
-                  PF_BLEND_BWD, PF_PREPROCESS_BWD, PF_KMEANS_ASSIGN, PF_MASK_STATS, PF_COUNT };
+                  PF_BLEND_BWD, PF_PREPROCESS_BWD, PF_KMEANS_ASSIGN, PF_MASK_STATS, PF_ADAM, PF_COUNT };
 void prof_begin(int family, cudaStream_t s);
 void prof_end(int family, cudaStream_t s);
 struct ProfScope {
@@ -268,5 +268,15 @@ int launch_cohesion_forward(int M, int C, int64_t HW, const float* feat, const u
                             float* npix, cudaStream_t s);
 int launch_cohesion_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* mean, const float* coef,
                              float* dfeat, float* dmean, cudaStream_t s);
+
+
+// pairwise mask intersections (mask_iou.cu)
+int64_t mask_iou_scratch_bytes(int n1, int n2, int64_t HW);
+int launch_mask_pair_counts(int n1, int n2, int64_t HW, const uint8_t* masks1, const uint8_t* masks2, uint32_t* scratch,
+                            int32_t* inter, int32_t* counts, cudaStream_t s);
+
+
+// optimiser step (adam.cu)
+int launch_adam_step(int n_tensors, const ogs_adam_tensor* tensors, float grad_scale, cudaStream_t s);
 
 }  // namespace ogs

@@ -3,7 +3,10 @@ streaming kernels of csrc/mask_stats.cu -- drop-ins for
 
 * ``utils/opengs_utlis.py::mask_feature_mean`` (:240-283)  -- same signature and return values,
 * ``train.py::cohesion_loss`` (:102-121) and ``train.py::separation_loss`` (:123-147),
-* ``utils/opengs_utlis.py::pair_mask_feature_mean`` (:184-201).
+* ``utils/opengs_utlis.py::pair_mask_feature_mean`` (:184-201),
+* ``utils/opengs_utlis.py::calculate_iou`` (:90-123) and the small distance helpers
+  ``calculate_pairwise_distances`` (:8-34) / ``calculate_distances`` (:36-58) used beside it by the
+  Stage-3 association (train.py:870-882).
 
 The reference expands ``feat_map [C,H,W]`` and ``gt_masks [M,H,W]`` to ``[M,C,H,W]`` float tensors
 (processed in 5x5 Python chunks to dodge OOM); here every pass streams the M*H*W mask bytes once.
@@ -155,3 +158,64 @@ def pair_mask_feature_mean(feat_map, masks):
                                                    _lib.ptr(counts), _stream(feat.device)), "ogs_mask_mean_forward")
         outs.append(sums[0] / (counts[0] + 1e-6))
     return torch.stack(outs) if outs else feat_map.new_zeros(0, feat_map.shape[1])
+
+
+def _as_mask_bytes(masks):
+    if not masks.is_cuda:
+        raise _lib.OgsError("calculate_iou needs CUDA tensors (no CPU path)")
+    m = masks.detach()
+    if m.dtype != torch.bool:
+        m = m != 0
+    return m.contiguous().view(torch.uint8)
+
+
+def mask_pair_counts(masks1, masks2):
+    """Integer statistics behind calculate_iou: (inter int32 [m,n], count1 int32 [n], count2 int32 [m])
+    for masks1 [n,H,W] and masks2 [m,H,W]."""
+    assert masks1.shape[1:] == masks2.shape[1:], "both mask sets must share H, W"
+    a, b = _as_mask_bytes(masks1), _as_mask_bytes(masks2)
+    n, m = a.shape[0], b.shape[0]
+    HW = int(a.shape[1] * a.shape[2])
+    dev = a.device
+    inter = torch.empty(m, n, dtype=torch.int32, device=dev)
+    counts = torch.empty(n + m, dtype=torch.int32, device=dev)
+    if n + m > 0:
+        nbytes = int(_lib.lib().ogs_mask_iou_scratch_bytes(n, m, HW))
+        scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().ogs_mask_pair_counts(n, m, HW, _lib.ptr(a), _lib.ptr(b), _lib.ptr(scratch), _lib.ptr(inter),
+                                                  _lib.ptr(counts), _stream(dev)), "ogs_mask_pair_counts")
+    return inter, counts[:n], counts[n:]
+
+
+def calculate_iou(masks1, masks2, base=None):
+    """IoU matrix [m, n] between masks1 [n,H,W] and masks2 [m,H,W] (reference :90-123; ``base="former"`` divides
+    by |masks1[i]|, ``"later"`` by |masks2[j]|, otherwise by the union).  Values equal the reference's float32
+    sums exactly: all counts are integers below 2^24."""
+    inter, c1, c2 = mask_pair_counts(masks1, masks2)
+    intersection = inter.float()
+    if base == "former":
+        union = c1.float()[None, :] + 1e-6
+    elif base == "later":
+        union = c2.float()[:, None] + 1e-6
+    else:
+        union = (c1[None, :] + c2[:, None] - inter).float() + 1e-6
+    return intersection / union
+
+
+def calculate_pairwise_distances(tensor1, tensor2, metric=None):
+    """L1 / L2 distances between every pair of rows of [m,D] and [n,D] (reference :8-34).  O(m n D): plain torch."""
+    t1, t2 = tensor1.unsqueeze(1), tensor2.unsqueeze(0)
+    if metric == "l1":
+        return torch.abs(t1 - t2).sum(dim=2), None
+    if metric == "l2":
+        return None, torch.sqrt((t1 - t2).pow(2).sum(dim=2))
+    return torch.abs(t1 - t2).sum(dim=2), torch.sqrt((t1 - t2).pow(2).sum(dim=2))
+
+
+def calculate_distances(tensor1, tensor2, metric=None):
+    """Row-wise L1 / L2 distances of two [N,D] tensors (reference :36-58)."""
+    if metric == "l1":
+        return torch.abs(tensor1 - tensor2).sum(dim=1)
+    if metric == "l2":
+        return torch.sqrt((tensor1 - tensor2).pow(2).sum(dim=1))
+    return torch.abs(tensor1 - tensor2).sum(dim=1), torch.sqrt((tensor1 - tensor2).pow(2).sum(dim=1))

@@ -2,7 +2,8 @@
 Stage-1 losses -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 Follows utils/opengs_utlis.py::mask_feature_mean (:240-283) and train.py::cohesion_loss (:102-121) /
-separation_loss (:123-155) without their [M,C,H,W] expansion.  Pinned against the reference functions
+separation_loss (:123-155) without their [M,C,H,W] expansion, and utils/opengs_utlis.py::calculate_iou
+(:90-123) as integer pixel counts.  Pinned against the reference functions
 themselves: tests/golden/make_mask_golden.py runs them (torch CPU) and commits outputs and autograd
 gradients; tests/test_oracle_cpu.py checks this restatement against those fixtures.
 """
@@ -52,3 +53,19 @@ def separation_loss(feat_mean_stack, iteration):
     if iteration > 35_000:
         loss_weight[loss_weight < 0.9] = 0.1
     return (inverse_distance * loss_weight).sum() / (N * (N - 1))
+
+
+def calculate_iou(masks1, masks2, base=None):
+    """Reference utils/opengs_utlis.py:90-123: masks1 [n,H,W], masks2 [m,H,W] -> IoU [m,n].  Pixel counts are
+    integers (exact in the reference's float32 sums below 2^24), the division is done in float32 like :120."""
+    a = (masks1 != 0).reshape(masks1.shape[0], -1).to(torch.int64)          # [n, HW]
+    b = (masks2 != 0).reshape(masks2.shape[0], -1).to(torch.int64)          # [m, HW]
+    inter = b @ a.t()                                                       # :110
+    ca, cb = a.sum(1), b.sum(1)
+    if base == "former":
+        union = ca[None, :].float() + 1e-6                                  # :114
+    elif base == "later":
+        union = cb[:, None].float() + 1e-6                                  # :116
+    else:
+        union = (ca[None, :] + cb[:, None] - inter).float() + 1e-6          # :118  |a or b| = |a| + |b| - |a and b|
+    return inter.float() / union

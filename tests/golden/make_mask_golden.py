@@ -2,6 +2,8 @@
 
 * utils/opengs_utlis.py::mask_feature_mean (:240-283), pair_mask_feature_mean (:184-201) -- the
   module is loaded by path with a stub for the missing `bitarray` package;
+* utils/opengs_utlis.py::calculate_iou (:90-123) on the masks of one case against a second, shifted set, for
+  base = None / "former" / "later" (`iou_inputs`);
 * train.py::cohesion_loss (:102-121) and separation_loss (:123-155) -- train.py itself cannot be
   imported here (pytorch3d, plyfile, a CUDA device ...), so the two function definitions are taken
   from its source with `ast` and executed unchanged.
@@ -44,6 +46,16 @@ def inputs(name):
     return feat, masks, img
 
 
+def iou_inputs(name):
+    """Second mask set for calculate_iou: the case's masks rolled by a few pixels, two of them merged, plus an
+    empty one and a full one; returned as (masks1 [n,H,W], masks2 [m,H,W])."""
+    _, masks, _ = inputs(name)
+    other = np.roll(masks[: max(2, masks.shape[0] // 2)], (2, -3), axis=(1, 2)).copy()
+    other[0] |= other[1]
+    other = np.concatenate([other, np.zeros_like(masks[:1]), np.ones_like(masks[:1])])
+    return masks, other
+
+
 def load_reference():
     sys.modules.setdefault("bitarray", types.SimpleNamespace(bitarray=object))
     spec = importlib.util.spec_from_file_location("ref_opengs_utlis", os.path.join(REF, "utils/opengs_utlis.py"))
@@ -84,6 +96,11 @@ def main():
             out[f"{name}/cnt"] = cnt.numpy()
             pm = ref.pair_mask_feature_mean(feat.detach().unsqueeze(0).repeat(3, 1, 1, 1), masks[:3])
             out[f"{name}/pair_mean"] = pm.numpy()
+            m1, m2 = iou_inputs(name)
+            for base in (None, "former", "later"):
+                # int32 inputs exercise the reference's .to(torch.bool) branch (:100-103)
+                iou = ref.calculate_iou(torch.from_numpy(m1), torch.from_numpy(m2.astype(np.int32)), base=base)
+                out[f"{name}/iou_{base}"] = iou.numpy()
     path = os.path.join(HERE, "mask_stats_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, sorted(out)[:8])

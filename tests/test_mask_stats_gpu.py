@@ -100,3 +100,52 @@ def test_empty_and_errors():
         mask_feature_mean(torch.rand(5, 16, 20, device="cuda"), empty)      # unsupported channel count
     with pytest.raises(_lib.OgsError):
         mask_feature_mean(torch.rand(6, 16, 20), empty.cpu())                # no CPU path
+
+
+@pytest.mark.parametrize("name", ["stage1_6ch", "no_image_mask", "rgb_3ch"])
+def test_calculate_iou_vs_reference_golden(name):
+    """csrc/mask_iou.cu through the C ABI == utils/opengs_utlis.py::calculate_iou, bit for bit (integer counts).
+    stage1_6ch has H*W % 16 != 0 (byte path), the other two take the 16-byte path."""
+    from opengaussian_b200.mask_stats import calculate_iou
+    m, gold = _gm(), np.load(GOLD)
+    m1, m2 = m.iou_inputs(name)
+    a = torch.from_numpy(m1).cuda()
+    b = torch.from_numpy(m2.astype(np.int32)).cuda()
+    for base in (None, "former", "later"):
+        iou = calculate_iou(a, b, base=base)
+        assert tuple(iou.shape) == (m2.shape[0], m1.shape[0]) and iou.dtype == torch.float32
+        assert np.array_equal(iou.cpu().numpy(), gold[f"{name}/iou_{base}"]), base
+
+
+@pytest.mark.parametrize("H,W,n,m", [(968, 1296, 120, 10), (1080, 1920, 37, 19), (61, 67, 3, 1)])
+def test_calculate_iou_vs_oracle_full_size(H, W, n, m):
+    """Stage-3 association sizes (train.py:870): SAM-like masks against leaf silhouettes; exact counts."""
+    from opengaussian_b200.mask_stats import calculate_iou, mask_pair_counts
+    from oracle import mask_stats as oms
+    m1 = _sam_like_masks(n, H, W, 5).cuda()
+    m2 = torch.roll(_sam_like_masks(m, H, W, 6).cuda(), (7, -11), dims=(1, 2))
+    inter, c1, c2 = mask_pair_counts(m1, m2)
+    a = m1.view(n, -1).float()
+    b = m2.view(m, -1).float()
+    assert torch.equal(inter, (b @ a.t()).round().to(torch.int32))       # fp32 GEMM of 0/1: exact below 2^24
+    assert torch.equal(c1, m1.view(n, -1).sum(1).to(torch.int32)) and torch.equal(c2, m2.view(m, -1).sum(1).to(torch.int32))
+    for base in (None, "former", "later"):
+        ref = oms.calculate_iou(m1.cpu(), m2.cpu(), base=base)
+        assert torch.equal(calculate_iou(m1, m2, base=base).cpu(), ref), base
+    # symmetry: IoU(a, b) == IoU(b, a)^T, and a set against itself has a unit diagonal (where non-empty)
+    assert torch.equal(calculate_iou(m1, m2), calculate_iou(m2, m1).t())
+    self_iou = calculate_iou(m1, m1).diagonal()
+    assert torch.all((self_iou == 0) | ((self_iou - 1).abs() < 1e-6))
+
+
+def test_calculate_iou_edge_cases():
+    from opengaussian_b200 import _lib
+    from opengaussian_b200.mask_stats import calculate_iou
+    z = torch.zeros(0, 8, 8, dtype=torch.bool, device="cuda")
+    o = torch.ones(2, 8, 8, dtype=torch.bool, device="cuda")
+    assert tuple(calculate_iou(z, o).shape) == (2, 0) and tuple(calculate_iou(o, z).shape) == (0, 2)
+    assert torch.equal(calculate_iou(o, torch.zeros_like(o)), torch.zeros(2, 2, device="cuda"))   # 0 / 1e-6
+    v = o[:, ::2]                                                  # non-contiguous view
+    assert torch.allclose(calculate_iou(v, v), torch.ones(2, 2, device="cuda"))
+    with pytest.raises(_lib.OgsError):
+        calculate_iou(o.cpu(), o.cpu())

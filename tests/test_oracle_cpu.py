@@ -243,3 +243,16 @@ def test_mask_stats_oracle_vs_reference_golden(name):
     assert np.abs(m2.numpy() - gold[f"{name}/mean_noimg"]).max() <= 2e-6
     assert np.abs(var.numpy() - gold[f"{name}/var"]).max() <= 2e-6
     assert np.array_equal(cnt.numpy(), gold[f"{name}/cnt"])
+
+
+@pytest.mark.parametrize("name", ["stage1_6ch", "no_image_mask", "rgb_3ch"])
+def test_iou_oracle_vs_reference_golden(name):
+    """oracle calculate_iou == utils/opengs_utlis.py::calculate_iou (:90-123), bit for bit."""
+    from oracle import mask_stats as oms
+    m, gold = _mask_golden_module(), np.load(MGOLD)
+    m1, m2 = m.iou_inputs(name)
+    for base in (None, "former", "later"):
+        iou = oms.calculate_iou(torch.from_numpy(m1), torch.from_numpy(m2.astype(np.int32)), base=base)
+        ref = gold[f"{name}/iou_{base}"]
+        assert iou.shape == ref.shape == (m2.shape[0], m1.shape[0])
+        assert np.array_equal(iou.numpy(), ref), base
