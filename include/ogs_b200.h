@@ -30,6 +30,7 @@
  *   ogs_kmeans_gather_st         scene/kmeans_quantize.py:273-275 (gather centres, straight-through)
  *   ogs_kmeans_count             scene/kmeans_quantize.py:89-144 (equalize_cluster_size member counts)
  *   ogs_mask_pair_counts         utils/opengs_utlis.py:90-123 (calculate_iou)
+ *   ogs_splat_footprint_votes    utils/sam_refinement_utils.py:902-913 (get_splat_id_and_weights, batched)
  *   ogs_adam_step                train.py:609 (gaussians.optimizer.step(), the torch.optim.Adam of
  *                                scene/gaussian_model.py:215-230)
  *   ogs_mask_mean_forward/backward, ogs_mask_var_forward
@@ -142,9 +143,9 @@ const char* ogs_last_error(void);
 
 /* Optional device timing of the kernel families (CUDA events recorded on the launching stream).
  * Families: 0 preprocess_fwd, 1 depth_sort_scan, 2 emit, 3 tile_sort, 4 tile_ranges, 5 blend_fwd,
- * 6 blend_bwd, 7 preprocess_bwd, 8 kmeans_assign, 9 mask_stats, 10 adam.  ogs_profile_read synchronises the recorded
+ * 6 blend_bwd, 7 preprocess_bwd, 8 kmeans_assign, 9 mask_stats, 10 adam, 11 footprint.  ogs_profile_read synchronises the recorded
  * events, writes the summed milliseconds and launch counts of the first n families and resets. */
-#define OGS_PROFILE_FAMILIES 11
+#define OGS_PROFILE_FAMILIES 12
 void ogs_profile_enable(int on);
 int ogs_profile_read(float* ms_out_host, int32_t* launches_out_host, int32_t n);
 
@@ -223,6 +224,36 @@ int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, c
 int64_t ogs_mask_iou_scratch_bytes(int32_t n1, int32_t n2, int64_t HW);
 int ogs_mask_pair_counts(int32_t n1, int32_t n2, int64_t HW, const uint8_t* masks1, const uint8_t* masks2,
                          void* scratch, int32_t* inter, int32_t* counts, void* stream);
+
+/* ---- batched single-splat footprints and their SAM-id votes: utils/sam_refinement_utils.py::
+ * MultiViewSAMMaskRefiner.get_splat_id_and_weights (:902-913) = render_single_gaussian (:330-403, white
+ * view-independent SH, black background) + fix_image (:143-176) + rgb_to_weight_map (:103-141) +
+ * get_most_common_id_in_mask_weighted (:645-702), for P selected Gaussians in ONE camera ----
+ * means3D [P,3], opacities [P], scales [P,3], rotations [P,4]: the (gathered) rows of the selected Gaussians,
+ * activated unless act_flags says otherwise; camera as in ogs_raster_inputs; sam_ids int32 [H*W]; empty_id = the id
+ * reported for an empty footprint (the reference's argmax over all-zero counts: the smallest id if that is
+ * negative or the only one, else 0); color = the
+ * splat's constant colour (0.28209479177387814f + 0.5f for the white SH).  Per splat i:
+ *   dominant_id[i]      id with the largest sum of q = uint8(color * alpha * 255) under the footprint (ties: lowest)
+ *   dominant_weight[i]  that sum (-1: see overflow);   footprint_pixels[i]  pixels with q > 0;   q_max[i]  largest q (the normaliser
+ *   of rgb_to_weight_map);   radii[i]  as the rasterizer reports it (0 = culled).
+ * *overflow_host receives the number of splats whose footprint touched more than 128 distinct ids (their
+ * dominant id is then unreliable; the caller falls back for those).  Synchronises the stream. */
+typedef struct ogs_footprint_inputs {
+    int32_t P, W, H, act_flags;
+    const float* means3D;
+    const float* opacities;
+    const float* scales;
+    const float* rotations;
+    float scale_modifier, tanfovx, tanfovy, color;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const int32_t* sam_ids;
+    int32_t empty_id, reserved_;
+} ogs_footprint_inputs;
+int ogs_splat_footprint_votes(const ogs_footprint_inputs* in, int32_t* dominant_id, int32_t* dominant_weight,
+                              int32_t* footprint_pixels, int32_t* q_max, int32_t* radii,
+                              int32_t* overflow_host, void* stream);
 
 /* ---- optimiser step: gaussians.optimizer.step() (train.py:609) for torch.optim.Adam(l, lr=0.0, eps=1e-15)
  * (scene/gaussian_model.py:215-230) -- all parameter tensors in one launch ----

@@ -48,6 +48,13 @@ class RasterGradsOut(C.Structure):
                 ("accumulate", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class FootprintInputs(C.Structure):
+    _fields_ = [("P", C.c_int32), ("W", C.c_int32), ("H", C.c_int32), ("act_flags", C.c_int32),
+                ("means3D", _fp), ("opacities", _fp), ("scales", _fp), ("rotations", _fp),
+                ("scale_modifier", C.c_float), ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("color", C.c_float),
+                ("viewmatrix", _fp), ("projmatrix", _fp), ("sam_ids", _fp), ("empty_id", C.c_int32), ("reserved_", C.c_int32)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", _fp), ("grad", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("n", C.c_int64),
                 ("step_size", C.c_float), ("bias_correction2_sqrt", C.c_float), ("beta1", C.c_float),
@@ -77,6 +84,8 @@ EXPORTS = {
     "ogs_mask_var_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "ogs_cohesion_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "ogs_cohesion_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_splat_footprint_votes": (C.c_int, [C.POINTER(FootprintInputs), _fp, _fp, _fp, _fp, _fp, C.POINTER(C.c_int32),
+                                            C.c_void_p]),
     "ogs_adam_step": (C.c_int, [C.c_int32, C.c_void_p, C.c_float, C.c_void_p]),
     "ogs_mask_iou_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int64]),
     "ogs_mask_pair_counts": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
@@ -116,7 +125,7 @@ def check(rc: int, what: str):
 
 
 PROFILE_FAMILIES = ("preprocess_fwd", "depth_sort_scan", "emit", "tile_sort", "tile_ranges", "blend_fwd",
-                    "blend_bwd", "preprocess_bwd", "kmeans_assign", "mask_stats", "adam")
+                    "blend_bwd", "preprocess_bwd", "kmeans_assign", "mask_stats", "adam", "footprint")
 
 
 def profile_enable(on: bool):

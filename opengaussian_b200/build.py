@@ -28,6 +28,7 @@ UNITS = {
     "mask_stats.cu": [],
     "mask_iou.cu": [],
     "adam.cu": [],
+    "footprint.cu": [],
     "capi.cu": [],
 }
 

@@ -538,6 +538,63 @@ int ogs_mask_pair_counts(int32_t n1, int32_t n2, int64_t HW, const uint8_t* mask
     return 0;
 }
 
+int ogs_splat_footprint_votes(const ogs_footprint_inputs* in, int32_t* dominant_id, int32_t* dominant_weight,
+                              int32_t* footprint_pixels, int32_t* q_max, int32_t* radii, int32_t* overflow_host,
+                              void* stream_) {
+    if (!in) { set_error("footprint_votes: inputs is NULL"); return -1; }
+    if (in->P < 0 || in->W <= 0 || in->H <= 0) { set_error("footprint_votes: bad sizes P=%d W=%d H=%d", in->P, in->W, in->H); return -1; }
+    if (overflow_host) *overflow_host = 0;
+    const int P = in->P;
+    if (P == 0) return 0;
+    if (!in->means3D || !in->opacities || !in->scales || !in->rotations || !in->viewmatrix || !in->projmatrix || !in->sam_ids ||
+        !dominant_id || !dominant_weight || !footprint_pixels || !q_max || !radii) {
+        set_error("footprint_votes: all inputs and outputs must be set");
+        return -1;
+    }
+    if (in->act_flags & ~(OGS_ACT_SCALE_EXP | OGS_ACT_ROT_NORMALIZE | OGS_ACT_OPACITY_SIGMOID)) {
+        set_error("footprint_votes: only the scale / rotation / opacity activations apply");
+        return -1;
+    }
+    const int gx = (in->W + 15) / 16, gy = (in->H + 15) / 16;
+    if ((int64_t)gx * gy > 65535) { set_error("image too large: %d tiles (max 65535)", gx * gy); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = ensure_pool();
+    if (rc) return rc;
+    ProfScope ps(PF_FOOTPRINT, s);
+    const GeomLayout gl = GeomLayout::make(P, false, 0);
+    const size_t pw = align_up((size_t)P * 4, 256);
+    char* scratch = nullptr;
+    OGS_CUDA(cudaMallocAsync((void**)&scratch, gl.total + 2 * pw + 256, s));
+    const GeomPtrs g = GeomPtrs::from(scratch, gl);
+    int32_t* d_over = (int32_t*)(scratch + gl.total + 2 * pw);
+    cudaError_t e = cudaMemsetAsync(d_over, 0, 4, s);
+    if (e != cudaSuccess) { cudaFreeAsync(scratch, s); return cuda_fail(e, "footprint_votes memset"); }
+    PreprocessArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.P = P; pa.D = 0; pa.M = 0; pa.W = in->W; pa.H = in->H;
+    pa.act_flags = in->act_flags;
+    pa.means3D = in->means3D; pa.scales = in->scales; pa.rotations = in->rotations; pa.opacities = in->opacities;
+    pa.scale_modifier = in->scale_modifier; pa.tanfovx = in->tanfovx; pa.tanfovy = in->tanfovy;
+    pa.view = in->viewmatrix; pa.proj = in->projmatrix;
+    pa.radii = radii; pa.g = g;
+    pa.depth_keys = (uint32_t*)(scratch + gl.total);
+    pa.depth_vals = (uint32_t*)(scratch + gl.total + pw);
+    rc = launch_preprocess_forward(pa, s);
+    if (!rc) rc = launch_footprint_votes(P, in->W, in->H, g, in->sam_ids, in->empty_id, in->color, dominant_id, dominant_weight,
+                                         footprint_pixels, q_max, d_over, s);
+    int32_t over = 0;
+    if (!rc) {
+        e = cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "footprint_votes");
+    }
+    cudaFreeAsync(scratch, s);
+    if (rc) return rc;
+    if (overflow_host) *overflow_host = over;
+    return 0;
+}
+
 int ogs_adam_step(int32_t n_tensors, const ogs_adam_tensor* tensors, float grad_scale, void* stream_) {
     if (n_tensors < 0 || (n_tensors > 0 && !tensors)) { set_error("adam_step: bad arguments"); return -1; }
     if (n_tensors == 0) return 0;

@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns (int)e
 
 // ---- optional per-family device timing (CUDA events on the launching stream) ----
 enum ProfFamily { PF_PREPROCESS_FWD = 0, PF_DEPTH_SORT_SCAN, PF_EMIT, PF_TILE_SORT, PF_RANGES, PF_BLEND_FWD,
-                  PF_BLEND_BWD, PF_PREPROCESS_BWD, PF_KMEANS_ASSIGN, PF_MASK_STATS, PF_ADAM, PF_COUNT };
+                  PF_BLEND_BWD, PF_PREPROCESS_BWD, PF_KMEANS_ASSIGN, PF_MASK_STATS, PF_ADAM, PF_FOOTPRINT, PF_COUNT };
 void prof_begin(int family, cudaStream_t s);
 void prof_end(int family, cudaStream_t s);
 struct ProfScope {
@@ -275,6 +275,11 @@ int64_t mask_iou_scratch_bytes(int n1, int n2, int64_t HW);
 int launch_mask_pair_counts(int n1, int n2, int64_t HW, const uint8_t* masks1, const uint8_t* masks2, uint32_t* scratch,
                             int32_t* inter, int32_t* counts, cudaStream_t s);
 
+
+// single-splat footprint votes (footprint.cu)
+int launch_footprint_votes(int P, int W, int H, const GeomPtrs& g, const int32_t* sam_ids, int empty_id, float color,
+                           int32_t* dominant_id, int32_t* dominant_weight, int32_t* footprint_pixels, int32_t* q_max,
+                           int32_t* overflow, cudaStream_t s);
 
 // optimiser step (adam.cu)
 int launch_adam_step(int n_tensors, const ogs_adam_tensor* tensors, float grad_scale, cudaStream_t s);

@@ -256,3 +256,31 @@ def test_iou_oracle_vs_reference_golden(name):
         ref = gold[f"{name}/iou_{base}"]
         assert iou.shape == ref.shape == (m2.shape[0], m1.shape[0])
         assert np.array_equal(iou.numpy(), ref), base
+
+
+# ---- single-splat footprint votes: oracle vs the reference's own post-processing (golden) ----
+FGOLD = os.path.join(os.path.dirname(__file__), "golden", "footprint_golden.npz")
+
+
+def _footprint_golden_module():
+    spec = importlib.util.spec_from_file_location("mfg", os.path.join(os.path.dirname(FGOLD), "make_footprint_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("name", ["ids_from_minus1", "ids_from_3"])
+def test_footprint_oracle_vs_reference_golden(name):
+    """oracle/footprint.py (rect-restricted single-splat image + integer vote) == the C oracle's full P = 1 render
+    pushed through the reference's fix_image / rgb_to_weight_map / get_most_common_id_in_mask_weighted."""
+    import helpers
+    from oracle import footprint as ofp
+    m, gold = _footprint_golden_module(), np.load(FGOLD)
+    gs, cam, sam = m.inputs(name)
+    g = helpers.np_inputs(gs)
+    out = ofp.splat_votes(helpers.to_oracle_cam(cam), g["means3D"], g["opacities"], g["scales"], g["rotations"], sam)
+    assert np.array_equal(out["visible"], gold[f"{name}/visible"])
+    assert np.array_equal(out["footprint_pixels"], gold[f"{name}/footprint_pixels"])
+    assert np.array_equal(out["q_max"], gold[f"{name}/q_max"])
+    assert np.array_equal(out["dominant_id"], gold[f"{name}/dominant_id"])
+    assert (out["footprint_pixels"] > 0).sum() >= 40 and len(set(out["dominant_id"].tolist())) >= 10
