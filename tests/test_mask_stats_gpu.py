@@ -92,7 +92,7 @@ def test_empty_and_errors():
     assert mask_feature_mean(feat, none).shape == (0, 6)
     empty = torch.zeros(2, 16, 20, dtype=torch.bool, device="cuda")
     mean = mask_feature_mean(feat, empty)
-    assert float(mean.abs().max()) == 0.0                       # 0 / clamp(0, min=1)
+    assert float(mean.detach().abs().max()) == 0.0                       # 0 / clamp(0, min=1)
     lc = cohesion_loss(feat, empty, mean)
     lc.backward()
     assert float(lc) == 0.0 and float(feat.grad.abs().max()) == 0.0

@@ -284,3 +284,36 @@ def test_footprint_oracle_vs_reference_golden(name):
     assert np.array_equal(out["q_max"], gold[f"{name}/q_max"])
     assert np.array_equal(out["dominant_id"], gold[f"{name}/dominant_id"])
     assert (out["footprint_pixels"] > 0).sum() >= 40 and len(set(out["dominant_id"].tolist())) >= 10
+
+
+@pytest.mark.parametrize("name", ["ids_from_minus1", "ids_from_3"])
+def test_sam_footprint_host_functions_vs_reference_golden(name):
+    """opengaussian_b200.sam_footprints.fix_image / rgb_to_weight_map / most_common_id_weighted (the torch side of
+    get_splat_id_and_weights) == the reference's own functions, on one-splat renders of the C oracle."""
+    import helpers
+    from opengaussian_b200 import sam_footprints as sf
+    from oracle import raster as orc
+    m, gold = _footprint_golden_module(), np.load(FGOLD)
+    gs, cam, sam = m.inputs(name)
+    g = helpers.np_inputs(gs)
+    ocam = helpers.to_oracle_cam(cam)
+    white = np.zeros((1, 16, 3), np.float32)
+    white[:, 0, :] = 1.0
+    assert abs(sf.WHITE_SH_COLOR - 0.7820948) < 1e-6
+    for i in range(0, g["means3D"].shape[0], 3):
+        sl = slice(i, i + 1)
+        st = orc.forward(ocam, g["means3D"][sl], g["opacities"][sl], g["scales"][sl], g["rotations"][sl], shs=white,
+                         bg=np.zeros(3, np.float32))
+        img = sf.fix_image(torch.from_numpy(st.color[:3].copy()))
+        assert img.dtype == torch.uint8 and tuple(img.shape) == (cam.image_height, cam.image_width, 3)
+        w = sf.rgb_to_weight_map(img)
+        assert tuple(w.shape) == (cam.image_height, cam.image_width, 1)
+        assert int(img.max()) == gold[f"{name}/q_max"][i] and int((img != 0).any(2).sum()) == gold[f"{name}/footprint_pixels"][i]
+        if gold[f"{name}/visible"][i]:
+            assert float(w.max()) == 1.0
+        assert sf.most_common_id_weighted(torch.from_numpy(sam), w) == gold[f"{name}/dominant_id"][i]
+    # all-zero weights: index 0 of the shifted ids (the smallest id only if it is negative), one id everywhere: that id
+    zero = torch.zeros(sam.shape[0], sam.shape[1], 1)
+    lo = int(sam.min())
+    assert sf.most_common_id_weighted(torch.from_numpy(sam), zero) == (lo if lo < 0 else 0)
+    assert sf.most_common_id_weighted(torch.full((4, 5), 9), torch.zeros(4, 5, 1)) == 9
