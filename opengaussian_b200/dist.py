@@ -4,6 +4,10 @@ hot path shards in exactly two places (section 8e):
 
 * rasterizer: over CAMERA VIEWS -- every rank renders its own views against a full replica of the
   Gaussians; per-parameter gradients are summed with all-reduce (`allreduce_gradients`);
+* forward-only sweeps (construct_pseudo_ins_feat, the Stage-2.2 / Stage-3 association loops of
+  train.py:676-681,755-760,846-856): over CAMERA VIEWS too, with no collective for the images; the per-view
+  columns of `match_info [k1*k2, V, 3]` are merged once at the end (`merge_view_columns`) and the per-cluster
+  object counts `iClusterSubNum [k1]` with one all-reduce(max) (`allreduce_max`);
 * k-means: over POINTS -- every rank owns a contiguous shard, centres are replicated, and one
   all-reduce of the packed [k*D sums | k counts] buffer is done per Lloyd iteration
   (`shard_kmeans` switches a Quantize_kMeans instance into that mode; ids stay sharded,
@@ -131,6 +135,37 @@ def gather_ids(local_ids: torch.Tensor, group=None) -> torch.Tensor:
     outs = [torch.zeros_like(pad) for _ in range(w)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat([o[:int(s)] for o, s in zip(outs, sizes)])
+
+
+def view_indices(n_views: int, group=None) -> List[int]:
+    """Indices of the views `split_views` gives this rank (r, r+R, ...): the columns of a per-view table it owns."""
+    r, w = world(group)
+    return list(range(r, n_views, w))
+
+
+def merge_view_columns(table: torch.Tensor, view_dim: int = 1, group=None) -> torch.Tensor:
+    """Merges a per-view table whose columns were filled by the ranks that rendered those views
+    (`match_info [k1*k2, V, 3]`, train.py:844-890; rank r owns the columns `view_indices(V)`): every rank ends up
+    with the complete table.  Columns a rank does not own are ignored (they need not be zero)."""
+    r, w = world(group)
+    if w == 1:
+        return table
+    own = torch.zeros(table.shape[view_dim], dtype=torch.bool, device=table.device)
+    own[r::w] = True
+    shape = [1] * table.dim()
+    shape[view_dim] = -1
+    merged = torch.where(own.view(shape), table, torch.zeros_like(table)).contiguous()
+    dist.all_reduce(merged, op=dist.ReduceOp.SUM, group=group)      # disjoint supports: the sum is a merge
+    return merged
+
+
+def allreduce_max(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Element-wise maximum over ranks, in place (`iClusterSubNum [k1]`, train.py:754,804: the largest number of
+    objects any view saw in a coarse cluster)."""
+    r, w = world(group)
+    if w > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
 
 
 _SIDE_STREAMS = {}

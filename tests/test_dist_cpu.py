@@ -92,8 +92,18 @@ def _worker(rank, world, port, out):
             return loss
 
         total = ogd.render_views_backward(render_loss, views, [p1, p2, p3])
+
+        # forward-only sweep: each rank fills the match_info columns of its views, garbage elsewhere
+        V = 5
+        assert ogd.view_indices(V) == list(range(rank, V, world))
+        match_info = torch.full((6, V, 3), float("nan") if rank else -7.0)
+        for v in ogd.view_indices(V):
+            match_info[:, v] = torch.arange(18, dtype=torch.float32).view(6, 3) + 100 * v
+        merged = ogd.merge_view_columns(match_info)
+        sub_num = torch.tensor([1, 4, 2], dtype=torch.int32) if rank == 0 else torch.tensor([3, 1, 2], dtype=torch.int32)
+        ogd.allreduce_max(sub_num)
         if rank == 0:
-            out.put(dict(centers=q.centers.numpy(), ids=ids_all.numpy(), c2=[c.numpy() for c in c2],
+            out.put(dict(merged=merged.numpy(), sub_num=sub_num.numpy(),centers=q.centers.numpy(), ids=ids_all.numpy(), c2=[c.numpy() for c in c2],
                          g1=p1.grad.numpy(), g2=p2.grad.numpy(), g3=p3.grad.numpy(), total=float(total)))
         dist.barrier()
     finally:
@@ -126,6 +136,9 @@ def test_sharded_kmeans_and_grad_allreduce_world2():
     assert np.allclose(res["g3"], np.full(2, 3.0, np.float32))           # rank 0 rendered views 0, 2, 4
     w_sum = sum((np.arange(6) * (i + 1)).sum() + 4 * i for i in v) + 3 * 2
     assert abs(res["total"] - w_sum) < 1e-3
+    want = np.stack([np.arange(18, dtype=np.float32).reshape(6, 3) + 100 * i for i in range(5)], axis=1)
+    assert np.array_equal(res["merged"], want)                           # every view's column, from its owner
+    assert res["sub_num"].tolist() == [3, 4, 2]
 
 
 def test_coalesced_gradient_view_cpu():
