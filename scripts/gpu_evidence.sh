@@ -17,3 +17,11 @@ ncu --set full --clock-control none --import-source on -k regex:"blend|preproces
 python scripts/kmeans_bench.py --iters 2 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:kmeans_assign -s 3 -c 1 \
     -o gpurun_out/${TAG}_kmeans python scripts/kmeans_bench.py --iters 2 > gpurun_out/${TAG}_ncu_kmeans.log 2>&1; echo "ncu kmeans rc=$?"
+# section-8f kernels (mask statistics, mask IoU, Adam, footprint votes): probes first, then one full capture of each
+python scripts/stage3_bench.py > gpurun_out/${TAG}_stage3_probe.jsonl 2> gpurun_out/${TAG}_stage3_probe.err; echo "stage3 probe rc=$?"
+python scripts/footprint_bench.py >> gpurun_out/${TAG}_stage3_probe.jsonl 2>> gpurun_out/${TAG}_stage3_probe.err; echo "footprint probe rc=$?"
+python scripts/mask_bench.py >> gpurun_out/${TAG}_stage3_probe.jsonl 2>> gpurun_out/${TAG}_stage3_probe.err; echo "mask probe rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|mask_pack|mask_pair" -s 6 -c 3 \
+    -o gpurun_out/${TAG}_stage3 python scripts/stage3_bench.py > gpurun_out/${TAG}_ncu_stage3.log 2>&1; echo "ncu stage3 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"footprint_vote" -s 1 -c 1 \
+    -o gpurun_out/${TAG}_footprint python scripts/footprint_bench.py > gpurun_out/${TAG}_ncu_footprint.log 2>&1; echo "ncu footprint rc=$?"

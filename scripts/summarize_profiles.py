@@ -38,7 +38,8 @@ FAMILY = [  # kernel-name substring -> bench.py breakdown family
     ("blend_bwd", "blend_bwd"), ("emit_kernel", "emit"), ("ranges_kernel", "tile_ranges"),
     ("rs_pass_kernel<unsigned short", "tile_sort"), ("rs_tile_hist", "tile_sort"), ("rs_tile_scan", "tile_sort"),
     ("rs_pass_kernel<unsigned int", "depth_sort_scan"), ("rs_hist_kernel", "depth_sort_scan"),
-    ("scan_gather", "depth_sort_scan"), ("kmeans_assign", "kmeans_assign"),
+    ("scan_gather", "depth_sort_scan"), ("kmeans_assign", "kmeans_assign"), ("adam_kernel", "adam"),
+    ("mask_pack_kernel", "mask_iou"), ("mask_pair_kernel", "mask_iou"), ("footprint_vote", "footprint"),
 ]
 
 
@@ -80,7 +81,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     traffic = {}
     table = []
-    for part in ("raster", "kmeans"):
+    for part in ("raster", "kmeans", "stage3", "footprint"):
         rep = os.path.join(SRC, f"{tag}_{part}.ncu-rep")
         if not os.path.exists(rep):
             print("missing", rep)
@@ -107,7 +108,8 @@ def main():
     # number of frames captured = launches of blend_fwd (one per frame)
     frames = max(1, fam_acc.get("blend_fwd", {}).get("launches", 1))
     for fam, a in fam_acc.items():
-        n = frames if fam != "kmeans_assign" else max(1, a["launches"])
+        per_launch = fam in ("kmeans_assign", "adam", "mask_iou", "footprint")
+        n = max(1, a["launches"]) if per_launch else frames
         traffic[fam] = {"dram_bytes_per_frame": a["bytes"] / n, "ncu_time_us_per_frame": a["time_us"] / n,
                         "kernels": a["names"], "frames_captured": n}
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
