@@ -25,3 +25,5 @@ ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|mas
     -o gpurun_out/${TAG}_stage3 python scripts/stage3_bench.py > gpurun_out/${TAG}_ncu_stage3.log 2>&1; echo "ncu stage3 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"footprint_vote" -s 1 -c 1 \
     -o gpurun_out/${TAG}_footprint python scripts/footprint_bench.py > gpurun_out/${TAG}_ncu_footprint.log 2>&1; echo "ncu footprint rc=$?"
+# GPU comparator (restatement of the upstream kernel structure): parity vs the product, then frames/s of both
+python scripts/upstream_structure_bench.py > gpurun_out/${TAG}_upstream_structure.json 2> gpurun_out/${TAG}_upstream_structure.err; echo "comparator rc=$?"
