@@ -27,3 +27,5 @@ ncu --set full --clock-control none --import-source on -k regex:"footprint_vote"
     -o gpurun_out/${TAG}_footprint python scripts/footprint_bench.py > gpurun_out/${TAG}_ncu_footprint.log 2>&1; echo "ncu footprint rc=$?"
 # GPU comparator (restatement of the upstream kernel structure): parity vs the product, then frames/s of both
 python scripts/upstream_structure_bench.py > gpurun_out/${TAG}_upstream_structure.json 2> gpurun_out/${TAG}_upstream_structure.err; echo "comparator rc=$?"
+# end-to-end Stage-1 loop (fused render + mask losses + backward + one-launch Adam): the loss must decrease
+python scripts/stage1_train_demo.py > gpurun_out/${TAG}_stage1_demo.json 2> gpurun_out/${TAG}_stage1_demo.err; echo "stage1 demo rc=$?"
