@@ -301,11 +301,11 @@ static int launch_cg(const BlendBwdArgs& a, cudaStream_t s) {
     const int pairs = env_pairs ? env_pairs : (C <= 9 ? 2 : 1);
     dim3 grid((a.W + 15) / 16, (a.H + 15) / 16);
     const size_t smem = (size_t)2 * (4 / (pairs == 2 ? 2 : 1)) * BB * V * sizeof(float);
-    static bool attr_done[2] = {false, false};
-    if (smem > 24 * 1024 && !attr_done[pairs == 2]) {   // static + dynamic shared memory may pass the 48 KB default
+    static PerDeviceOnce attr_done[2];
+    if (smem > 24 * 1024 && attr_done[pairs == 2].todo()) {   // static + dynamic shared memory may pass the 48 KB default
         if (pairs == 2) OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         else OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_done[pairs == 2] = true;
+        attr_done[pairs == 2].done();
     }
     if (pairs == 2) blend_bwd_kernel<C, GEOM, 2><<<grid, 64, smem, s>>>(a);
     else blend_bwd_kernel<C, GEOM, 1><<<grid, 128, smem, s>>>(a);

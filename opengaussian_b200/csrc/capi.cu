@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -31,6 +32,7 @@ static bool g_prof_on = false;
 static std::vector<ProfPair> g_prof_pairs;
 static std::vector<cudaEvent_t> g_prof_free;
 static cudaEvent_t g_prof_open[PF_COUNT];
+static std::mutex g_prof_mu;      // the profile is a per-process measurement aid; the lock keeps it consistent
 
 static cudaEvent_t prof_event() {
     if (!g_prof_free.empty()) { cudaEvent_t e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
@@ -40,12 +42,15 @@ static cudaEvent_t prof_event() {
 }
 void prof_begin(int family, cudaStream_t s) {
     if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEvent_t e = prof_event();
     cudaEventRecord(e, s);
     g_prof_open[family] = e;
 }
 void prof_end(int family, cudaStream_t s) {
-    if (!g_prof_on || !g_prof_open[family]) return;
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_open[family]) return;
     cudaEvent_t e = prof_event();
     cudaEventRecord(e, s);
     g_prof_pairs.push_back({g_prof_open[family], e, family});
@@ -65,14 +70,24 @@ static int ensure_pool(void) {
     return 0;
 }
 
-static thread_local uint64_t g_cap_hint = 0;   // running estimate of num_rendered (+25 %), see ogs_raster_forward
+// Per host thread AND per device: running estimate of num_rendered (+25 %, see ogs_raster_forward), the pinned
+// word the scan total is copied to, and the event that marks that copy.  (Events and pinned allocations belong to
+// the device/context that was current when they were made.)
+struct ForwardCtx {
+    uint64_t cap_hint = 0;
+    uint32_t* pinned = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+static ForwardCtx& forward_ctx(void) {
+    static thread_local ForwardCtx ctx[OGS_MAX_DEVICES];
+    return ctx[current_device()];
+}
 
-static uint32_t* pinned_scalar(void) {
-    static thread_local uint32_t* p = nullptr;
-    if (!p) {
-        if (cudaMallocHost((void**)&p, 64) != cudaSuccess) p = nullptr;
+static uint32_t* pinned_scalar(ForwardCtx& fc) {
+    if (!fc.pinned) {
+        if (cudaMallocHost((void**)&fc.pinned, 64) != cudaSuccess) fc.pinned = nullptr;
     }
-    return p;
+    return fc.pinned;
 }
 
 __global__ void export_keys_kernel(int tiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -127,7 +142,7 @@ static int validate_inputs(const ogs_raster_inputs* in) {
     }
     if ((in->act_flags & OGS_ACT_EXTRA_UNIT_HALF) && in->n_extra <= 0) { set_error("extra activation needs n_extra > 0"); return -1; }
     const int gx = (in->W + 15) / 16, gy = (in->H + 15) / 16;
-    if ((int64_t)gx * gy > 65535) { set_error("image too large: %d tiles (max 65535)", gx * gy); return -1; }
+    if ((int64_t)gx * gy > 65536) { set_error("image too large: %d tiles (max 65536: the tile id is a 16-bit sort key)", gx * gy); return -1; }
     if (!in->bg || !in->viewmatrix || !in->projmatrix || !in->campos) { set_error("bg/viewmatrix/projmatrix/campos must be set"); return -1; }
     return 0;
 }
@@ -141,6 +156,7 @@ extern "C" {
 int ogs_abi_version(void) { return OGS_ABI_VERSION; }
 
 void ogs_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = on != 0;
     if (g_prof_on && g_prof_free.size() < 2048) {   // pre-create so that recording costs no driver allocation
         for (int i = 0; i < 2048; i++) {
@@ -153,6 +169,7 @@ void ogs_profile_enable(int on) {
 int ogs_profile_read(float* ms_out, int32_t* launches_out, int32_t n) {
     float ms[PF_COUNT] = {0};
     int cnt[PF_COUNT] = {0};
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& p : g_prof_pairs) {
         cudaError_t e = cudaEventSynchronize(p.b);
         float t = 0.f;
@@ -208,19 +225,21 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     uint32_t* h = nullptr;
     const uint32_t* n_ptr = nullptr;
     cudaEvent_t n_event = nullptr;
-    char* scratch1 = nullptr;
+    ForwardCtx& fc = forward_ctx();
+    AsyncScratch scratch1(s);          // freed (stream-ordered) on every exit path
     BinScratch sc;
     memset(&sc, 0, sizeof sc);
     if (P > 0) {
         const size_t pw = align_up((size_t)P * 4, 256);
         sc.cub_temp_bytes = align_up(depth_sort_temp_bytes(P), 256);
-        OGS_CUDA(cudaMallocAsync((void**)&scratch1, pw * 5 + sc.cub_temp_bytes, s));
-        sc.dkeys_in = (uint32_t*)(scratch1);
-        sc.dvals_in = (uint32_t*)(scratch1 + pw);
-        sc.dkeys_out = (uint32_t*)(scratch1 + 2 * pw);
-        sc.dvals_out = (uint32_t*)(scratch1 + 3 * pw);
-        sc.offsets = (uint32_t*)(scratch1 + 4 * pw);
-        sc.cub_temp = scratch1 + 5 * pw;
+        OGS_CUDA(scratch1.alloc(pw * 5 + sc.cub_temp_bytes));
+        char* s1 = (char*)scratch1.p;
+        sc.dkeys_in = (uint32_t*)(s1);
+        sc.dvals_in = (uint32_t*)(s1 + pw);
+        sc.dkeys_out = (uint32_t*)(s1 + 2 * pw);
+        sc.dvals_out = (uint32_t*)(s1 + 3 * pw);
+        sc.offsets = (uint32_t*)(s1 + 4 * pw);
+        sc.cub_temp = s1 + 5 * pw;
 
         PreprocessArgs pa;
         pa.P = P; pa.D = in->sh_degree; pa.M = in->M; pa.W = W; pa.H = H;
@@ -233,30 +252,29 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         prof_begin(PF_PREPROCESS_FWD, s);
         rc = launch_preprocess_forward(pa, s);
         prof_end(PF_PREPROCESS_FWD, s);
-        if (rc) { cudaFreeAsync(scratch1, s); return rc; }
+        if (rc) return rc;
         OGS_KERNEL_CHECK("preprocess_forward", in->debug, s);
         prof_begin(PF_DEPTH_SORT_SCAN, s);
         rc = depth_sort_and_scan(P, g, sc, s, in->debug);
         prof_end(PF_DEPTH_SORT_SCAN, s);
-        if (rc) { cudaFreeAsync(scratch1, s); return rc; }
-        h = pinned_scalar();
-        if (!h) { cudaFreeAsync(scratch1, s); set_error("cudaMallocHost failed"); return 2; }
+        if (rc) return rc;
+        h = pinned_scalar(fc);
+        if (!h) { set_error("cudaMallocHost failed"); return 2; }
         n_ptr = sc.offsets + (P - 1);
         OGS_CUDA(cudaMemcpyAsync(h, n_ptr, 4, cudaMemcpyDeviceToHost, s));
-        // Capacity speculation: the binning buffers are sized from the running estimate g_cap_hint and
+        // Capacity speculation: the binning buffers are sized from the running estimate cap_hint and
         // the N-dependent kernels take N from device memory, so emit/sort/blend are queued WITHOUT
         // waiting for the scan; the host reads N only after everything is launched (the scan has long
         // finished by then).  If the estimate was too small the binning + blend are redone (rare).
-        if (g_cap_hint == 0 || in->debug) {
+        if (fc.cap_hint == 0 || in->debug) {
             OGS_CUDA(cudaStreamSynchronize(s));
             N = (int64_t)*h;
             cap = N;
         } else {
-            static thread_local cudaEvent_t ev = nullptr;
-            if (!ev) OGS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            OGS_CUDA(cudaEventRecord(ev, s));
-            n_event = ev;
-            cap = (int64_t)g_cap_hint;
+            if (!fc.ev) OGS_CUDA(cudaEventCreateWithFlags(&fc.ev, cudaEventDisableTiming));
+            OGS_CUDA(cudaEventRecord(fc.ev, s));
+            n_event = fc.ev;
+            cap = (int64_t)fc.cap_hint;
             speculative = true;
         }
     }
@@ -266,24 +284,24 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         const BinLayout bl = BinLayout::make(cap, tiles);
         st->binning = alloc(alloc_user, bl.total, "binning");
         st->binning_bytes = (int64_t)bl.total;
-        if (!st->binning) { if (scratch1) cudaFreeAsync(scratch1, s); set_error("allocation callback returned NULL"); return -6; }
+        if (!st->binning) { set_error("allocation callback returned NULL"); return -6; }
         point_list = (uint32_t*)((char*)st->binning + bl.point_list);
         ranges = (uint2*)((char*)st->binning + bl.ranges);
-        char* scratch2 = nullptr;
         if (cap > 0 && P > 0) {
+            AsyncScratch scratch2(s);
             const size_t k2 = align_up((size_t)cap * 2, 256), v4 = align_up((size_t)cap * 4, 256);
             const size_t tb = align_up(tile_sort_temp_bytes(cap), 256);
-            OGS_CUDA(cudaMallocAsync((void**)&scratch2, 2 * k2 + v4 + tb, s));
-            sc.cub_temp = scratch2 + 2 * k2 + v4;
+            OGS_CUDA(scratch2.alloc(2 * k2 + v4 + tb));
+            char* s2 = (char*)scratch2.p;
+            sc.cub_temp = s2 + 2 * k2 + v4;
             sc.cub_temp_bytes = tb;
-            rc = emit_sort_ranges(P, W, H, n_ptr, cap, g, sc, (uint16_t*)scratch2, (uint32_t*)(scratch2 + 2 * k2),
-                                  (uint16_t*)(scratch2 + k2), point_list, ranges, s, in->debug);
+            rc = emit_sort_ranges(P, W, H, n_ptr, cap, g, sc, (uint16_t*)s2, (uint32_t*)(s2 + 2 * k2),
+                                  (uint16_t*)(s2 + k2), point_list, ranges, s, in->debug);
         } else {
             cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s);
             if (e != cudaSuccess) rc = cuda_fail(e, "memset ranges");
         }
-        if (scratch2) cudaFreeAsync(scratch2, s);
-        if (rc) { if (scratch1) cudaFreeAsync(scratch1, s); return rc; }
+        if (rc) return rc;
 
         BlendFwdArgs ba;
         ba.W = W; ba.H = H; ba.C = C;
@@ -295,7 +313,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         prof_begin(PF_BLEND_FWD, s);
         rc = launch_blend_forward(ba, s);
         prof_end(PF_BLEND_FWD, s);
-        if (rc) { if (scratch1) cudaFreeAsync(scratch1, s); return rc; }
+        if (rc) return rc;
         OGS_KERNEL_CHECK("blend_forward", in->debug, s);
         if (!speculative) break;
         OGS_CUDA(cudaEventSynchronize(n_event));
@@ -304,11 +322,11 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         if (N <= cap) break;
         cap = N;                       // estimate too small: redo binning + blend with the exact size
     }
-    if (scratch1) cudaFreeAsync(scratch1, s);
+    scratch1.release();
     if (P > 0) {
         const uint64_t want = (uint64_t)N + (uint64_t)N / 4 + 65536;
-        const uint64_t decay = g_cap_hint - g_cap_hint / 32;
-        g_cap_hint = want > decay ? want : decay;
+        const uint64_t decay = fc.cap_hint - fc.cap_hint / 32;
+        fc.cap_hint = want > decay ? want : decay;
     }
     st->num_rendered = N;
     return 0;

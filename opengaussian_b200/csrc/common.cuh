@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/ogs_b200.h"
 
 #ifndef OGS_FWD_PAIRS
@@ -28,6 +30,33 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns (int)e
         if (_e == cudaSuccess && (dbg)) _e = cudaStreamSynchronize(stream); \
         if (_e != cudaSuccess) return ogs::cuda_fail(_e, name);       \
     } while (0)
+
+// Function attributes (cudaFuncSetAttribute) belong to a device: "already done" flags are kept per device so that
+// one process driving several GPUs (or several host threads) sets them on each.  Racing threads may both set the
+// attribute; that is harmless.
+#define OGS_MAX_DEVICES 64
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & (OGS_MAX_DEVICES - 1);
+}
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool todo() const { return !((mask.load(std::memory_order_relaxed) >> current_device()) & 1ull); }
+    void done() { mask.fetch_or(1ull << current_device(), std::memory_order_relaxed); }
+};
+
+// Frees stream-ordered scratch on every exit path of a launcher.
+struct AsyncScratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    explicit AsyncScratch(cudaStream_t s_) : s(s_) {}
+    AsyncScratch(const AsyncScratch&) = delete;
+    AsyncScratch& operator=(const AsyncScratch&) = delete;
+    cudaError_t alloc(size_t bytes) { release(); return cudaMallocAsync(&p, bytes, s); }
+    void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; } }
+    ~AsyncScratch() { release(); }
+};
 
 // ---- optional per-family device timing (CUDA events on the launching stream) ----
 enum ProfFamily { PF_PREPROCESS_FWD = 0, PF_DEPTH_SORT_SCAN, PF_EMIT, PF_TILE_SORT, PF_RANGES, PF_BLEND_FWD,

@@ -263,10 +263,11 @@ static int launch_assign_d(int64_t N, const float* a, int Da, const float* b, in
     size_t smem = (size_t)2 * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
     if (fuse) smem += (size_t)KM_WARPS * k * (D + 1) * sizeof(float);
     if (smem > 220 * 1024) { set_error("kmeans_assign: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
+    static std::atomic<size_t> attr[OGS_MAX_DEVICES];        // per device: largest size the attribute was raised to
+    std::atomic<size_t>& at = attr[current_device()];
+    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
         OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+        at.store(smem, std::memory_order_relaxed);
     }
     // bulk copies need 16-byte aligned sources and sizes: tile strides are multiples of 4096 bytes
     const int bulk_ok = (((uintptr_t)a & 15) == 0 && (Db == 0 || ((uintptr_t)b & 15) == 0)) ? 1 : 0;

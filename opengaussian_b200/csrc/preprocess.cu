@@ -284,10 +284,10 @@ int launch_preprocess_forward(const PreprocessArgs& a, cudaStream_t s) {
     const int blocks = (a.P + PF - 1) / PF;
     if (a.shs) {
         const size_t smem = (size_t)PF * (a.M * 3 + 1) * sizeof(float);
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(preprocess_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attr_done = true;
+        static PerDeviceOnce attr_done;
+        if (attr_done.todo()) {
+            OGS_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done.done();
         }
         if (smem > 100 * 1024) { set_error("preprocess: SH block too large (M=%d)", a.M); return -3; }
         preprocess_fwd_kernel<true><<<blocks, PF, smem, s>>>(a);

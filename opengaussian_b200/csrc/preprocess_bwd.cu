@@ -120,7 +120,6 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
 
     // colour / feature gradients pass straight through
     if (a.dL_dcolors_precomp) {
-#pragma unroll
         if (vis || !(a.accumulate & 1))
             for (int c = 0; c < 3; c++) put(a.dL_dcolors_precomp + 3 * (size_t)i + c, vis ? acc[c] : 0.f, (a.accumulate & 1) != 0);
     }
@@ -428,10 +427,10 @@ int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
         return -3;
     }
     if (staged) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attr_done = true;
+        static PerDeviceOnce attr_done;
+        if (attr_done.todo()) {
+            OGS_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done.done();
         }
         preprocess_bwd_kernel<true><<<(a.P + PB - 1) / PB, PB, smem, s>>>(a);
     } else {

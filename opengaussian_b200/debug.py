@@ -31,7 +31,7 @@ def forward_with_state(rs: GaussianRasterizationSettings, means3D, opacities, sh
     st = _lib.RasterState()
     alloc = _Alloc(dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, None, C.byref(st), C.c_void_p(stream)),
+    _lib.check(L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, alloc.user, C.byref(st), C.c_void_p(stream)),
                "ogs_raster_forward")
     N = int(st.num_rendered)
     out = dict(color=color, depth=depth, alpha=alpha, radii=radii, N=N, _bufs=alloc.bufs, _state=st, _inputs=ri,

@@ -41,76 +41,68 @@ def shard_range(n: int, group=None):
     return min(n, r * per), min(n, (r + 1) * per)
 
 
-def allreduce_gradients(params: Iterable[torch.Tensor], group=None, bucket_bytes: int = 256 << 20,
+def _flat_layout(params):
+    """Offsets (in floats) of every parameter's gradient in the step's flat buffer: the parameters in the given
+    order, each slice aligned to 64 floats -- a function of the parameter SHAPES only, hence identical on every
+    rank.  It is also the layout the rasterizer's backward carves its gradients from (rasterizer.py), so that
+    buffer is reduced in place when the caller lists the parameters in the rasterizer's order."""
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + 63) // 64 * 64
+    span = offs[-1] + params[-1].numel() if params else 0
+    return offs, span
+
+
+def allreduce_gradients(params: Iterable[torch.Tensor], group=None, bucket_bytes: int = 1 << 30,
                         average: bool = False):
-    """Sums .grad of every parameter across ranks, packing small tensors into flat buckets
-    (bucket size chosen for launch latency, not link count: NVSwitch gives every peer full
-    bandwidth).  Parameters whose .grad is None on this rank contribute zeros."""
+    """Sums .grad of every parameter across ranks with ONE collective over a flat fp32 buffer (split into
+    `bucket_bytes` pieces only beyond that size: NVSwitch gives every peer full bandwidth, so buckets are sized for
+    launch latency, not link count).  The collective sequence is RANK-INVARIANT: its element count comes from the
+    parameter shapes alone (`_flat_layout`), and a parameter whose .grad is None on this rank -- a rank that had
+    no view this step -- contributes zeros.  Afterwards every .grad is a view into the reduced buffer."""
     r, w = world(group)
     if w == 1:
         return
     params = [p for p in params if p.requires_grad]
-    flat = _coalesced_grads(params)
-    if flat is not None:          # the rasterizer's backward carves all gradients out of one buffer
-        dist.all_reduce(flat, group=group)
-        if average:
-            flat.div_(w)
+    if not params:
         return
-    bucket, size = [], 0
-
-    def flush():
-        nonlocal bucket, size
-        if not bucket:
-            return
-        if len(bucket) == 1 and bucket[0].grad is not None and bucket[0].grad.is_contiguous():
-            dist.all_reduce(bucket[0].grad, group=group)
-            if average:
-                bucket[0].grad.div_(w)
-        else:
-            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float()
-                              for p in bucket])
-            dist.all_reduce(flat, group=group)
-            if average:
-                flat.div_(w)
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                g = flat[off:off + n].view_as(p).to(p.dtype)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
-                off += n
-        bucket, size = [], 0
-
-    for p in params:
-        nbytes = p.numel() * 4
-        if nbytes >= bucket_bytes:
-            flush()
-            bucket = [p]
-            flush()
-            continue
-        if size + nbytes > bucket_bytes:
-            flush()
-        bucket.append(p)
-        size += nbytes
-    flush()
+    offs, span = _flat_layout(params)
+    flat = _coalesced_grads(params, offs, span)
+    packed = flat is None
+    if packed:
+        flat = torch.zeros(span, dtype=torch.float32, device=params[0].device)
+        for p, o in zip(params, offs):
+            if p.grad is not None:
+                flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
+    step = max(1, bucket_bytes // 4)
+    for lo in range(0, span, step):
+        dist.all_reduce(flat[lo:lo + step], group=group)
+    if average:
+        flat.div_(w)
+    if packed:
+        for p, o in zip(params, offs):
+            g = flat[o:o + p.numel()].view(p.shape)
+            p.grad = g if p.dtype == torch.float32 else g.to(p.dtype)
 
 
-def _coalesced_grads(params) -> Optional[torch.Tensor]:
-    """If every .grad is a contiguous fp32 view into ONE storage and together they (almost) tile a span of
-    it, returns that span as a flat tensor (alignment gaps between the slices ride along)."""
+def _coalesced_grads(params, offs=None, span=None) -> Optional[torch.Tensor]:
+    """If every .grad is a contiguous fp32 view into ONE storage laid out exactly as `_flat_layout` says, returns
+    that span as a flat tensor (the alignment gaps between the slices ride along), else None."""
+    params = list(params)
+    if offs is None:
+        offs, span = _flat_layout(params)
     grads = [p.grad for p in params]
-    if len(grads) < 2 or any(g is None or g.dtype != torch.float32 or not g.is_contiguous() for g in grads):
+    if not grads or any(g is None or g.dtype != torch.float32 or not g.is_contiguous() for g in grads):
         return None
     st = grads[0].untyped_storage()
-    if any(g.untyped_storage().data_ptr() != st.data_ptr() for g in grads):
+    base = grads[0].storage_offset()
+    for g, o in zip(grads, offs):
+        if g.untyped_storage().data_ptr() != st.data_ptr() or g.storage_offset() - base != o:
+            return None
+    if (base + span) * 4 > st.nbytes():
         return None
-    lo = min(g.storage_offset() for g in grads)
-    hi = max(g.storage_offset() + g.numel() for g in grads)
-    if hi - lo > sum(g.numel() for g in grads) + 64 * len(grads):
-        return None
-    return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, lo, (hi - lo,))
+    return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, base, (span,))
 
 
 def shard_kmeans(codebook, group=None):
@@ -236,6 +228,10 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
                 total = part if total is None else total + part
     allreduce_gradients(params, group)
     r, w = world(group)
-    if w > 1 and total is not None:
+    if w > 1:
+        # rank-invariant: a rank without views this step (fewer views than ranks) contributes a zero loss
+        if total is None:
+            dev = params[0].device if params else torch.device("cpu")
+            total = torch.zeros((), dtype=torch.float32, device=dev)
         dist.all_reduce(total, group=group)
     return total

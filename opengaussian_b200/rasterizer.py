@@ -11,6 +11,7 @@ more per-Gaussian channels (OpenGaussian's ``ins_feat``) in the SAME pass and ap
 return value ``feats [F,H,W]`` -- this is what lets ``render()`` replace its 4 passes by one.
 """
 import ctypes as C
+import itertools
 from typing import NamedTuple, Optional
 
 import torch
@@ -53,25 +54,31 @@ def _none_if_empty(t):
 
 
 class _Alloc:
-    """Allocation callback handed to the C ABI.  ONE process-wide ctypes thunk is created; each
-    forward installs a fresh dict that receives the torch buffers (kept alive by the autograd ctx).
-    No per-call ctypes objects and no reference cycles: buffers are released by refcount as soon as
-    the graph dies (a cycle here would park ~100 MB per frame until the cyclic GC runs and force
-    the caching allocator into cudaMalloc on every step)."""
-    _current = None
-    _device = None
+    """Allocation callback handed to the C ABI.  ONE process-wide ctypes thunk is created; the per-call
+    state travels through the ABI's `alloc_user` pointer (a key into `_live`), so concurrent forwards from
+    several Python threads / devices do not see each other.  Each forward owns a fresh dict that receives
+    the torch buffers (kept alive by the autograd ctx).  No per-call ctypes objects and no reference cycles:
+    buffers are released by refcount as soon as the graph dies (a cycle here would park ~100 MB per frame
+    until the cyclic GC runs and force the caching allocator into cudaMalloc on every step)."""
+    _live = {}
+    _next = itertools.count(1)
 
     @staticmethod
-    def _cb(_user, nbytes, tag):
-        t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_Alloc._device)
-        _Alloc._current[tag.decode()] = t
+    def _cb(user, nbytes, tag):
+        bufs, device = _Alloc._live[user]
+        t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        bufs[tag.decode()] = t
         return t.data_ptr()
 
     def __init__(self, device):
         self.bufs = {}
-        _Alloc._current = self.bufs
-        _Alloc._device = device
+        self.key = next(_Alloc._next)
+        _Alloc._live[self.key] = (self.bufs, device)
         self.fn = _ALLOC_THUNK
+        self.user = C.c_void_p(self.key)
+
+    def __del__(self):
+        _Alloc._live.pop(self.key, None)
 
 
 _ALLOC_THUNK = _lib.ALLOC_FN(_Alloc._cb)
@@ -198,7 +205,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         alloc = _Alloc(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            rc = L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, None, C.byref(st), C.c_void_p(stream))
+            rc = L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, alloc.user, C.byref(st), C.c_void_p(stream))
         _lib.check(rc, "ogs_raster_forward")
 
         ctx.rs = rs

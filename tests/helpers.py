@@ -25,3 +25,16 @@ def to_oracle_cam(cam, sh_degree=3, scale_modifier=1.0):
 
 def np_inputs(gs):
     return {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in gs.items()}
+
+
+def grad_violations(got, want, rtol=1e-3):
+    """Per-element gradient check (BASELINE north_star: "gradients within 1e-3 relative"): an element passes when
+    |got - want| <= rtol * |want| + rtol * rms(want).  Returns (violating fraction, worst |diff| / tolerance)."""
+    got = np.asarray(got, np.float64).reshape(-1)
+    want = np.asarray(want, np.float64).reshape(-1)
+    if want.size == 0:
+        return 0.0, 0.0
+    rms = float(np.sqrt(np.mean(want * want)))
+    tol = rtol * np.abs(want) + rtol * rms + 1e-30
+    ratio = np.abs(got - want) / tol
+    return float((ratio > 1.0).mean()), float(ratio.max())

@@ -93,6 +93,16 @@ def _worker(rank, world, port, out):
 
         total = ogd.render_views_backward(render_loss, views, [p1, p2, p3])
 
+        # fewer views than ranks: rank 1 renders nothing, yet must take part in the same collectives
+        # (zero gradients, zero loss) -- a rank-dependent sequence here hangs NCCL
+        q1 = torch.nn.Parameter(torch.full((70,), 2.0))
+        q2_ = torch.nn.Parameter(torch.ones(3, 3))
+        total1 = ogd.render_views_backward(lambda v: (q1 ** 2).sum() + 3.0 * q2_.sum(), [0], [q1, q2_])
+        assert q1.grad is not None and q2_.grad is not None and total1 is not None
+        few = dict(g1=q1.grad.clone(), g2=q2_.grad.clone(), total=float(total1))
+        few_all = [None] * world
+        dist.all_gather_object(few_all, few)
+
         # forward-only sweep: each rank fills the match_info columns of its views, garbage elsewhere
         V = 5
         assert ogd.view_indices(V) == list(range(rank, V, world))
@@ -104,7 +114,8 @@ def _worker(rank, world, port, out):
         ogd.allreduce_max(sub_num)
         if rank == 0:
             out.put(dict(merged=merged.numpy(), sub_num=sub_num.numpy(),centers=q.centers.numpy(), ids=ids_all.numpy(), c2=[c.numpy() for c in c2],
-                         g1=p1.grad.numpy(), g2=p2.grad.numpy(), g3=p3.grad.numpy(), total=float(total)))
+                         g1=p1.grad.numpy(), g2=p2.grad.numpy(), g3=p3.grad.numpy(), total=float(total),
+                         few=[{k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in f.items()} for f in few_all]))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -136,6 +147,9 @@ def test_sharded_kmeans_and_grad_allreduce_world2():
     assert np.allclose(res["g3"], np.full(2, 3.0, np.float32))           # rank 0 rendered views 0, 2, 4
     w_sum = sum((np.arange(6) * (i + 1)).sum() + 4 * i for i in v) + 3 * 2
     assert abs(res["total"] - w_sum) < 1e-3
+    for f in res["few"]:                                                 # both ranks hold the one view's gradients
+        assert np.allclose(f["g1"], np.full(70, 4.0, np.float32)) and np.allclose(f["g2"], np.full((3, 3), 3.0, np.float32))
+        assert abs(f["total"] - (70 * 4.0 + 27.0)) < 1e-3
     want = np.stack([np.arange(18, dtype=np.float32).reshape(6, 3) + 100 * i for i in range(5)], axis=1)
     assert np.array_equal(res["merged"], want)                           # every view's column, from its owner
     assert res["sub_num"].tolist() == [3, 4, 2]

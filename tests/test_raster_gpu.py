@@ -2,20 +2,22 @@
 
 Bars (BASELINE.json north_star): radii, tiles_touched, depth bits, sorted keys, point list and
 tile ranges BIT-EXACT; images/features within 1e-5 absolute (pixels whose skip/stop decision sits
-within the oracle's relative margin of a threshold are excluded and counted); gradients within
-1e-3 relative (to the tensor's max magnitude; atomic/reduction order differs).
+within the oracle's relative margin of a threshold are excluded, counted, printed and bounded to
+MAX_FLAGGED of the image); gradients within 1e-3 relative PER ELEMENT: |got - want| <=
+1e-3 |want| + 1e-3 rms(want) (helpers.grad_violations; the violating fraction is printed and must be 0).
 """
 import numpy as np
 import pytest
 import torch
 
-from helpers import np_inputs, small_scene, to_oracle_cam
+from helpers import grad_violations, np_inputs, small_scene, to_oracle_cam
 from oracle import raster as orc
 
 pytestmark = pytest.mark.gpu
 
 IMG_TOL = 1e-5
 GRAD_RTOL = 1e-3
+MAX_FLAGGED = 0.03      # largest admissible share of pixels the oracle flags as threshold-borderline
 
 
 def _settings(cam, bg, sh_degree=3, scale_modifier=1.0, dev="cuda"):
@@ -102,7 +104,8 @@ def test_forward_parity(name, P, W, H, kw):
     assert np.array_equal(out["ranges"].cpu().numpy().view(np.uint32), st.ranges)
     # ---- images ----
     ok = st.flags == 0
-    assert ok.mean() > 0.9
+    print(f"{name}: {int((~ok).sum())} of {ok.size} pixels flagged borderline ({1 - ok.mean():.3%})")
+    assert 1.0 - ok.mean() <= MAX_FLAGGED
     color = out["color"].cpu().numpy()
     assert np.abs(color - st.color)[:, ok].max() <= IMG_TOL
     assert np.abs(out["depth"].cpu().numpy() - st.out_depth)[ok].max() <= IMG_TOL * max(1.0, st.out_depth.max())
@@ -180,7 +183,9 @@ def test_backward_parity(name, P, W, H, kw):
         want = ref[k]
         got = t.grad.cpu().numpy().reshape(np.asarray(want).shape)
         assert np.isfinite(got).all(), k
-        assert _rel(got, want) <= GRAD_RTOL, (k, _rel(got, want))
+        frac, worst = grad_violations(got, want, GRAD_RTOL)
+        print(f"{name} dL/d{k}: violating fraction {frac:.2e}, worst |diff|/tol {worst:.3f}, max-rel {_rel(got, want):.2e}")
+        assert frac == 0.0, (k, frac, worst)
 
 
 def test_feature_only_backward_matches_full():
@@ -191,16 +196,17 @@ def test_feature_only_backward_matches_full():
     c = _cuda(gs)
     gcol = torch.randn(3, H, W, device="cuda")
     gfeat = torch.randn(6, H, W, device="cuda")
+    ref = orc.backward(st, (torch.cat([gcol, gfeat]).cpu().numpy() * (st.flags == 0)).astype(np.float32))
+    keep = torch.as_tensor(st.flags == 0, device="cuda")
     grads = []
     for full in (False, True):
         extra = c["ins_feat"].clone().requires_grad_(True)
         m3 = c["means3D"].clone().requires_grad_(full)
         r = GaussianRasterizer(rs)(means3D=m3, means2D=torch.zeros_like(m3), opacities=c["opacities"], shs=c["shs"],
                                    scales=c["scales"], rotations=c["rotations"], extra_feats=extra)
-        ((r[0] * gcol).sum() + (r[4] * gfeat).sum()).backward()
+        ((r[0] * gcol * keep).sum() + (r[4] * gfeat * keep).sum()).backward()
         grads.append(extra.grad.clone())
-    ref = orc.backward(st, torch.cat([gcol, gfeat]).cpu().numpy())
-    assert _rel(grads[0].cpu().numpy(), ref["extra"]) <= GRAD_RTOL
+    assert grad_violations(grads[0].cpu().numpy(), ref["extra"], GRAD_RTOL)[0] == 0.0
     assert _rel(grads[0].cpu().numpy(), grads[1].cpu().numpy()) <= 1e-4
 
 
@@ -441,3 +447,124 @@ def test_fused_gradient_accumulation_equals_autograd():
         assert len(res[(fresh_m2, True)]) == len(res[(fresh_m2, False)])
         for a, b in zip(res[(fresh_m2, True)], res[(fresh_m2, False)]):
             assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-9
+
+
+FULL_SIZE = [("blender_300k_800", True), ("scannet_1m_1296x968", True), ("lerf_1m_1080p", False), ("lerf_3m_1080p", False)]
+
+
+@pytest.mark.parametrize("scene,fused", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_oracle_parity(scene, fused):
+    """BASELINE.json configs 2-4 (and the metric's own 1 M / 1080p workload) at FULL size against the CPU oracle
+    (OpenMP: seconds per frame): sorted 64-bit keys, point list and tile ranges bit-exact at N up to ~25 M; images
+    within 1e-5 on unflagged pixels (flagged share printed and bounded); every gradient per element within
+    1e-3 |want| + 1e-3 rms(want)."""
+    from opengaussian_b200 import debug, synth
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    gs, cams = synth.make_scene(scene, n_views=4)
+    cam = cams[1]
+    W, H = cam.image_width, cam.image_height
+    bg = np.array([0.05, 0.1, 0.15], np.float32)
+    g = np_inputs(gs)
+    extra_np = g["ins_feat"] if fused else None
+    st = orc.forward(to_oracle_cam(cam), g["means3D"], g["opacities"], g["scales"], g["rotations"], shs=g["shs"],
+                     extra=extra_np, bg=bg)
+    c = _cuda(gs)
+    rs = _settings(cam, bg)._replace(debug=False)
+    out = debug.forward_with_state(rs, c["means3D"], c["opacities"], shs=c["shs"], scales=c["scales"],
+                                   rotations=c["rotations"], extra=c["ins_feat"] if fused else None)
+    assert out["N"] == st.N
+    assert np.array_equal(out["radii"].cpu().numpy(), st.radii)
+    assert np.array_equal(out["keys"].cpu().numpy().view(np.uint64), st.keys)
+    assert np.array_equal(out["point_list"].cpu().numpy().view(np.uint32), st.point_list)
+    assert np.array_equal(out["ranges"].cpu().numpy().view(np.uint32), st.ranges)
+    ok = st.flags == 0
+    print(f"{scene}: N = {st.N}, {int((~ok).sum())} of {ok.size} pixels flagged borderline ({1 - ok.mean():.3%})")
+    assert 1.0 - ok.mean() <= MAX_FLAGGED
+    assert np.abs(out["color"].cpu().numpy() - st.color)[:, ok].max() <= IMG_TOL
+    assert np.abs(out["depth"].cpu().numpy() - st.out_depth)[ok].max() <= IMG_TOL * max(1.0, float(st.out_depth.max()))
+    assert np.abs(out["alpha"].cpu().numpy() - st.out_alpha)[ok].max() <= IMG_TOL
+    assert np.array_equal(out["n_contrib"].cpu().numpy().view(np.uint32)[ok], st.n_contrib[ok])
+    del out
+    # gradients of every input, borderline pixels' loss zeroed on both sides
+    Cn = 9 if fused else 3
+    rng = np.random.default_rng(11)
+    m = ok.astype(np.float32)
+    gc = rng.standard_normal((Cn, H, W)).astype(np.float32) * m
+    gd = rng.standard_normal((H, W)).astype(np.float32) * m
+    ga = rng.standard_normal((H, W)).astype(np.float32) * m
+    ref = orc.backward(st, gc, gd, ga)
+    leaves = {k: c[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    leaves["means2D"] = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    args = dict(leaves)
+    if fused:
+        leaves["extra"] = c["ins_feat"].clone().requires_grad_(True)
+        args["extra_feats"] = leaves["extra"]
+    res = GaussianRasterizer(rs)(**args)
+    t = lambda a: torch.as_tensor(a, device="cuda")  # noqa: E731
+    loss = (res[0] * t(gc[:3])).sum() + (res[2][0] * t(gd)).sum() + (res[3][0] * t(ga)).sum()
+    if fused:
+        loss = loss + (res[4] * t(gc[3:])).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    for k, leaf in leaves.items():
+        want = np.asarray(ref[k])
+        got = leaf.grad.cpu().numpy().reshape(want.shape)
+        frac, worst = grad_violations(got, want, GRAD_RTOL)
+        print(f"{scene} dL/d{k}: violating fraction {frac:.2e}, worst |diff|/tol {worst:.3f}")
+        assert np.isfinite(got).all() and frac == 0.0, (k, frac, worst)
+
+
+def test_plumbing_config_vs_fp64_autograd():
+    """Second, independent pin of the blending and of the whole backward (BASELINE config 1: 10 k Gaussians,
+    256 x 256): the CUDA images and gradients against oracle/raster_torch.py -- the forward formulas in fp64 torch,
+    gradients from autograd -- with NO C oracle in between (tile lists and radii are the CUDA path's own export)."""
+    from opengaussian_b200 import debug, synth
+    from opengaussian_b200.rasterizer import GaussianRasterizer
+    from oracle import raster_torch
+    gs, cams = synth.make_scene("plumbing_10k_256", n_views=3)
+    cam = cams[2]
+    W, H = cam.image_width, cam.image_height
+    P = gs["means3D"].shape[0]
+    bg = np.array([0.2, 0.1, 0.3], np.float32)
+    c = _cuda(gs)
+    rs = _settings(cam, bg)
+    out = debug.forward_with_state(rs, c["means3D"], c["opacities"], shs=c["shs"], scales=c["scales"],
+                                   rotations=c["rotations"], extra=c["ins_feat"])
+    d = lambda x: x.detach().double().cpu().requires_grad_(True)  # noqa: E731
+    lv = dict(means3D=d(gs["means3D"]), means2D=torch.zeros(P, 3, dtype=torch.float64, requires_grad=True),
+              opacities=d(gs["opacities"]), scales=d(gs["scales"]), rotations=d(gs["rotations"]), shs=d(gs["shs"]),
+              extra=d(gs["ins_feat"]))
+    col64, dep64, alp64 = raster_torch.render(
+        to_oracle_cam(cam), out["radii"].cpu().numpy(), out["point_list"].cpu().numpy().view(np.uint32),
+        out["ranges"].cpu().numpy().view(np.uint32).reshape(-1, 2), lv["means3D"], lv["means2D"], lv["opacities"],
+        scales=lv["scales"], rotations=lv["rotations"], shs=lv["shs"], extra=lv["extra"], bg=bg)
+    color = out["color"].double().cpu()
+    # fp64 has no borderline pixels of its own; a pixel differs visibly only where an fp32 decision flipped
+    diff = (color - col64.detach()).abs().amax(0)
+    clean = diff <= 2e-5
+    print(f"plumbing fp64: {int((~clean).sum())} of {clean.numel()} pixels beyond 2e-5 (max {float(diff.max()):.2e})")
+    assert float((~clean).float().mean()) <= MAX_FLAGGED
+    assert float((out["depth"].double().cpu() - dep64.detach()).abs()[clean].max()) <= 2e-5 * max(1.0, float(dep64.max()))
+    assert float((out["alpha"].double().cpu() - alp64.detach()).abs()[clean].max()) <= 2e-5
+    gen = torch.Generator().manual_seed(9)
+    m = clean.double()
+    gc = torch.randn(9, H, W, generator=gen, dtype=torch.float64) * m
+    gd = torch.randn(H, W, generator=gen, dtype=torch.float64) * m
+    ga = torch.randn(H, W, generator=gen, dtype=torch.float64) * m
+    ((col64 * gc).sum() + (dep64 * gd).sum() + (alp64 * ga).sum()).backward()
+    leaves = {k: c[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    leaves["means2D"] = torch.zeros(P, 3, device="cuda", requires_grad=True)
+    leaves["extra"] = c["ins_feat"].clone().requires_grad_(True)
+    args = {k: v for k, v in leaves.items() if k != "extra"}
+    res = GaussianRasterizer(rs)(extra_feats=leaves["extra"], **args)
+    f = lambda a: a.float().cuda()  # noqa: E731
+    ((res[0] * f(gc[:3])).sum() + (res[4] * f(gc[3:])).sum() + (res[2][0] * f(gd)).sum() + (res[3][0] * f(ga)).sum()).backward()
+    for k, leaf in leaves.items():
+        want = lv[k].grad.numpy()
+        got = leaf.grad.cpu().numpy().reshape(want.shape)
+        if k == "means2D":
+            want = want.copy()
+            want[:, 2] = 0
+        frac, worst = grad_violations(got, want, GRAD_RTOL)
+        print(f"plumbing fp64 dL/d{k}: violating fraction {frac:.2e}, worst |diff|/tol {worst:.3f}")
+        assert frac == 0.0, (k, frac, worst)
