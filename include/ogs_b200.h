@@ -29,6 +29,10 @@
  *   ogs_kmeans_finalize          scene/kmeans_quantize.py:208-214 (centres = sums / counts, reset)
  *   ogs_kmeans_gather_st         scene/kmeans_quantize.py:273-275 (gather centres, straight-through)
  *   ogs_kmeans_count             scene/kmeans_quantize.py:89-144 (equalize_cluster_size member counts)
+ *   ogs_kmeans_assign_segmented, ogs_kmeans_finalize_fixed
+ *                                scene/kmeans_quantize.py:196-214,233-238 (leaf mode) for all coarse clusters at once
+ *   ogs_peer_*                   no reference counterpart (the reference is single-GPU): the all-reduce of the
+ *                                sharded k-means' centroid partials over NVLink peer memory
  *   ogs_mask_pair_counts         utils/opengs_utlis.py:90-123 (calculate_iou)
  *   ogs_splat_footprint_votes    utils/sam_refinement_utils.py:902-913 (get_splat_id_and_weights, batched)
  *   ogs_adam_step                train.py:609 (gaussians.optimizer.step(), the torch.optim.Adam of
@@ -49,7 +53,7 @@
 extern "C" {
 #endif
 
-#define OGS_ABI_VERSION 2
+#define OGS_ABI_VERSION 3
 #define OGS_TILE 16
 #define OGS_MAX_CHANNELS 16 /* 3 colour channels + n_extra <= OGS_MAX_CHANNELS */
 
@@ -192,6 +196,42 @@ int ogs_kmeans_gather_st(int64_t N, const float* feat, int32_t Dout, const float
 
 /* Per-cluster member counts: counts_out int64 [k] (zeroed by the call). */
 int ogs_kmeans_count(int64_t N, const int64_t* ids, int32_t k, int64_t* counts_out, void* stream);
+
+/* ---- fine level of the two-level codebook, ALL coarse clusters in one launch ----
+ * Replaces k1 calls of the reference's leaf mode (scene/kmeans_quantize.py:196-206 assign + :82-87,:202-205
+ * centroid sums, :233-238 reassign; one coarse cluster per call, driven by train.py:322-332).
+ * Point i (a [N,D] floats) with coarse id c = coarse_ids[i] in [0, k1) competes among the rows
+ * [c*k2, c*k2 + seg_k[c]) of seg_centers [>= k1*k2, D] (= leaf_centers; seg_k = iLeafSubNum, int32 [k1]) and gets
+ * ids_out[i] = c*k2 + argmin (same fmaf chain and tie rule as ogs_kmeans_assign); points whose coarse id is outside
+ * [0, k1) or whose cluster has seg_k <= 0 keep ids_out[i] untouched.
+ * acc (int64 [k1*k2, D+1], ADDED to, caller zeroes; NULL = pure reassign): exact fixed-point centroid sums and
+ * counts: acc[r][d] += llrint(x_d * 2^fix_bits), acc[r][D] += 1.  Integer sums do not depend on the summation
+ * order, the grid or the sharding; the caller picks fix_bits so that max|x| * 2^fix_bits < 2^32 and
+ * N * max|x| * 2^fix_bits < 2^63. */
+int ogs_kmeans_assign_segmented(int64_t N, const float* a, int32_t D, const int64_t* coarse_ids,
+                                const float* seg_centers, const int32_t* seg_k, int32_t k1, int32_t k2,
+                                int64_t* ids_out, int64_t* acc, int32_t fix_bits, void* stream);
+
+/* One Lloyd update of all rows from the exact sums with the reference's count bookkeeping
+ * (scene/kmeans_quantize.py:167,186,208-214): counts_state[r] += acc[r][D] + eps_add;
+ * centers[r, :] = (acc[r, :D] * 2^-fix_bits) / counts_state[r]; counts_state[r] = 0 where it exceeds 0.1. */
+int ogs_kmeans_finalize_fixed(int32_t rows, int32_t D, const int64_t* acc, int32_t fix_bits, float eps_add,
+                              float* counts_state, float* centers, void* stream);
+
+/* ---- small all-reduce over NVLink peer memory in ONE kernel (the [k, D+1] centroid partials of
+ * the sharded k-means; the reference has no distributed code) ----
+ * One communicator per process (one process per GPU, same node).  create: allocates this rank's inbox (2 parities x
+ * world slots of max_bytes) and returns its 64-byte cudaIpc handle in handle_out; the caller exchanges the handles
+ * (e.g. torch.distributed.all_gather_object) and passes all `world` of them, in rank order, to connect.
+ * allreduce: in-place sum of buf [n] (dtype 0 = float32, 1 = int64) over the ranks, enqueued on `stream`; every rank
+ * adds the contributions in rank order, so all ranks end with bit-identical results.  All ranks must issue the same
+ * sequence of calls.  error: 1 if a call gave up waiting for a peer (~20 s) since the last check. */
+typedef struct ogs_peer_comm ogs_peer_comm;
+int ogs_peer_comm_create(int32_t rank, int32_t world, int64_t max_bytes, ogs_peer_comm** out, void* handle_out);
+int ogs_peer_comm_connect(ogs_peer_comm* comm, const void* all_handles);
+int ogs_peer_allreduce(ogs_peer_comm* comm, void* buf, int64_t n, int32_t dtype, void* stream);
+int ogs_peer_comm_error(ogs_peer_comm* comm, void* stream);
+int ogs_peer_comm_destroy(ogs_peer_comm* comm);
 
 /* ---- per-mask feature statistics and the Stage-1 cohesion loss ----
  * Replace utils/opengs_utlis.py::mask_feature_mean (:240-283) and train.py::cohesion_loss (:102-121).

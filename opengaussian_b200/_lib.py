@@ -79,6 +79,14 @@ EXPORTS = {
     "ogs_kmeans_finalize": (C.c_int, [C.c_int32, C.c_int32, _fp, _fp, C.c_float, _fp, C.c_void_p]),
     "ogs_kmeans_gather_st": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_void_p]),
     "ogs_kmeans_count": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, C.c_void_p]),
+    "ogs_kmeans_assign_segmented": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp,
+                                              C.c_int32, C.c_void_p]),
+    "ogs_kmeans_finalize_fixed": (C.c_int, [C.c_int32, C.c_int32, _fp, C.c_int32, C.c_float, _fp, _fp, C.c_void_p]),
+    "ogs_peer_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "ogs_peer_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ogs_peer_allreduce": (C.c_int, [C.c_void_p, _fp, C.c_int64, C.c_int32, C.c_void_p]),
+    "ogs_peer_comm_error": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ogs_peer_comm_destroy": (C.c_int, [C.c_void_p]),
     "ogs_mask_mean_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "ogs_mask_mean_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "ogs_mask_var_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
@@ -110,7 +118,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ogs_abi_version() != 2:
+        if L.ogs_abi_version() != 3:
             raise OgsError("libogs_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

@@ -24,6 +24,8 @@ UNITS = {
     "blend_fwd.cu": [],
     "blend_bwd.cu": [],
     "preprocess_bwd.cu": [],
+    "kmeans_seg.cu": [],
+    "peer.cu": [],
     "kmeans.cu": [],
     "mask_stats.cu": [],
     "mask_iou.cu": [],

@@ -469,6 +469,31 @@ int ogs_kmeans_count(int64_t N, const int64_t* ids, int32_t k, int64_t* counts_o
     return 0;
 }
 
+int ogs_kmeans_assign_segmented(int64_t N, const float* a, int32_t D, const int64_t* coarse_ids, const float* seg_centers,
+                                const int32_t* seg_k, int32_t k1, int32_t k2, int64_t* ids_out, int64_t* acc,
+                                int32_t fix_bits, void* stream_) {
+    if (N < 0 || D < 1 || k1 < 1 || k2 < 1 || !seg_centers || !seg_k || fix_bits < 0 || fix_bits > 40 ||
+        (N > 0 && (!a || !coarse_ids || !ids_out))) {
+        set_error("kmeans_assign_segmented: bad arguments");
+        return -1;
+    }
+    if (N == 0) return 0;
+    int rc = ensure_pool();
+    if (rc) return rc;
+    ProfScope ps(PF_KMEANS_ASSIGN, (cudaStream_t)stream_);
+    return launch_kmeans_assign_segmented(N, a, D, coarse_ids, seg_centers, seg_k, k1, k2, ids_out, acc, fix_bits,
+                                          (cudaStream_t)stream_);
+}
+
+int ogs_kmeans_finalize_fixed(int32_t rows, int32_t D, const int64_t* acc, int32_t fix_bits, float eps_add,
+                              float* counts_state, float* centers, void* stream_) {
+    if (rows < 0 || D < 1 || !acc || !counts_state || !centers || fix_bits < 0 || fix_bits > 40) {
+        set_error("kmeans_finalize_fixed: bad arguments");
+        return -1;
+    }
+    return launch_kmeans_seg_finalize(rows, D, acc, fix_bits, eps_add, counts_state, centers, (cudaStream_t)stream_);
+}
+
 #define OGS_MASK_ARGS_OK(what)                                                                          \
     if (M < 0 || HW < 0 || ((M > 0 || HW > 0) && !feat) || (M > 0 && HW > 0 && !masks)) {                \
         set_error(what ": bad arguments");                                                               \

@@ -105,12 +105,121 @@ def _coalesced_grads(params, offs=None, span=None) -> Optional[torch.Tensor]:
     return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, base, (span,))
 
 
-def shard_kmeans(codebook, group=None):
-    """Puts a Quantize_kMeans into sharded mode: its forward() then sees only this rank's points."""
+def shard_kmeans(codebook, group=None, peer_reduce: bool = False):
+    """Puts a Quantize_kMeans into sharded mode: its forward() then sees only this rank's points.
+    peer_reduce=True (CUDA, one node): the per-pass all-reduce of the centroid partials is done by the library's own
+    one-kernel reduction over NVLink peer memory (PeerReducer) instead of a torch.distributed call."""
     r, w = world(group)
     codebook.process_group = group
     codebook.distributed = w > 1
+    if peer_reduce and w > 1:
+        k1, k2 = codebook.num_clusters, codebook.leaf_num_clusters
+        codebook.reducer = PeerReducer(max(k1 * (codebook.vec_dim + 1) * 4, k1 * k2 * (codebook.leaf_vec_dim + 1) * 8) + 256,
+                                       group=group)
     return codebook
+
+
+class PeerReducer:
+    """In-place all-reduce(sum) of a small float32 / int64 CUDA tensor in ONE kernel over NVLink peer memory
+    (C ABI ogs_peer_*, csrc/peer.cu): every rank pushes its vector into every rank's inbox, signals, waits, and sums
+    the inbox in rank order (bit-identical results on all ranks).  ~5 us per call against ~45 us for a library
+    collective of a few KB -- what the sharded k-means needs once per Lloyd pass.  torch.distributed is
+    only used once, to exchange the 64-byte memory handles.  If peer memory cannot be mapped (`kind == "nccl"`)
+    the calls go to torch.distributed.all_reduce instead."""
+
+    def __init__(self, max_bytes: int, group=None, device=None):
+        import ctypes as C
+        from . import _lib
+        self.group = group
+        self.rank, self.world = world(group)
+        self.kind = "nccl"
+        self.comm = None
+        self._C, self._lib = C, _lib
+        if self.world == 1:
+            self.kind = "single"
+            return
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        L = _lib.lib()
+        handle = (C.c_char * 64)()
+        comm = C.c_void_p()
+        ok = 1
+        with torch.cuda.device(self.device):
+            rc = L.ogs_peer_comm_create(self.rank, self.world, int(max_bytes), C.byref(comm), handle)
+        if rc != 0:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, bytes(handle)), group=group)
+        if all(h[0] for h in handles):
+            blob = b"".join(h[1] for h in handles)
+            with torch.cuda.device(self.device):
+                rc = L.ogs_peer_comm_connect(comm, blob)
+            ok = 1 if rc == 0 else 0
+        else:
+            ok = 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=group)
+        if all(flags):
+            self.comm, self.kind = comm, "nvlink peer memory, one kernel (ogs_peer_allreduce)"
+        elif comm:
+            L.ogs_peer_comm_destroy(comm)
+
+    def all_reduce(self, t: torch.Tensor):
+        if self.world == 1:
+            return t
+        if self.comm is None:
+            dist.all_reduce(t, group=self.group)
+            return t
+        if not t.is_contiguous() or t.dtype not in (torch.float32, torch.int64):
+            raise self._lib.OgsError("PeerReducer.all_reduce needs a contiguous float32 or int64 tensor")
+        L = self._lib.lib()
+        stream = self._C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        with torch.cuda.device(t.device):
+            rc = L.ogs_peer_allreduce(self.comm, t.data_ptr(), t.numel(), 0 if t.dtype == torch.float32 else 1, stream)
+        self._lib.check(rc, "ogs_peer_allreduce")
+        return t
+
+    def check(self):
+        """Raises if a call timed out waiting for a peer (synchronises the current stream)."""
+        if self.comm is not None:
+            L = self._lib.lib()
+            stream = self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            with torch.cuda.device(self.device):
+                if L.ogs_peer_comm_error(self.comm, stream) != 0:
+                    raise self._lib.OgsError("ogs_peer_allreduce: a rank did not arrive within the time-out")
+
+    def close(self):
+        if self.comm is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)         # nobody unmaps while a peer may still push
+            self._lib.lib().ogs_peer_comm_destroy(self.comm)
+            self.comm = None
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[int]:
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers (first touch)
+    and the copy engine's reads stay on the GPU's own socket: with 8 ranks feeding ~25 GB/s each from one node the
+    cross-socket link is what limits the end-to-end step.  Best effort: returns the node, or None if the topology
+    cannot be read (then nothing changes)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def gather_ids(local_ids: torch.Tensor, group=None) -> torch.Tensor:
@@ -172,7 +281,7 @@ def _side_streams(device, n):
 
 def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.Tensor], group=None,
                           already_split: bool = False, streams: int = 1,
-                          fuse_accumulate: bool = True) -> Optional[torch.Tensor]:
+                          fuse_accumulate: bool = True, reduce: bool = True) -> Optional[torch.Tensor]:
     """One view-parallel step: this rank renders ITS views (`render_loss(view) -> scalar loss`),
     backpropagates, and the parameter gradients of all ranks are summed.  Equivalent to one
     process rendering every view and summing the losses.
@@ -226,8 +335,10 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
                 part = run(v)
             if part is not None:
                 total = part if total is None else total + part
-    allreduce_gradients(params, group)
     r, w = world(group)
+    if not reduce:          # measurement aid: the step without its collectives (bench.py's exposed-collective figure)
+        return total
+    allreduce_gradients(params, group)
     if w > 1:
         # rank-invariant: a rank without views this step (fewer views than ranks) contributes a zero loss
         if total is None:

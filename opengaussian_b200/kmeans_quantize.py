@@ -58,6 +58,43 @@ def kmeans_assign(a, b, scale_b, centers, select_ids=None, selected=-1, id_offse
     return ids_out
 
 
+def fixed_point_bits(n_points: int, max_abs: float) -> int:
+    """Largest fix_bits <= 30 with max_abs * 2^fix_bits < 2^31 (the kernel's 32-bit partial words) and
+    n_points * max_abs * 2^fix_bits < 2^62 (exact int64 centroid sums)."""
+    import math
+    e = max(0, math.floor(math.log2(float(max_abs))) + 1) if max_abs > 0 else 0
+    n = max(1, math.ceil(math.log2(max(int(n_points), 1) + 1)))
+    return int(max(0, min(30, 31 - e, 62 - n - e)))
+
+
+def kmeans_assign_segmented(a, coarse_ids, seg_centers, seg_k, k2, ids_out=None, acc=None, fix_bits=30):
+    """Fine level for ALL coarse clusters in one launch (C ABI ogs_kmeans_assign_segmented): point i competes among
+    rows [c*k2, c*k2 + seg_k[c]) of seg_centers, c = coarse_ids[i]; ids_out[i] = c*k2 + argmin.  acc (int64
+    [k1*k2*(D+1)], added to) receives the exact fixed-point centroid sums and counts."""
+    L = _lib.lib()
+    a = a.detach()
+    if a.dtype != torch.float32 or not a.is_contiguous():
+        a = a.float().contiguous()
+    if a.device.type != "cuda":
+        raise _lib.OgsError("k-means kernels need CUDA tensors (there is no CPU fallback)")
+    seg_centers = seg_centers.detach().float().contiguous()
+    seg_k = seg_k.to(device=a.device, dtype=torch.int32).contiguous()
+    coarse_ids = coarse_ids.to(torch.int64).contiguous()
+    N, D = a.shape
+    k1 = seg_k.numel()
+    if seg_centers.shape[0] < k1 * k2 or seg_centers.shape[1] != D:
+        raise _lib.OgsError(f"seg_centers must be [>= {k1 * k2}, {D}] (got {tuple(seg_centers.shape)})")
+    if ids_out is None:
+        ids_out = torch.full((N,), k1 * k2, dtype=torch.int64, device=a.device)
+    if acc is not None and (acc.dtype != torch.int64 or acc.numel() < k1 * k2 * (D + 1) or not acc.is_contiguous()):
+        raise _lib.OgsError("acc must be a contiguous int64 tensor of k1*k2*(D+1) elements")
+    with torch.cuda.device(a.device):
+        rc = L.ogs_kmeans_assign_segmented(N, _lib.ptr(a), D, _lib.ptr(coarse_ids), _lib.ptr(seg_centers), _lib.ptr(seg_k),
+                                           k1, int(k2), _lib.ptr(ids_out), _lib.ptr(acc), int(fix_bits), _stream(a.device))
+    _lib.check(rc, "ogs_kmeans_assign_segmented")
+    return ids_out
+
+
 class _GatherStraightThrough(torch.autograd.Function):
     """_ins_feat_q = _ins_feat - _ins_feat.detach() + centres[ids][:, :D]  (reference :273-275)."""
 
@@ -100,6 +137,7 @@ class Quantize_kMeans():
         # opengaussian_b200.dist.shard_kmeans(); None = single process (the reference's behaviour).
         self.process_group = None
         self.distributed = False
+        self.reducer = None                         # dist.PeerReducer (in-kernel NVLink all-reduce) or None = torch.distributed
         self.pos_centers = torch.empty(0)
 
     # ------------------------------------------------------------------ lazily materialised lists
@@ -236,7 +274,7 @@ class Quantize_kMeans():
                 # sums/counts rows beyond n_sub stay zero -> those centres become 0 / eps = 0 (:211)
                 kmeans_assign(a, b, scale_b, cur, select, selected, id_offset, ids, sums[:n_sub], cnt[:n_sub])
             if dist_on:
-                dist.all_reduce(buf, group=self.process_group)
+                self._all_reduce(buf)
             counts_state += cnt + n_eps * 1e-6
             new_centers = sums / counts_state.unsqueeze(-1)
             if mode == "root":
@@ -256,6 +294,69 @@ class Quantize_kMeans():
             self.leaf_cls_ids = ids
             self.nn_index = self.leaf_cls_ids
         self.equalize_cluster_size(mode=mode)
+
+    def _all_reduce(self, t):
+        if self.reducer is not None:
+            self.reducer.all_reduce(t)
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.process_group)
+
+    def cluster_assign_all_leaves(self, gaussian=None, feat=None):
+        """The fine level of EVERY coarse cluster in one go: equivalent to
+        ``for c in range(k1): self.forward(gaussian, it, assign=True, mode="leaf", selected_leaf=c)`` of the
+        reference (scene/kmeans_quantize.py:196-214,233-238 per call; train.py:322-332 drives one cluster per
+        training iteration), because the per-cluster Lloyd iterations never read each other's state.  One segmented
+        launch per Lloyd pass over all N points (C ABI ogs_kmeans_assign_segmented) instead of k1 x (iters + 1)
+        passes that each re-read all N coarse ids; exact integer centroid sums, one [k1*k2, D+1] all-reduce per
+        pass when sharded.  Needs ``cls_ids`` (coarse ids) and ``iLeafSubNum``; initialises ``leaf_centers`` the way
+        the reference does when they are empty."""
+        a = (gaussian._ins_feat if feat is None else feat).detach()
+        if a.dtype != torch.float32 or not a.is_contiguous():
+            a = a.float().contiguous()
+        dev, N, D = a.device, a.shape[0], a.shape[1]
+        k1, k2 = self.num_clusters, self.leaf_num_clusters
+        rows = k1 * k2
+        if len(self.leaf_centers) == 0:
+            self.leaf_centers = a[torch.randperm(N)[:rows + 1].to(dev)].float()
+            if self.distributed:
+                import torch.distributed as dist
+                dist.broadcast(self.leaf_centers, src=dist.get_global_rank(self.process_group, 0)
+                               if self.process_group is not None else 0, group=self.process_group)
+        if len(self.leaf_cls_ids) != N:
+            self.leaf_cls_ids = torch.ones(N, device=dev).to(torch.int64) * rows
+        self.leaf_centers = self.leaf_centers.detach().float().contiguous().to(dev)
+        seg_k = torch.as_tensor(self.iLeafSubNum).to(device=dev, dtype=torch.int32).contiguous()
+        # exact sums need a bound on |x|: one host read per call (not per pass)
+        stats = torch.stack([a.abs().max() if N > 0 else a.new_zeros(()), a.new_tensor(float(N))])
+        if self.distributed:
+            import torch.distributed as dist
+            mx = stats[:1].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.process_group)
+            nn = stats[1:].clone()
+            dist.all_reduce(nn, group=self.process_group)
+            stats = torch.cat([mx, nn])
+        max_abs, n_glob = (float(v) for v in stats.tolist())
+        fix = fixed_point_bits(int(n_glob), max_abs)
+        L = _lib.lib()
+        acc = torch.zeros(rows * (D + 1), dtype=torch.int64, device=dev)
+        counts_state = torch.full((rows,), 1e-6, dtype=torch.float32, device=dev)
+        ids = self.leaf_cls_ids
+        for _ in range(self.num_kmeans_iters):
+            acc.zero_()
+            kmeans_assign_segmented(a, self.cls_ids, self.leaf_centers, seg_k, k2, ids, acc, fix)
+            if self.distributed:
+                self._all_reduce(acc)
+            with torch.cuda.device(dev):
+                rc = L.ogs_kmeans_finalize_fixed(rows, D, _lib.ptr(acc), fix, 1e-6, _lib.ptr(counts_state),
+                                                 _lib.ptr(self.leaf_centers), _stream(dev))
+            _lib.check(rc, "ogs_kmeans_finalize_fixed")
+        kmeans_assign_segmented(a, self.cls_ids, self.leaf_centers, seg_k, k2, ids, None, fix)
+        self.leaf_cls_ids = ids
+        self.nn_index = ids
+        self.equalize_cluster_size(mode="leaf")
+        if gaussian is not None:
+            gaussian._ins_feat_q = _GatherStraightThrough.apply(gaussian._ins_feat, self.leaf_centers, self.nn_index)
 
     def rescale(self, feat, scale=None):
         if scale is None:

@@ -87,3 +87,31 @@ def cluster_assign_leaf(feat, cls_ids, leaf_centers0, leaf_cls_ids0, selected, n
         counts_state[counts_state > 0.1] = 0.0
     assign(feat, None, 1.0, leaf_centers[start:start + n_sub], cls_ids, selected, start, ids)
     return leaf_centers, ids
+
+
+def assign_segmented(a, coarse_ids, seg_centers, seg_k, k2, ids_out=None):
+    """All coarse clusters' leaf assigns (scene/kmeans_quantize.py:196-206 run for every idx_c): k1 calls of the
+    per-cluster oracle, each restricted to its own points and its own centre block."""
+    a = np.ascontiguousarray(a, np.float32)
+    k1 = len(seg_k)
+    if ids_out is None:
+        ids_out = np.full(a.shape[0], k1 * k2, np.int64)
+    for c in range(k1):
+        n = int(min(max(int(seg_k[c]), 0), k2))
+        if n > 0:
+            assign(a, None, 1.0, seg_centers[c * k2:c * k2 + n], coarse_ids, c, c * k2, ids_out)
+    return ids_out
+
+
+def accumulate_fixed(a, ids, rows, fix_bits, valid):
+    """Exact fixed-point centroid sums and counts: int64 [rows, D+1] with acc[r, d] = sum rint(x_d * 2^fix_bits),
+    acc[r, D] = member count, over the points flagged `valid`."""
+    a = np.ascontiguousarray(a, np.float32)
+    D = a.shape[1]
+    q = np.rint(a.astype(np.float64) * float(2 ** fix_bits)).astype(np.int64)
+    acc = np.zeros((rows, D + 1), np.int64)
+    sel = np.flatnonzero(valid)
+    for d in range(D):
+        np.add.at(acc[:, d], ids[sel], q[sel, d])
+    np.add.at(acc[:, D], ids[sel], 1)
+    return acc

@@ -154,3 +154,102 @@ def test_full_size_properties():
                           rtol=1e-4, atol=1e-1)
     # idempotence: same centres -> same ids
     assert torch.equal(kmeans_assign(a, b, 0.5, centers), ids)
+
+
+@pytest.mark.parametrize("N,D,k1,k2", [(200_003, 6, 8, 5), (1, 6, 3, 2), (50_000, 3, 64, 10), (4099, 5, 2, 7)])
+def test_segmented_assign_bit_exact_and_exact_sums(N, D, k1, k2):
+    """ogs_kmeans_assign_segmented: ids bit-exact against k1 per-cluster calls of the oracle (ragged seg_k incl. 0,
+    coarse ids outside [0, k1) untouched); the fixed-point centroid sums are EXACT integers."""
+    from opengaussian_b200.kmeans_quantize import kmeans_assign_segmented
+    rs = np.random.RandomState(N % 89)
+    a = (rs.rand(N, D).astype(np.float32) * 2 - 1)
+    coarse = rs.randint(-1, k1 + 1, size=N).astype(np.int64)          # -1 and k1 are "not mine"
+    seg_k = rs.randint(0, k2 + 1, size=k1).astype(np.int32)
+    seg_k[0] = k2
+    if k1 > 2:
+        seg_k[1] = 0
+    centers = rs.rand(k1 * k2 + 1, D).astype(np.float32) * 2 - 1
+    if k2 > 2:
+        centers[1] = centers[0]                                        # tie: lowest index wins
+    want = okm.assign_segmented(a, coarse, centers, seg_k, k2)
+    fix = 30
+    acc = torch.zeros(k1 * k2 * (D + 1), dtype=torch.int64, device="cuda")
+    ids0 = torch.full((N,), k1 * k2, dtype=torch.int64, device="cuda")
+    ids = kmeans_assign_segmented(torch.from_numpy(a).cuda(), torch.from_numpy(coarse).cuda(), torch.from_numpy(centers).cuda(),
+                                  torch.from_numpy(seg_k), k2, ids0, acc, fix)
+    assert np.array_equal(ids.cpu().numpy(), want)
+    valid = want != k1 * k2
+    assert valid.any() or N < 10
+    wacc = okm.accumulate_fixed(a, want, k1 * k2, fix, valid)
+    assert np.array_equal(acc.cpu().numpy().reshape(k1 * k2, D + 1), wacc)
+    # pure reassign (acc = NULL) gives the same ids
+    assert torch.equal(kmeans_assign_segmented(torch.from_numpy(a).cuda(), torch.from_numpy(coarse).cuda(),
+                                               torch.from_numpy(centers).cuda(), torch.from_numpy(seg_k), k2,
+                                               torch.full((N,), k1 * k2, dtype=torch.int64, device="cuda")), ids)
+
+
+def test_all_leaves_in_one_go_equals_per_cluster_calls():
+    """Quantize_kMeans.cluster_assign_all_leaves == the reference's per-cluster leaf calls for every coarse cluster
+    (scene/kmeans_quantize.py:196-214,233-238), on the golden scene: same ids away from near-ties, same centres."""
+    from opengaussian_b200.kmeans_quantize import Quantize_kMeans
+    gold = np.load(GOLD)
+    (ins_feat, xyz), (N, k1, k2, iters, pw) = _golden_inputs("root_25k")
+    sub = torch.full((k1,), k2, dtype=torch.int64)
+    sub[7] = 4
+    sub[2] = 1
+    qs = []
+    for all_at_once in (False, True):
+        g = _G()
+        g._ins_feat = torch.from_numpy(ins_feat).cuda().requires_grad_(True)
+        g._xyz = torch.from_numpy(xyz).cuda()
+        q = Quantize_kMeans(num_clusters=k1, num_leaf_clusters=k2, num_iters=iters, dim=9)
+        q.cls_ids = torch.from_numpy(gold["root_25k/cls_ids"].astype(np.int64)).cuda()
+        q.leaf_centers = torch.from_numpy(ins_feat[:k1 * k2 + 1].copy()).cuda()
+        q.leaf_cls_ids = torch.ones(N, device="cuda").to(torch.int64) * k1 * k2
+        q.iLeafSubNum = sub
+        if all_at_once:
+            q.cluster_assign_all_leaves(g)
+        else:
+            for c in range(k1):
+                q.forward(g, 1, assign=True, mode="leaf", selected_leaf=c)
+        qs.append((q, g))
+    (q0, g0), (q1, g1) = qs
+    a, b = q0.leaf_cls_ids.cpu().numpy(), q1.leaf_cls_ids.cpu().numpy()
+    assert (a != b).mean() <= 1e-4
+    assert a.max() < k1 * k2                                              # every point got a fine id
+    assert np.allclose(q0.leaf_centers.cpu().numpy()[:k1 * k2], q1.leaf_centers.cpu().numpy()[:k1 * k2], rtol=1e-4, atol=1e-5)
+    assert np.all(q1.leaf_centers.cpu().numpy()[7 * k2 + 4:8 * k2] == 0.0)  # rows beyond iLeafSubNum are rewritten to 0 (:211)
+    for sel in (3, 7):                                                    # the two clusters the golden file holds
+        m = gold["root_25k/cls_ids"] == sel
+        assert (b[m] != gold["root_25k/leaf_cls_ids"].astype(np.int64)[m]).mean() <= 2e-3
+    assert torch.allclose(g1._ins_feat_q, q1.leaf_centers[q1.leaf_cls_ids])
+    # determinism: exact integer sums -> the same centres bit for bit on a second run
+    q2, g2 = Quantize_kMeans(num_clusters=k1, num_leaf_clusters=k2, num_iters=iters, dim=9), _G()
+    g2._ins_feat = g1._ins_feat
+    q2.cls_ids, q2.iLeafSubNum = q1.cls_ids, sub
+    q2.leaf_centers = torch.from_numpy(ins_feat[:k1 * k2 + 1].copy()).cuda()
+    q2.cluster_assign_all_leaves(g2)
+    assert torch.equal(q2.leaf_centers, q1.leaf_centers) and torch.equal(q2.leaf_cls_ids, q1.leaf_cls_ids)
+
+
+def test_segmented_full_size_properties():
+    """BASELINE config 5's fine level at 5 M points (k1 = 64, k2 = 10, D = 6): every id lies in its coarse cluster's
+    block and is the nearest row of that block; counts add up to N."""
+    from opengaussian_b200.kmeans_quantize import kmeans_assign_segmented
+    N, k1, k2 = 5_000_000, 64, 10
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.rand(N, 6, device="cuda", generator=gen)
+    coarse = torch.randint(0, k1, (N,), device="cuda", generator=gen)
+    centers = a[:k1 * k2 + 1].contiguous()
+    acc = torch.zeros(k1 * k2 * 7, dtype=torch.int64, device="cuda")
+    ids = kmeans_assign_segmented(a, coarse, centers, torch.full((k1,), k2, dtype=torch.int32), k2, None, acc, 30)
+    assert torch.equal(ids // k2, coarse)
+    accv = acc.view(k1 * k2, 7)
+    assert int(accv[:, 6].sum()) == N and torch.equal(torch.bincount(ids, minlength=k1 * k2), accv[:, 6])
+    idx = torch.randint(0, N, (100_000,), device="cuda", generator=gen)
+    blk = centers[:k1 * k2].view(k1, k2, 6)[coarse[idx]].double()         # [n, k2, 6]
+    d = (blk - a[idx].double()[:, None, :]).norm(dim=2)
+    mine = d.gather(1, (ids[idx] % k2)[:, None])[:, 0]
+    assert float((mine - d.min(1).values).max()) <= 1e-5
+    want = torch.zeros(k1 * k2, 6, device="cuda", dtype=torch.float64).index_add_(0, ids, a.double())
+    assert torch.allclose(accv[:, :6].double() / 2 ** 30, want, rtol=0, atol=N * 2.0 ** -31)

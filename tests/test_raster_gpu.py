@@ -242,17 +242,24 @@ def test_argument_errors():
                                scales=c["scales"], rotations=c["rotations"])
     with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
         GaussianRasterizer(rs)(means3D=c["means3D"], means2D=c["means3D"], opacities=c["opacities"], shs=c["shs"])
-    # maximum size: the tile id is a 16-bit sort key, so at most 65535 tiles (4096 x 4096 pixels = 65536 tiles)
+    # maximum size: the tile id is a 16-bit sort key, so at most 65536 tiles (4096 x 4096 pixels exactly)
     from opengaussian_b200 import _lib
-    big = rs._replace(image_height=4096, image_width=4096)
+    big = rs._replace(image_height=4112, image_width=4096)
     with pytest.raises(_lib.OgsError, match="image too large"):
         GaussianRasterizer(big)(means3D=c["means3D"], means2D=c["means3D"], opacities=c["opacities"], shs=c["shs"],
                                 scales=c["scales"], rotations=c["rotations"])
-    # the largest supported image renders (4096 x 4080 = 65280 tiles)
-    ok = rs._replace(image_height=4080, image_width=4096)
+    # the largest supported image renders and matches a crop-consistent smaller render (tile id 65535 is a real tile)
+    ok = rs._replace(image_height=4096, image_width=4096)
     out = GaussianRasterizer(ok)(means3D=c["means3D"], means2D=c["means3D"], opacities=c["opacities"], shs=c["shs"],
                                  scales=c["scales"], rotations=c["rotations"])
-    assert out[0].shape == (3, 4080, 4096) and bool(torch.isfinite(out[0]).all())
+    assert out[0].shape == (3, 4096, 4096) and bool(torch.isfinite(out[0]).all())
+    from opengaussian_b200 import debug
+    st = debug.forward_with_state(ok._replace(debug=False), c["means3D"], c["opacities"], shs=c["shs"], scales=c["scales"],
+                                  rotations=c["rotations"])
+    assert st["N"] == int(st["tiles_touched"].long().sum()) and st["N"] > 0
+    lens = (st["ranges"][:, 1].long() - st["ranges"][:, 0].long())
+    assert st["ranges"].shape[0] == 65536 and int(lens.sum()) == st["N"]
+    del out, st
     # CPU tensors are refused (no CPU path)
     with pytest.raises(_lib.OgsError):
         GaussianRasterizer(rs)(means3D=gs["means3D"], means2D=gs["means3D"], opacities=gs["opacities"], shs=gs["shs"],
