@@ -205,3 +205,36 @@ def sam_like_masks(M: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
         h, w = int(torch.randint(8, H // 3, (1,), generator=g)), int(torch.randint(8, W // 3, (1,), generator=g))
         ids[y0:y0 + h, x0:x0 + w] = m
     return torch.stack([(ids == m) for m in range(M)])
+
+
+def blob_labels(gs, n_blobs: int, seed: int = 0) -> torch.Tensor:
+    """A spatial partition of the Gaussians into n_blobs Voronoi cells of randomly chosen Gaussians: [P] int64."""
+    g = torch.Generator().manual_seed(seed)
+    centres = gs["means3D"][torch.randperm(gs["means3D"].shape[0], generator=g)[:n_blobs]]
+    return torch.cdist(gs["means3D"], centres).argmin(1)
+
+
+def blob_view_masks(cam, pc, labels: torch.Tensor, n_blobs: int, min_pixels: int = 50) -> torch.Tensor:
+    """View-consistent synthetic "SAM" masks for a camera: [M,H,W] bool, mask m = pixels whose accumulated blending
+    weight is dominated by blob m (the blobs are rendered one-hot, 13 channels per pass, through the rasterizer);
+    masks smaller than min_pixels are dropped (get_SAM_mask_and_feat's filter_th, utils/opengs_utlis.py:125-182)."""
+    from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    dev = labels.device
+    H, W = cam.image_height, cam.image_width
+    rs = GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                       cam.world_view_transform, cam.full_proj_transform, 0, cam.camera_center, False, False)
+    rast = GaussianRasterizer(rs)
+    onehot = torch.nn.functional.one_hot(labels, n_blobs).float()
+    maps = []
+    with torch.no_grad():
+        for c0 in range(0, n_blobs, 13):
+            extra = onehot[:, c0:c0 + 13].contiguous()
+            out = rast(means3D=pc.get_xyz, means2D=torch.zeros_like(pc.get_xyz), opacities=pc.get_opacity,
+                       colors_precomp=torch.zeros(labels.shape[0], 3, device=dev), scales=pc.get_scaling,
+                       rotations=pc.get_rotation, extra_feats=extra)
+            maps.append(out[4])
+    votes = torch.cat(maps, 0)
+    ids = votes.argmax(0)
+    covered = votes.sum(0) > 0.5
+    masks = torch.stack([(ids == k) & covered for k in range(n_blobs)])
+    return masks[masks.flatten(1).sum(1) > min_pixels]

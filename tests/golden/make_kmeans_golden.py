@@ -36,6 +36,18 @@ def inputs(name):
     return ins_feat, xyz
 
 
+def equalize_inputs(mode):
+    """nn_index [40000] int64: cluster 2 has 15000 members, cluster 5 has 11000 (both above max_cnt_th = 10000),
+    cluster 6 is empty, the rest share the remainder; leaf mode spreads over 8*3+1 ids incl. the sentinel 24."""
+    rs = np.random.RandomState(3 if mode == "root" else 4)
+    k = 8 if mode == "root" else 25
+    big, second, empty = (2, 5, 6) if mode == "root" else (7, 24, 11)
+    others = [i for i in range(k) if i not in (big, second, empty)]
+    ids = np.concatenate([np.full(15000, big), np.full(11000, second), rs.choice(others, size=14000)])
+    rs.shuffle(ids)
+    return ids.astype(np.int64)
+
+
 def load_reference():
     torch.Tensor.cuda = lambda self, *a, **k: self
     for m in ("tqdm",):
@@ -82,6 +94,19 @@ def main():
             out[f"{name}/leaf_centers"] = q.leaf_centers.numpy().copy()
             out[f"{name}/leaf_cls_ids"] = q.leaf_cls_ids.numpy().astype(np.int16)
             out[f"{name}/leaf_ins_feat_q"] = g._ins_feat_q.detach().numpy()[:512].copy()
+    # equalize_cluster_size (:89-144) on crafted assignments: two clusters above the 10000-member threshold (their
+    # overflow goes to excl_cluster_ids), an empty cluster, and the leaf mode's k1*k2+1 rows with the sentinel id
+    for mode in ("root", "leaf"):
+        q = ref.Quantize_kMeans(num_clusters=8, num_leaf_clusters=3, num_iters=1, dim=9)
+        q.nn_index = torch.from_numpy(equalize_inputs(mode))
+        q.equalize_cluster_size(mode=mode)
+        out[f"equalize_{mode}/cluster_ids"] = q.cluster_ids.numpy().astype(np.int32)
+        out[f"equalize_{mode}/cluster_len"] = q.cluster_len.numpy().astype(np.int64)
+        out[f"equalize_{mode}/max_cnt"] = np.int64(int(q.max_cnt))
+        out[f"equalize_{mode}/excl_clusters"] = np.array([int(e) for e in q.excl_clusters], np.int64)
+        for i, e in enumerate(q.excl_cluster_ids):
+            out[f"equalize_{mode}/excl_cluster_ids/{i}"] = e.numpy().astype(np.int32)
+        assert q.n_excl_cls == 2 and (q.cls_ids if mode == "root" else q.leaf_cls_ids) is q.nn_index
     np.savez_compressed(os.path.join(HERE, "kmeans_golden.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, v.dtype)

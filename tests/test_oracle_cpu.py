@@ -317,3 +317,30 @@ def test_sam_footprint_host_functions_vs_reference_golden(name):
     lo = int(sam.min())
     assert sf.most_common_id_weighted(torch.from_numpy(sam), zero) == (lo if lo < 0 else 0)
     assert sf.most_common_id_weighted(torch.full((4, 5), 9), torch.zeros(4, 5, 1)) == 9
+
+
+@pytest.mark.parametrize("mode", ["root", "leaf"])
+def test_equalize_cluster_size_vs_reference_golden(mode):
+    """Quantize_kMeans.equalize_cluster_size products (cluster_ids, cluster_len, max_cnt, excl_clusters,
+    excl_cluster_ids) against what the reference's own method (scene/kmeans_quantize.py:89-144) produced on the same
+    assignments (tests/golden/make_kmeans_golden.py): two clusters above the 10000-member threshold, an empty
+    cluster, leaf mode with its k1*k2+1 rows.  Pure torch ops: runs on the CPU."""
+    import importlib.util
+    from opengaussian_b200.kmeans_quantize import Quantize_kMeans
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("mkg_eq", os.path.join(gdir, "make_kmeans_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    gold = np.load(os.path.join(gdir, "kmeans_golden.npz"))
+    q = Quantize_kMeans(num_clusters=8, num_leaf_clusters=3, num_iters=1, dim=9)
+    q.nn_index = torch.from_numpy(m.equalize_inputs(mode))
+    q.equalize_cluster_size(mode=mode)
+    assert (q.cls_ids if mode == "root" else q.leaf_cls_ids) is q.nn_index
+    assert int(q.max_cnt) == int(gold[f"equalize_{mode}/max_cnt"]) and q.n_excl_cls == 2
+    assert [int(e) for e in q.excl_clusters] == gold[f"equalize_{mode}/excl_clusters"].tolist()
+    assert q.cluster_ids.dtype == torch.long and q.cluster_len.dtype == torch.long
+    assert np.array_equal(q.cluster_ids.numpy(), gold[f"equalize_{mode}/cluster_ids"].astype(np.int64))
+    assert np.array_equal(q.cluster_len.numpy(), gold[f"equalize_{mode}/cluster_len"])
+    assert len(q.excl_cluster_ids) == 2
+    for i, e in enumerate(q.excl_cluster_ids):
+        assert np.array_equal(e.numpy(), gold[f"equalize_{mode}/excl_cluster_ids/{i}"].astype(np.int64))
