@@ -218,6 +218,31 @@ int ogs_kmeans_assign_segmented(int64_t N, const float* a, int32_t D, const int6
 int ogs_kmeans_finalize_fixed(int32_t rows, int32_t D, const int64_t* acc, int32_t fix_bits, float eps_add,
                               float* counts_state, float* centers, void* stream);
 
+/* ---- one whole Lloyd iteration in ONE launch (scene/kmeans_quantize.py:180-214 for the root mode, :196-214 for one
+ * leaf call): assign every point (ogs_kmeans_assign's arithmetic and tie rule), accumulate the centroid sums and
+ * counts, and -- in the LAST CTA to finish -- sum the per-CTA partials in a fixed order, all-reduce the [k, D+1] vector
+ * over the peers' memory when `comm` is given (points sharded over GPUs; ogs_peer_* below), and update the centres the
+ * way the reference does:  counts_state[j] += count_j + eps_add;  centers[j, :] = sum_j / counts_state[j];
+ * counts_state[j] = 0 where it exceeds 0.1, for j < k_out (rows in [k, k_out) have no members and become 0).
+ * centers [>= max(k, k_out), D] is read (rows < k) and updated IN PLACE; counts_state float [k_out].
+ * workspace: ogs_kmeans_lloyd_workspace_bytes(k, D) bytes of device memory, zero-initialised ONCE by the caller and
+ * reusable by consecutive calls on one stream.  An empty shard (N = 0) still takes part in the collective. */
+typedef struct ogs_peer_comm ogs_peer_comm;
+size_t ogs_kmeans_lloyd_workspace_bytes(int32_t k, int32_t D);
+int ogs_kmeans_lloyd_pass(int64_t N, const float* a, int32_t Da, const float* b, int32_t Db, float scale_b,
+                          float* centers, int32_t k, int32_t k_out, const int64_t* select_ids, int64_t selected,
+                          int64_t id_offset, int64_t* ids_out, float* counts_state, float eps_add,
+                          ogs_peer_comm* comm, void* workspace, void* stream);
+
+/* The same for the fine level of ALL coarse clusters (ogs_kmeans_assign_segmented + the integer all-reduce +
+ * ogs_kmeans_finalize_fixed in one launch): seg_centers [>= k1*k2, D] is read and updated in place, counts_state float
+ * [k1*k2]; workspace: ogs_kmeans_lloyd_segmented_workspace_bytes(k1, k2, D) bytes, zero-initialised once. */
+size_t ogs_kmeans_lloyd_segmented_workspace_bytes(int32_t k1, int32_t k2, int32_t D);
+int ogs_kmeans_lloyd_pass_segmented(int64_t N, const float* a, int32_t D, const int64_t* coarse_ids, float* seg_centers,
+                                    const int32_t* seg_k, int32_t k1, int32_t k2, int64_t* ids_out, int32_t fix_bits,
+                                    float* counts_state, float eps_add, ogs_peer_comm* comm, void* workspace,
+                                    void* stream);
+
 /* ---- small all-reduce over NVLink peer memory in ONE kernel (the [k, D+1] centroid partials of
  * the sharded k-means; the reference has no distributed code) ----
  * One communicator per process (one process per GPU, same node).  create: allocates this rank's inbox (2 parities x
@@ -226,7 +251,6 @@ int ogs_kmeans_finalize_fixed(int32_t rows, int32_t D, const int64_t* acc, int32
  * allreduce: in-place sum of buf [n] (dtype 0 = float32, 1 = int64) over the ranks, enqueued on `stream`; every rank
  * adds the contributions in rank order, so all ranks end with bit-identical results.  All ranks must issue the same
  * sequence of calls.  error: 1 if a call gave up waiting for a peer (~20 s) since the last check. */
-typedef struct ogs_peer_comm ogs_peer_comm;
 int ogs_peer_comm_create(int32_t rank, int32_t world, int64_t max_bytes, ogs_peer_comm** out, void* handle_out);
 int ogs_peer_comm_connect(ogs_peer_comm* comm, const void* all_handles);
 int ogs_peer_allreduce(ogs_peer_comm* comm, void* buf, int64_t n, int32_t dtype, void* stream);

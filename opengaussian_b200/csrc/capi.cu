@@ -485,6 +485,52 @@ int ogs_kmeans_assign_segmented(int64_t N, const float* a, int32_t D, const int6
                                           (cudaStream_t)stream_);
 }
 
+namespace ogs {
+int launch_kmeans_lloyd_pass(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b, float* centers, int k,
+                             int k_out, const int64_t* select_ids, int64_t selected, int64_t id_offset, int64_t* ids_out,
+                             float* counts_state, float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s);
+}
+
+namespace ogs {
+size_t kmeans_seg_lloyd_workspace_bytes(int k1, int k2, int D);
+int launch_kmeans_seg_lloyd_pass(int64_t N, const float* a, int D, const int64_t* coarse_ids, float* seg_centers,
+                                 const int32_t* seg_k, int k1, int k2, int64_t* ids_out, int fix_bits, float* counts_state,
+                                 float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s);
+}
+
+size_t ogs_kmeans_lloyd_segmented_workspace_bytes(int32_t k1, int32_t k2, int32_t D) {
+    return kmeans_seg_lloyd_workspace_bytes(k1, k2, D);
+}
+
+int ogs_kmeans_lloyd_pass_segmented(int64_t N, const float* a, int32_t D, const int64_t* coarse_ids, float* seg_centers,
+                                    const int32_t* seg_k, int32_t k1, int32_t k2, int64_t* ids_out, int32_t fix_bits,
+                                    float* counts_state, float eps_add, ogs_peer_comm* comm, void* workspace, void* stream_) {
+    if (N < 0 || D < 1 || k1 < 1 || k2 < 1 || !seg_centers || !seg_k || !counts_state || !workspace || fix_bits < 0 ||
+        fix_bits > 40 || (N > 0 && (!a || !coarse_ids || !ids_out))) {
+        set_error("kmeans_lloyd_pass_segmented: bad arguments");
+        return -1;
+    }
+    ProfScope ps(PF_KMEANS_ASSIGN, (cudaStream_t)stream_);
+    return launch_kmeans_seg_lloyd_pass(N, a, D, coarse_ids, seg_centers, seg_k, k1, k2, ids_out, fix_bits, counts_state,
+                                        eps_add, comm, workspace, (cudaStream_t)stream_);
+}
+
+size_t ogs_kmeans_lloyd_workspace_bytes(int32_t k, int32_t D) { return kmeans_lloyd_workspace_bytes(k, D); }
+
+int ogs_kmeans_lloyd_pass(int64_t N, const float* a, int32_t Da, const float* b, int32_t Db, float scale_b, float* centers,
+                          int32_t k, int32_t k_out, const int64_t* select_ids, int64_t selected, int64_t id_offset,
+                          int64_t* ids_out, float* counts_state, float eps_add, ogs_peer_comm* comm, void* workspace,
+                          void* stream_) {
+    if (N < 0 || Da < 0 || Db < 0 || Da + Db < 1 || k < 1 || k_out < k || !centers || !counts_state || !workspace ||
+        (N > 0 && (!a || !ids_out)) || (Db > 0 && N > 0 && !b)) {
+        set_error("kmeans_lloyd_pass: bad arguments");
+        return -1;
+    }
+    ProfScope ps(PF_KMEANS_ASSIGN, (cudaStream_t)stream_);
+    return launch_kmeans_lloyd_pass(N, a, Da, b, Db, scale_b, centers, k, k_out, select_ids, selected, id_offset, ids_out,
+                                    counts_state, eps_add, comm, workspace, (cudaStream_t)stream_);
+}
+
 int ogs_kmeans_finalize_fixed(int32_t rows, int32_t D, const int64_t* acc, int32_t fix_bits, float eps_add,
                               float* counts_state, float* centers, void* stream_) {
     if (rows < 0 || D < 1 || !acc || !counts_state || !centers || fix_bits < 0 || fix_bits > 40) {

@@ -284,6 +284,7 @@ int launch_kmeans_finalize(int k, int D, const float* sums, const float* counts,
 int launch_kmeans_gather_st(int64_t N, const float* feat, int Dout, const float* centers, int Dc, const int64_t* ids,
                             float* out, cudaStream_t s);
 int launch_kmeans_count(int64_t N, const int64_t* ids, int k, int64_t* counts, cudaStream_t s);
+size_t kmeans_lloyd_workspace_bytes(int k, int D);
 int launch_kmeans_assign_segmented(int64_t N, const float* a, int D, const int64_t* coarse_ids, const float* seg_centers,
                                    const int32_t* seg_k, int k1, int k2, int64_t* ids_out, int64_t* acc, int fix_bits,
                                    cudaStream_t s);

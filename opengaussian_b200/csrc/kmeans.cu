@@ -25,7 +25,10 @@
 // deterministic.  Block partials go to a [grid][k][D+1] scratch
 // that a second tiny kernel reduces in fixed order.
 // HBM-bound at the fine level (k <= 10), FP32-bound at the coarse level (k = 64, D = 9).
+#include <string.h>
+
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace ogs {
 
@@ -62,6 +65,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
+// Optional tail of the assign kernel: the LAST CTA to finish (atomic ticket) sums the per-CTA partials in CTA order,
+// all-reduces the [k][D+1] vector over the peers' memory (peer.cuh) when the points are sharded over GPUs, and applies
+// the reference's centre update -- so that one Lloyd iteration (scene/kmeans_quantize.py:180-214) is ONE launch:
+//   counts_state[j] += count_j + eps_add;  centre_j = sum_j / counts_state[j];  counts_state[j] = 0 where > 0.1
+// for j < k_out (rows at or beyond k have no members: sum 0 -> centre 0, as the reference's leaf mode rewrites them).
+struct KmTail {
+    int mode;                    // 0: off (partials are reduced by kmeans_reduce_partials_kernel)
+    unsigned int* ticket;        // zero at launch; the last CTA resets it
+    int has_peer;
+    PeerDev peer;
+    float* counts_state;         // [k_out]
+    float eps_add;
+    float* centers_out;          // [k_out][D]
+    int k_out;
+};
+
 // Persistent CTAs walk 1024-point tiles.  A tile's rows (a: [1024][Da], b: [1024][Db], contiguous in
 // global memory) are brought into shared memory by ONE cp.async.bulk per array, double-buffered on
 // two mbarriers, so the next tile streams in while the current one is scored; the ragged last tile
@@ -71,7 +90,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
     int64_t N, const float* __restrict__ a, int Da, const float* __restrict__ b, int Db, float scale_b,
     const float* __restrict__ centers, int k, const int64_t* __restrict__ select_ids, int64_t selected,
     int64_t id_offset, int64_t* __restrict__ ids_out, float* __restrict__ partials /* [grid][k][D+1] or NULL */,
-    int bulk_ok) {
+    int bulk_ok, KmTail tail) {
     constexpr int DP = (D + 1 + 3) & ~3;      // centre row [c_0..c_D-1, ||c||^2] padded to whole float4s
     constexpr int ROW = D + 1;
     extern __shared__ __align__(128) float smem[];
@@ -241,6 +260,37 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
             out[e] = s;
         }
     }
+    if (tail.mode && partials) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        float* vec = s_acc;                                  // [k][ROW]: the per-warp accumulators are done with
+        for (int e = threadIdx.x; e < k * ROW; e += KM_THREADS) {
+            float s = 0.f;
+            for (unsigned bk = 0; bk < gridDim.x; bk++) s += __ldcg(partials + (size_t)bk * k * ROW + e);
+            vec[e] = s;
+        }
+        __syncthreads();
+        bool ok = true;
+        if (tail.has_peer) ok = peer_allreduce_cta<float>(tail.peer, vec, k * ROW);
+        if (ok) {
+            for (int e = threadIdx.x; e < tail.k_out * D; e += KM_THREADS) {
+                const int j = e / D, d = e - j * D;
+                const float cnt = __fadd_rn(tail.counts_state[j], __fadd_rn(j < k ? vec[j * ROW + D] : 0.f, tail.eps_add));
+                tail.centers_out[e] = __fdiv_rn(j < k ? vec[j * ROW + d] : 0.f, cnt);
+            }
+            __syncthreads();
+            for (int j = threadIdx.x; j < tail.k_out; j += KM_THREADS) {
+                const float cnt = __fadd_rn(tail.counts_state[j], __fadd_rn(j < k ? vec[j * ROW + D] : 0.f, tail.eps_add));
+                tail.counts_state[j] = cnt > 0.1f ? 0.f : cnt;
+            }
+        }
+        if (threadIdx.x == 0) *tail.ticket = 0u;
+    }
 }
 
 __global__ void kmeans_reduce_partials_kernel(int nblocks, int k, int D, const float* __restrict__ partials,
@@ -277,8 +327,10 @@ static int launch_assign_d(int64_t N, const float* a, int Da, const float* b, in
     if (grid < 1) grid = 1;
     float* partials = nullptr;
     if (fuse) OGS_CUDA(cudaMallocAsync((void**)&partials, (size_t)grid * k * (D + 1) * sizeof(float), s));
+    KmTail tail;
+    memset(&tail, 0, sizeof tail);
     kmeans_assign_kernel<D><<<grid, KM_THREADS, smem, s>>>(N, a, Da, b, Db, scale_b, centers, k, select_ids, selected,
-                                                           id_offset, ids_out, partials, bulk_ok);
+                                                           id_offset, ids_out, partials, bulk_ok, tail);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && fuse) {
         const int tot = k * (D + 1);
@@ -302,6 +354,62 @@ int launch_kmeans_assign(int64_t N, const float* a, int Da, const float* b, int 
     }
 #undef OGS_KM_CASE
     set_error("kmeans_assign: unsupported point dimension %d (1..16)", D);
+    return -5;
+}
+
+// ---- one Lloyd iteration in one launch (assign + centroid sums + [peer all-reduce] + centre update) ----
+// workspace (caller-owned, zero-initialised once): [ticket: 256 B][partials: grid_max * k * (D+1) floats]
+size_t kmeans_lloyd_workspace_bytes(int k, int D) { return 256 + (size_t)OGS_NUM_SMS * 2 * k * (D + 1) * sizeof(float); }
+
+template <int D>
+static int launch_lloyd_d(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b, float* centers, int k,
+                          int k_out, const int64_t* select_ids, int64_t selected, int64_t id_offset, int64_t* ids_out,
+                          float* counts_state, float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s) {
+    size_t smem = (size_t)2 * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
+    smem += (size_t)KM_WARPS * k * (D + 1) * sizeof(float);
+    if (smem > 220 * 1024) { set_error("kmeans_lloyd_pass: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
+    if (comm && (size_t)k * (D + 1) * sizeof(float) > peer_comm_slot_bytes(comm)) {
+        set_error("kmeans_lloyd_pass: the communicator's slots are too small for k=%d D=%d", k, D);
+        return -1;
+    }
+    static std::atomic<size_t> attr[OGS_MAX_DEVICES];
+    std::atomic<size_t>& at = attr[current_device()];
+    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
+        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        at.store(smem, std::memory_order_relaxed);
+    }
+    const int bulk_ok = (((uintptr_t)a & 15) == 0 && (Db == 0 || ((uintptr_t)b & 15) == 0)) ? 1 : 0;
+    int64_t want = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
+    const int per_sm = smem > 110 * 1024 ? 1 : 2;
+    int grid = (int)(want < (int64_t)OGS_NUM_SMS * per_sm ? want : (int64_t)OGS_NUM_SMS * per_sm);
+    if (grid < 1) grid = 1;                          // an empty shard still takes part in the collective
+    KmTail tail;
+    memset(&tail, 0, sizeof tail);
+    tail.mode = 1;
+    tail.ticket = (unsigned int*)workspace;
+    tail.has_peer = comm ? 1 : 0;
+    if (comm) tail.peer = *peer_comm_dev(comm);
+    tail.counts_state = counts_state; tail.eps_add = eps_add; tail.centers_out = centers; tail.k_out = k_out;
+    float* partials = (float*)((char*)workspace + 256);
+    kmeans_assign_kernel<D><<<grid, KM_THREADS, smem, s>>>(N, a, Da, b, Db, scale_b, centers, k, select_ids, selected,
+                                                           id_offset, ids_out, partials, bulk_ok, tail);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kmeans_lloyd_pass");
+    return 0;
+}
+
+int launch_kmeans_lloyd_pass(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b, float* centers, int k,
+                             int k_out, const int64_t* select_ids, int64_t selected, int64_t id_offset, int64_t* ids_out,
+                             float* counts_state, float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s) {
+    const int D = Da + Db;
+#define OGS_KL_CASE(DD) case DD: return launch_lloyd_d<DD>(N, a, Da, b, Db, scale_b, centers, k, k_out, select_ids, selected, id_offset, ids_out, counts_state, eps_add, comm, workspace, s);
+    switch (D) {
+        OGS_KL_CASE(1) OGS_KL_CASE(2) OGS_KL_CASE(3) OGS_KL_CASE(4) OGS_KL_CASE(5) OGS_KL_CASE(6) OGS_KL_CASE(7)
+        OGS_KL_CASE(8) OGS_KL_CASE(9) OGS_KL_CASE(10) OGS_KL_CASE(11) OGS_KL_CASE(12) OGS_KL_CASE(13)
+        OGS_KL_CASE(14) OGS_KL_CASE(15) OGS_KL_CASE(16)
+    }
+#undef OGS_KL_CASE
+    set_error("kmeans_lloyd_pass: unsupported point dimension %d (1..16)", D);
     return -5;
 }
 

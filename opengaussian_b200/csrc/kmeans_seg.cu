@@ -17,7 +17,10 @@
 // associative, so the result does not depend on the order of the atomics, on the grid, or on how the points
 // are sharded over GPUs: a sharded run reproduces the single-GPU centres bit for bit after the (integer)
 // all-reduce.  The kernel is HBM-bound: 4 D + 8 (coarse id) + 8 (fine id) bytes per point.
+#include <string.h>
+
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace ogs {
 
@@ -32,20 +35,35 @@ namespace ogs {
 // points neither word can overflow provided |x| * 2^fix_bits < 2^32 (the caller's contract); the CTA then folds
 // the pairs into its own row of the int64 partial table in global memory (plain read-modify-write: the row is
 // private to the CTA) and clears them.
+// Optional tail (as in kmeans.cu): the LAST CTA to finish sums the per-CTA int64 partial tables, all-reduces the
+// [k1*k2][D+1] integers over the peers' memory when the points are sharded, and applies the reference's centre update
+// to every block -- one Lloyd pass of ALL coarse clusters' fine levels is then one launch.
+struct KsTail {
+    int mode;                    // 0: off (partials are ADDED to zeroed tables and reduced by kmeans_seg_reduce_kernel)
+    unsigned int* ticket;
+    int has_peer;
+    PeerDev peer;
+    float* counts_state;         // [k1*k2]
+    float eps_add, inv_scale;
+    float* centers_out;          // [k1*k2][D]
+};
+
 template <int D>
 __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
     int64_t N, const float* __restrict__ a, const int64_t* __restrict__ coarse_ids, const float* __restrict__ seg_centers,
     const int32_t* __restrict__ seg_k, int k1, int k2, int64_t* __restrict__ ids_out,
-    unsigned long long* __restrict__ partials /* [grid][k1*k2][D+1] (zeroed) or NULL */, float fix_scale, int vec2_ok) {
+    unsigned long long* __restrict__ partials /* [grid][k1*k2][D+1] (zeroed unless tail.mode) or NULL */, float fix_scale,
+    int vec2_ok, KsTail tail) {
     constexpr int ROW = D + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int rows = k1 * k2;
     const int k2p = k2 | 1;
     const int rows_p = k1 * k2p;
-    float* s_c = reinterpret_cast<float*>(smem_raw);                      // [D + 1][rows_p]  (last plane: ||c||^2)
-    int* s_k = reinterpret_cast<int*>(s_c + (size_t)ROW * rows_p);        // [k1]
-    unsigned int* s_lo = reinterpret_cast<unsigned int*>(s_k + k1);       // [rows][ROW]      (if partials)
+    // accumulators first (8-byte aligned: the fused tail re-reads the two 32-bit planes' storage as int64)
+    unsigned int* s_lo = reinterpret_cast<unsigned int*>(smem_raw);       // [rows][ROW]      (if partials)
     int* s_hi = reinterpret_cast<int*>(s_lo + (size_t)rows * ROW);        // [rows][ROW]
+    float* s_c = reinterpret_cast<float*>(smem_raw + (partials ? (size_t)rows * ROW * 8 : 0));   // [D + 1][rows_p] (last plane: ||c||^2)
+    int* s_k = reinterpret_cast<int*>(s_c + (size_t)ROW * rows_p);        // [k1]
 
     for (int r = threadIdx.x; r < rows; r += KS_THREADS) {
         const int c = r / k2, j = r - c * k2;
@@ -66,15 +84,18 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
         for (int e = threadIdx.x; e < rows * ROW; e += KS_THREADS) { s_lo[e] = 0u; s_hi[e] = 0; }
     __syncthreads();
 
+    bool first_flush = tail.mode != 0;        // fused mode: the table is not pre-zeroed, the first flush overwrites it
     auto flush = [&]() {
         __syncthreads();
         unsigned long long* out = partials + (size_t)blockIdx.x * rows * ROW;
         for (int e = threadIdx.x; e < rows * ROW; e += KS_THREADS) {
             const long long v = (long long)s_hi[e] * 65536ll + (long long)s_lo[e];
-            if (v != 0) out[e] += (unsigned long long)v;
+            if (first_flush) out[e] = (unsigned long long)v;
+            else if (v != 0) out[e] += (unsigned long long)v;
             s_lo[e] = 0u;
             s_hi[e] = 0;
         }
+        first_flush = false;
         __syncthreads();
     };
 
@@ -134,6 +155,34 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
         if (partials && since_flush >= KS_FLUSH_POINTS) { flush(); since_flush = 0; }
     }
     if (partials) flush();
+    if (tail.mode && partials) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        long long* vec = reinterpret_cast<long long*>(s_lo);        // [rows][ROW] int64: exactly the two 32-bit planes
+        for (int e = threadIdx.x; e < rows * ROW; e += KS_THREADS) {
+            long long sum = 0;
+            for (unsigned bk = 0; bk < gridDim.x; bk++) sum += (long long)__ldcg(partials + (size_t)bk * rows * ROW + e);
+            vec[e] = sum;
+        }
+        __syncthreads();
+        bool ok = true;
+        if (tail.has_peer) ok = peer_allreduce_cta<long long>(tail.peer, vec, rows * ROW);
+        if (ok) {
+            for (int r = threadIdx.x; r < rows; r += KS_THREADS) {
+                const float cnt = __fadd_rn(tail.counts_state[r], __fadd_rn((float)vec[r * ROW + D], tail.eps_add));
+#pragma unroll
+                for (int d = 0; d < D; d++)
+                    tail.centers_out[(size_t)r * D + d] = __fdiv_rn((float)((double)vec[r * ROW + d] * (double)tail.inv_scale), cnt);
+                tail.counts_state[r] = cnt > 0.1f ? 0.f : cnt;
+            }
+        }
+        if (threadIdx.x == 0) *tail.ticket = 0u;
+    }
 }
 
 __global__ void kmeans_seg_reduce_kernel(int nblocks, int n, const unsigned long long* __restrict__ partials,
@@ -143,6 +192,13 @@ __global__ void kmeans_seg_reduce_kernel(int nblocks, int n, const unsigned long
     unsigned long long s = 0ull;
     for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * n + e];
     acc[e] += s;
+}
+
+static int seg_grid(int64_t N, size_t smem) {
+    const int64_t want = (N + KS_THREADS * KS_PPT - 1) / (KS_THREADS * KS_PPT);
+    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3);
+    int grid = (int)(want < (int64_t)OGS_NUM_SMS * per_sm ? want : (int64_t)OGS_NUM_SMS * per_sm);
+    return grid < 1 ? 1 : grid;
 }
 
 template <int D>
@@ -157,18 +213,17 @@ static int launch_seg_d(int64_t N, const float* a, const int64_t* coarse_ids, co
         OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_seg_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         at.store(smem, std::memory_order_relaxed);
     }
-    const int64_t want = (N + KS_THREADS * KS_PPT - 1) / (KS_THREADS * KS_PPT);
-    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3);
-    int grid = (int)(want < (int64_t)OGS_NUM_SMS * per_sm ? want : (int64_t)OGS_NUM_SMS * per_sm);
-    if (grid < 1) grid = 1;
+    const int grid = seg_grid(N, smem);
     AsyncScratch partials(s);
     if (acc) {
         OGS_CUDA(partials.alloc((size_t)grid * rows * (D + 1) * 8));
         OGS_CUDA(cudaMemsetAsync(partials.p, 0, (size_t)grid * rows * (D + 1) * 8, s));
     }
+    KsTail tail;
+    memset(&tail, 0, sizeof tail);
     kmeans_assign_seg_kernel<D><<<grid, KS_THREADS, smem, s>>>(N, a, coarse_ids, seg_centers, seg_k, k1, k2, ids_out,
                                                                (unsigned long long*)partials.p, ldexpf(1.0f, fix_bits),
-                                                               (((uintptr_t)a & 7) == 0) ? 1 : 0);
+                                                               (((uintptr_t)a & 7) == 0) ? 1 : 0, tail);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && acc) {
         const int n = rows * (D + 1);
@@ -190,6 +245,58 @@ int launch_kmeans_assign_segmented(int64_t N, const float* a, int D, const int64
     }
 #undef OGS_KS_CASE
     set_error("kmeans_assign_segmented: unsupported point dimension %d (1..12)", D);
+    return -5;
+}
+
+// ---- one Lloyd pass of every coarse cluster's fine level in one launch ----
+size_t kmeans_seg_lloyd_workspace_bytes(int k1, int k2, int D) {
+    return 256 + (size_t)OGS_NUM_SMS * 3 * k1 * k2 * (D + 1) * 8;
+}
+
+template <int D>
+static int launch_seg_lloyd_d(int64_t N, const float* a, const int64_t* coarse_ids, float* seg_centers, const int32_t* seg_k,
+                              int k1, int k2, int64_t* ids_out, int fix_bits, float* counts_state, float eps_add,
+                              const ogs_peer_comm* comm, void* workspace, cudaStream_t s) {
+    const int rows = k1 * k2;
+    const size_t smem = (size_t)rows * (D + 1) * 8 + (size_t)k1 * (k2 | 1) * (D + 1) * 4 + (size_t)k1 * 4;
+    if (smem > 200 * 1024) { set_error("kmeans_lloyd_pass_segmented: k1*k2=%d D=%d needs %zu B shared memory", rows, D, smem); return -5; }
+    if (comm && (size_t)rows * (D + 1) * 8 > peer_comm_slot_bytes(comm)) {
+        set_error("kmeans_lloyd_pass_segmented: the communicator's slots are too small");
+        return -1;
+    }
+    static std::atomic<size_t> attr[OGS_MAX_DEVICES];
+    std::atomic<size_t>& at = attr[current_device()];
+    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
+        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_seg_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        at.store(smem, std::memory_order_relaxed);
+    }
+    const int grid = seg_grid(N, smem);
+    KsTail tail;
+    memset(&tail, 0, sizeof tail);
+    tail.mode = 1;
+    tail.ticket = (unsigned int*)workspace;
+    tail.has_peer = comm ? 1 : 0;
+    if (comm) tail.peer = *peer_comm_dev(comm);
+    tail.counts_state = counts_state; tail.eps_add = eps_add; tail.inv_scale = ldexpf(1.0f, -fix_bits);
+    tail.centers_out = seg_centers;
+    kmeans_assign_seg_kernel<D><<<grid, KS_THREADS, smem, s>>>(N, a, coarse_ids, seg_centers, seg_k, k1, k2, ids_out,
+                                                               (unsigned long long*)((char*)workspace + 256),
+                                                               ldexpf(1.0f, fix_bits), (((uintptr_t)a & 7) == 0) ? 1 : 0, tail);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kmeans_lloyd_pass_segmented");
+    return 0;
+}
+
+int launch_kmeans_seg_lloyd_pass(int64_t N, const float* a, int D, const int64_t* coarse_ids, float* seg_centers,
+                                 const int32_t* seg_k, int k1, int k2, int64_t* ids_out, int fix_bits, float* counts_state,
+                                 float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s) {
+#define OGS_KSL_CASE(DD) case DD: return launch_seg_lloyd_d<DD>(N, a, coarse_ids, seg_centers, seg_k, k1, k2, ids_out, fix_bits, counts_state, eps_add, comm, workspace, s);
+    switch (D) {
+        OGS_KSL_CASE(1) OGS_KSL_CASE(2) OGS_KSL_CASE(3) OGS_KSL_CASE(4) OGS_KSL_CASE(5) OGS_KSL_CASE(6) OGS_KSL_CASE(7)
+        OGS_KSL_CASE(8) OGS_KSL_CASE(9) OGS_KSL_CASE(10) OGS_KSL_CASE(11) OGS_KSL_CASE(12)
+    }
+#undef OGS_KSL_CASE
+    set_error("kmeans_lloyd_pass_segmented: unsupported point dimension %d (1..12)", D);
     return -5;
 }
 

@@ -15,64 +15,21 @@
 // Two parities suffice: a rank can start call s+1 only after it finished s, i.e. after every peer pushed s, i.e.
 // after every peer finished reading s-1 -- so a push into parity (s+1) % 2 never overwrites a slot still in use.
 // A rank that waits longer than ~20 s gives up and raises the comm's error word (the host reports it) instead of
-// hanging the GPU.
+// hanging the GPU.  The sequence number lives in device memory and is advanced by the kernel itself, so a captured
+// CUDA graph can replay the call.  The device side (peer.cuh) is also called by the LAST CTA of the k-means kernels:
+// assign + centroid partials + all-reduce + centre update of a Lloyd pass are then ONE launch.
 #include <string.h>
 
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace ogs {
 
-#define PEER_MAX_RANKS 16
 #define PEER_THREADS 512
-
-struct PeerPtrs { char* base[PEER_MAX_RANKS]; };
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // one CTA.  T = float or long long.
 template <typename T>
-__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(PeerPtrs pp, T* __restrict__ buf, int n,
-                                                                      unsigned long long seq, int rank, int world,
-                                                                      size_t slot_bytes, size_t flag_off, int* __restrict__ err) {
-    const int par = (int)(seq & 1ull);
-    __shared__ int s_fail;
-    if (threadIdx.x == 0) s_fail = 0;
-    // 1. push
-    for (int p = 0; p < world; p++) {
-        T* dst = reinterpret_cast<T*>(pp.base[p] + (size_t)(par * world + rank) * slot_bytes);
-        for (int i = threadIdx.x; i < n; i += PEER_THREADS) dst[i] = buf[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. signal, 3. wait
-    if (threadIdx.x < world) {
-        unsigned long long* remote = reinterpret_cast<unsigned long long*>(pp.base[threadIdx.x] + flag_off) + (par * world + rank);
-        st_release_sys(remote, seq);
-        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pp.base[rank] + flag_off) + (par * world + threadIdx.x);
-        const long long t0 = clock64();
-        while (ld_acquire_sys(mine) < seq) {
-            if (clock64() - t0 > 40000000000ll) { s_fail = 1; break; }     // ~20 s at 2 GHz
-        }
-    }
-    __syncthreads();
-    if (s_fail) {
-        if (threadIdx.x == 0) atomicExch(err, 1);
-        return;
-    }
-    // 4. reduce in rank order
-    const char* inbox = pp.base[rank] + (size_t)(par * world) * slot_bytes;
-    for (int i = threadIdx.x; i < n; i += PEER_THREADS) {
-        T s = 0;
-        for (int p = 0; p < world; p++) s += __ldcg(reinterpret_cast<const T*>(inbox + (size_t)p * slot_bytes) + i);
-        buf[i] = s;
-    }
+__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(PeerDev pd, T* __restrict__ buf, int n) {
+    peer_allreduce_cta<T>(pd, buf, n);
 }
 
 }  // namespace ogs
@@ -83,13 +40,17 @@ struct ogs_peer_comm {
     int rank, world, dev;
     size_t slot_bytes, flag_off, total;
     char* local;
-    PeerPtrs ptrs;
+    PeerDev dev_desc;     // passed by value to the kernels
     bool opened[PEER_MAX_RANKS];
     int* err_dev;
     int* err_host;        // pinned mirror read by ogs_peer_comm_error
-    unsigned long long seq;
     cudaIpcMemHandle_t handle;
 };
+
+namespace ogs {
+const PeerDev* peer_comm_dev(const ogs_peer_comm* c) { return c ? &c->dev_desc : nullptr; }
+size_t peer_comm_slot_bytes(const ogs_peer_comm* c) { return c ? c->slot_bytes : 0; }
+}
 
 extern "C" {
 
@@ -117,7 +78,11 @@ int ogs_peer_comm_create(int32_t rank, int32_t world, int64_t max_bytes, ogs_pee
     }
     *c->err_host = 0;
     c->err_dev = reinterpret_cast<int*>(c->local + c->total - 256);
-    c->ptrs.base[rank] = c->local;
+    c->dev_desc.base[rank] = c->local;
+    c->dev_desc.rank = rank; c->dev_desc.world = world;
+    c->dev_desc.slot_bytes = c->slot_bytes; c->dev_desc.flag_off = c->flag_off;
+    c->dev_desc.seq = reinterpret_cast<unsigned long long*>(c->local + c->total - 128);   // zeroed with the buffer
+    c->dev_desc.err = c->err_dev;
     memcpy(handle_out64, &c->handle, 64);
     OGS_CUDA(cudaDeviceSynchronize());
     *out = c;
@@ -134,7 +99,7 @@ int ogs_peer_comm_connect(ogs_peer_comm* c, const void* all_handles) {
         void* ptr = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer memory over NVLink unavailable?)");
-        c->ptrs.base[p] = (char*)ptr;
+        c->dev_desc.base[p] = (char*)ptr;
         c->opened[p] = true;
     }
     return 0;
@@ -147,13 +112,8 @@ int ogs_peer_allreduce(ogs_peer_comm* c, void* buf, int64_t n, int32_t dtype, vo
     if (bytes > c->slot_bytes) { set_error("peer_allreduce: %zu bytes exceed the slot size %zu", bytes, c->slot_bytes); return -1; }
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream_;
-    c->seq += 1;
-    if (dtype == 0)
-        peer_allreduce_kernel<float><<<1, PEER_THREADS, 0, s>>>(c->ptrs, (float*)buf, (int)n, c->seq, c->rank, c->world,
-                                                                 c->slot_bytes, c->flag_off, c->err_dev);
-    else
-        peer_allreduce_kernel<long long><<<1, PEER_THREADS, 0, s>>>(c->ptrs, (long long*)buf, (int)n, c->seq, c->rank, c->world,
-                                                                     c->slot_bytes, c->flag_off, c->err_dev);
+    if (dtype == 0) peer_allreduce_kernel<float><<<1, PEER_THREADS, 0, s>>>(c->dev_desc, (float*)buf, (int)n);
+    else peer_allreduce_kernel<long long><<<1, PEER_THREADS, 0, s>>>(c->dev_desc, (long long*)buf, (int)n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "peer_allreduce");
     return 0;
@@ -172,7 +132,7 @@ int ogs_peer_comm_destroy(ogs_peer_comm* c) {
     if (!c) return 0;
     cudaDeviceSynchronize();
     for (int p = 0; p < c->world; p++)
-        if (c->opened[p]) cudaIpcCloseMemHandle(c->ptrs.base[p]);
+        if (c->opened[p]) cudaIpcCloseMemHandle(c->dev_desc.base[p]);
     if (c->local) cudaFree(c->local);
     if (c->err_host) cudaFreeHost(c->err_host);
     delete c;

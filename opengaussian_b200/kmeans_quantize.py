@@ -261,27 +261,49 @@ class Quantize_kMeans():
         else:
             raise ValueError(mode)
 
-        buf = torch.zeros(k * D + k, dtype=torch.float32, device=dev)   # [sums | counts]: one collective
-        sums = buf[:k * D].view(k, D)
-        cnt = buf[k * D:]
-        counts_state = torch.full((k,), 1e-6, dtype=torch.float32, device=dev)
-        for _ in range(self.num_kmeans_iters):
-            buf.zero_()
+        comm = self.reducer.comm if (dist_on and self.reducer is not None) else None
+        if not dist_on or comm is not None:
+            # ONE launch per Lloyd iteration (C ABI ogs_kmeans_lloyd_pass): assign + centroid sums + [all-reduce over
+            # NVLink peer memory by the kernel's last CTA] + the reference's centre update, in place on `cur`
+            L = _lib.lib()
             if mode == "root":
-                kmeans_assign(a, b, scale_b, centers, None, -1, 0, ids, sums, cnt)
+                cur, k_in, k_out, eps_add = centers.clone(), k, k, n_eps * 1e-6
             else:
-                cur = self.leaf_centers[start_id:start_id + n_sub]
-                # sums/counts rows beyond n_sub stay zero -> those centres become 0 / eps = 0 (:211)
-                kmeans_assign(a, b, scale_b, cur, select, selected, id_offset, ids, sums[:n_sub], cnt[:n_sub])
-            if dist_on:
+                cur, k_in, k_out, eps_add = self.leaf_centers[start_id:start_id + k2], n_sub, k2, 1e-6
+            ws = torch.zeros((L.ogs_kmeans_lloyd_workspace_bytes(k_in, D) + 3) // 4, dtype=torch.int32, device=dev)
+            counts_state = torch.full((k_out,), 1e-6, dtype=torch.float32, device=dev)
+            a_c = a if (a.dtype == torch.float32 and a.is_contiguous()) else a.float().contiguous()
+            b_c = None if b is None else (b if (b.dtype == torch.float32 and b.is_contiguous()) else b.float().contiguous())
+            for _ in range(self.num_kmeans_iters):
+                with torch.cuda.device(dev):
+                    rc = L.ogs_kmeans_lloyd_pass(N, _lib.ptr(a_c), a_c.shape[1], _lib.ptr(b_c), 0 if b_c is None else b_c.shape[1],
+                                                 float(scale_b), _lib.ptr(cur), k_in, k_out, _lib.ptr(select), int(selected),
+                                                 int(id_offset), _lib.ptr(ids), _lib.ptr(counts_state), float(eps_add), comm,
+                                                 _lib.ptr(ws), _stream(dev))
+                _lib.check(rc, "ogs_kmeans_lloyd_pass")
+            if mode == "root":
+                centers = cur
+        else:
+            buf = torch.zeros(k * D + k, dtype=torch.float32, device=dev)   # [sums | counts]: one collective
+            sums = buf[:k * D].view(k, D)
+            cnt = buf[k * D:]
+            counts_state = torch.full((k,), 1e-6, dtype=torch.float32, device=dev)
+            for _ in range(self.num_kmeans_iters):
+                buf.zero_()
+                if mode == "root":
+                    kmeans_assign(a, b, scale_b, centers, None, -1, 0, ids, sums, cnt)
+                else:
+                    cur = self.leaf_centers[start_id:start_id + n_sub]
+                    # sums/counts rows beyond n_sub stay zero -> those centres become 0 / eps = 0 (:211)
+                    kmeans_assign(a, b, scale_b, cur, select, selected, id_offset, ids, sums[:n_sub], cnt[:n_sub])
                 self._all_reduce(buf)
-            counts_state += cnt + n_eps * 1e-6
-            new_centers = sums / counts_state.unsqueeze(-1)
-            if mode == "root":
-                centers = new_centers
-            else:
-                self.leaf_centers[start_id:start_id + k2] = new_centers
-            counts_state[counts_state > 0.1] = 0.
+                counts_state += cnt + n_eps * 1e-6
+                new_centers = sums / counts_state.unsqueeze(-1)
+                if mode == "root":
+                    centers = new_centers
+                else:
+                    self.leaf_centers[start_id:start_id + k2] = new_centers
+                counts_state[counts_state > 0.1] = 0.
 
         # final reassign with the new centres (:217-240)
         if mode == "root":
@@ -339,18 +361,30 @@ class Quantize_kMeans():
         max_abs, n_glob = (float(v) for v in stats.tolist())
         fix = fixed_point_bits(int(n_glob), max_abs)
         L = _lib.lib()
-        acc = torch.zeros(rows * (D + 1), dtype=torch.int64, device=dev)
         counts_state = torch.full((rows,), 1e-6, dtype=torch.float32, device=dev)
         ids = self.leaf_cls_ids
-        for _ in range(self.num_kmeans_iters):
-            acc.zero_()
-            kmeans_assign_segmented(a, self.cls_ids, self.leaf_centers, seg_k, k2, ids, acc, fix)
-            if self.distributed:
+        comm = self.reducer.comm if (self.distributed and self.reducer is not None) else None
+        coarse = self.cls_ids.to(torch.int64).contiguous()
+        if not self.distributed or comm is not None:
+            # ONE launch per Lloyd pass: segmented assign + exact sums + [integer all-reduce over NVLink peer memory by the
+            # kernel's last CTA] + centre update of every block, in place on leaf_centers
+            ws = torch.zeros((L.ogs_kmeans_lloyd_segmented_workspace_bytes(k1, k2, D) + 3) // 4, dtype=torch.int32, device=dev)
+            for _ in range(self.num_kmeans_iters):
+                with torch.cuda.device(dev):
+                    rc = L.ogs_kmeans_lloyd_pass_segmented(N, _lib.ptr(a), D, _lib.ptr(coarse), _lib.ptr(self.leaf_centers),
+                                                           _lib.ptr(seg_k), k1, k2, _lib.ptr(ids), fix, _lib.ptr(counts_state),
+                                                           1e-6, comm, _lib.ptr(ws), _stream(dev))
+                _lib.check(rc, "ogs_kmeans_lloyd_pass_segmented")
+        else:
+            acc = torch.zeros(rows * (D + 1), dtype=torch.int64, device=dev)
+            for _ in range(self.num_kmeans_iters):
+                acc.zero_()
+                kmeans_assign_segmented(a, coarse, self.leaf_centers, seg_k, k2, ids, acc, fix)
                 self._all_reduce(acc)
-            with torch.cuda.device(dev):
-                rc = L.ogs_kmeans_finalize_fixed(rows, D, _lib.ptr(acc), fix, 1e-6, _lib.ptr(counts_state),
-                                                 _lib.ptr(self.leaf_centers), _stream(dev))
-            _lib.check(rc, "ogs_kmeans_finalize_fixed")
+                with torch.cuda.device(dev):
+                    rc = L.ogs_kmeans_finalize_fixed(rows, D, _lib.ptr(acc), fix, 1e-6, _lib.ptr(counts_state),
+                                                     _lib.ptr(self.leaf_centers), _stream(dev))
+                _lib.check(rc, "ogs_kmeans_finalize_fixed")
         kmeans_assign_segmented(a, self.cls_ids, self.leaf_centers, seg_k, k2, ids, None, fix)
         self.leaf_cls_ids = ids
         self.nn_index = ids

@@ -253,3 +253,44 @@ def test_segmented_full_size_properties():
     assert float((mine - d.min(1).values).max()) <= 1e-5
     want = torch.zeros(k1 * k2, 6, device="cuda", dtype=torch.float64).index_add_(0, ids, a.double())
     assert torch.allclose(accv[:, :6].double() / 2 ** 30, want, rtol=0, atol=N * 2.0 ** -31)
+
+
+def test_fused_lloyd_pass_equals_separate_kernels():
+    """ogs_kmeans_lloyd_pass (assign + sums + centre update in ONE launch, the last CTA finishing the pass) against the
+    separate assign / finalize calls: same ids bit for bit, same centres up to the order of the float sums; the
+    workspace is reusable across consecutive passes without re-zeroing."""
+    import ctypes as C
+    from opengaussian_b200 import _lib
+    from opengaussian_b200.kmeans_quantize import kmeans_assign
+    L = _lib.lib()
+    rs = np.random.RandomState(3)
+    N, k = 300_001, 64
+    a = torch.from_numpy(rs.rand(N, 6).astype(np.float32)).cuda()
+    b = torch.from_numpy((rs.rand(N, 3).astype(np.float32) - 0.5) * 6).cuda()
+    c0 = torch.cat([a[:k], b[:k] * 0.5], 1).contiguous()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ws = torch.zeros((L.ogs_kmeans_lloyd_workspace_bytes(k, 9) + 3) // 4, dtype=torch.int32, device="cuda")
+    cen = c0.clone()
+    state = torch.full((k,), 1e-6, device="cuda")
+    ids = torch.empty(N, dtype=torch.int64, device="cuda")
+    ref_c, ref_state = c0.clone(), torch.full((k,), 1e-6, device="cuda")
+    for it in range(3):
+        # reference: separate kernels + the Python update of cluster_assign
+        sums, cnt = torch.zeros(k, 9, device="cuda"), torch.zeros(k, device="cuda")
+        ref_ids = kmeans_assign(a, b, 0.5, ref_c, sums=sums, counts=cnt)
+        ref_state += cnt + 31 * 1e-6
+        ref_c = sums / ref_state.unsqueeze(-1)
+        ref_state[ref_state > 0.1] = 0.
+        before = cen.clone()
+        rc = L.ogs_kmeans_lloyd_pass(N, a.data_ptr(), 6, b.data_ptr(), 3, 0.5, cen.data_ptr(), k, k, None, -1, 0, ids.data_ptr(),
+                                     state.data_ptr(), 31 * 1e-6, None, ws.data_ptr(), stream)
+        _lib.check(rc, "ogs_kmeans_lloyd_pass")
+        torch.cuda.synchronize()
+        assert int(ws[0]) == 0                                            # the ticket was reset by the last CTA
+        if it == 0:
+            assert torch.equal(ids, ref_ids)                              # same centres in -> same ids out
+        else:
+            assert torch.equal(ids, kmeans_assign(a, b, 0.5, before))
+            assert float((ids != ref_ids).float().mean()) <= 1e-4
+        assert torch.allclose(cen, ref_c, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(state, ref_state, rtol=1e-5, atol=1e-7)
