@@ -501,11 +501,11 @@ def issue_roofline(stats, fam_ms, traffic, sm_mhz):
 def kmeans_leg(cx, a):
     """BASELINE config 5: two-level codebook over 5 M points sharded over the ranks.  Coarse level: k = 64 over
     [ins_feat | xyz] (D = 9); fine level: k = 10 per coarse cluster over ins_feat (D = 6), ALL coarse clusters in one
-    segmented launch.  One pass = assign + fused centroid sums + the all-reduce of the packed partials
-    (opengaussian_b200.dist.PeerReducer: in-kernel NVLink reduction; NCCL when peer memory is unavailable)."""
+    segmented launch.  One pass = one Lloyd iteration = ONE kernel launch: assign + fused centroid sums + (N > 1) the
+    all-reduce of the partials over NVLink peer memory by the kernel's last CTA + the centre update."""
     torch, dev, world, rank = cx.torch, cx.dev, cx.world, cx.rank
     from opengaussian_b200 import dist as ogd
-    from opengaussian_b200.kmeans_quantize import kmeans_assign, kmeans_assign_segmented
+    from opengaussian_b200.kmeans_quantize import LloydWorkspace, kmeans_assign, lloyd_pass, lloyd_pass_segmented
     Nk = 5_000_000 // world
     g2 = torch.Generator(device=dev).manual_seed(7 + rank)
     fa = torch.rand(Nk, 6, device=dev, generator=g2)
@@ -513,32 +513,33 @@ def kmeans_leg(cx, a):
     cen = torch.cat([fa[:64], fb[:64]], 1).contiguous()
     if world > 1:
         cx.dist.broadcast(cen, 0)
+    cen0 = cen.clone()
     ids = torch.empty(Nk, dtype=torch.int64, device=dev)
     red = ogd.PeerReducer(64 * 10 * 8 * 8 + 4096) if world > 1 else None
-    buf = torch.zeros(64 * 9 + 64, device=dev)      # [sums | counts] packed: one memset, one collective
-    s9, c1 = buf[:64 * 9].view(64, 9), buf[64 * 9:]
-
-    def coarse_pass():
-        buf.zero_()
-        kmeans_assign(fa, fb, 1.0, cen, ids_out=ids, sums=s9, counts=c1)
-        if red is not None:
-            red.all_reduce(buf)
-
-    # fine level on the coarse ids just produced
-    coarse_pass()
+    comm = red.comm if red is not None else None
+    if world > 1 and comm is None:
+        raise RuntimeError("k-means leg: NVLink peer memory could not be mapped (" + red.kind + ")")
     k1, k2 = 64, 10
-    leaf_c = fa[:k1 * k2 + 1].contiguous()
+    ws_c = LloydWorkspace(dev, k=64, D=9)
+    ws_f = LloydWorkspace(dev, k1=k1, k2=k2, D=6)
+    state_c = torch.full((64,), 1e-6, device=dev)
+    n_eps = (Nk * world) // 10000 + 1
+
+    def coarse_pass():        # ONE launch: assign + sums + [peer all-reduce] + centre update
+        lloyd_pass(fa, fb, 1.0, cen, state_c, n_eps * 1e-6, ids, ws_c, comm)
+
+    # fine level on the coarse ids of one assign pass
+    kmeans_assign(fa, fb, 1.0, cen0, ids_out=ids)
+    coarse_ids = ids.clone()
+    leaf_c = fa[:k1 * k2 + 1].contiguous().clone()
     if world > 1:
         cx.dist.broadcast(leaf_c, 0)
     seg_k = torch.full((k1,), k2, dtype=torch.int32, device=dev)
     leaf_ids = torch.empty(Nk, dtype=torch.int64, device=dev)
-    fbuf = torch.zeros(k1 * k2 * 7, dtype=torch.int64, device=dev)     # exact fixed-point [sums | counts]
+    state_f = torch.full((k1 * k2,), 1e-6, device=dev)
 
-    def fine_pass():
-        fbuf.zero_()
-        kmeans_assign_segmented(fa, ids, leaf_c, seg_k, k2, ids_out=leaf_ids, acc=fbuf)
-        if red is not None:
-            red.all_reduce(fbuf)
+    def fine_pass():          # ONE launch for all 64 coarse clusters' fine levels
+        lloyd_pass_segmented(fa, coarse_ids, leaf_c, seg_k, k2, state_f, leaf_ids, 30, ws_f, comm)
 
     out = {}
     for name, fn, bytes_pt in (("coarse", coarse_pass, 44), ("fine", fine_pass, 40)):
@@ -551,7 +552,8 @@ def kmeans_leg(cx, a):
     out["coarse"]["k"], out["coarse"]["D"], out["fine"]["k"], out["fine"]["D"] = 64, 9, "10 per coarse cluster (640 rows)", 6
     km = {"metric": "kmeans assign + centroid-sum pass (BASELINE config 5: 5 M points, coarse k=64 D=9; fine k=10 per cluster D=6)",
           "points": Nk * world, "sharding": f"points sharded x{world}" if world > 1 else "single GPU",
-          "collective": (red.kind if red is not None else None), "coarse": out["coarse"], "fine": out["fine"],
+          "collective": (red.kind + ", inside the assign kernel's last CTA" if red is not None else None),
+          "launches_per_pass": 1, "coarse": out["coarse"], "fine": out["fine"],
           # kept at the top level for continuity with round 1
           "ms_per_pass": out["coarse"]["ms_per_pass"], "gpts_per_s": out["coarse"]["gpts_per_s"], "hbm_frac": out["coarse"]["hbm_frac"]}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

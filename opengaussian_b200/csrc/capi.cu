@@ -485,19 +485,6 @@ int ogs_kmeans_assign_segmented(int64_t N, const float* a, int32_t D, const int6
                                           (cudaStream_t)stream_);
 }
 
-namespace ogs {
-int launch_kmeans_lloyd_pass(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b, float* centers, int k,
-                             int k_out, const int64_t* select_ids, int64_t selected, int64_t id_offset, int64_t* ids_out,
-                             float* counts_state, float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s);
-}
-
-namespace ogs {
-size_t kmeans_seg_lloyd_workspace_bytes(int k1, int k2, int D);
-int launch_kmeans_seg_lloyd_pass(int64_t N, const float* a, int D, const int64_t* coarse_ids, float* seg_centers,
-                                 const int32_t* seg_k, int k1, int k2, int64_t* ids_out, int fix_bits, float* counts_state,
-                                 float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s);
-}
-
 size_t ogs_kmeans_lloyd_segmented_workspace_bytes(int32_t k1, int32_t k2, int32_t D) {
     return kmeans_seg_lloyd_workspace_bytes(k1, k2, D);
 }

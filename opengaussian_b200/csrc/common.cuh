@@ -285,6 +285,13 @@ int launch_kmeans_gather_st(int64_t N, const float* feat, int Dout, const float*
                             float* out, cudaStream_t s);
 int launch_kmeans_count(int64_t N, const int64_t* ids, int k, int64_t* counts, cudaStream_t s);
 size_t kmeans_lloyd_workspace_bytes(int k, int D);
+size_t kmeans_seg_lloyd_workspace_bytes(int k1, int k2, int D);
+int launch_kmeans_lloyd_pass(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b, float* centers, int k,
+                             int k_out, const int64_t* select_ids, int64_t selected, int64_t id_offset, int64_t* ids_out,
+                             float* counts_state, float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s);
+int launch_kmeans_seg_lloyd_pass(int64_t N, const float* a, int D, const int64_t* coarse_ids, float* seg_centers,
+                                 const int32_t* seg_k, int k1, int k2, int64_t* ids_out, int fix_bits, float* counts_state,
+                                 float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s);
 int launch_kmeans_assign_segmented(int64_t N, const float* a, int D, const int64_t* coarse_ids, const float* seg_centers,
                                    const int32_t* seg_k, int k1, int k2, int64_t* ids_out, int64_t* acc, int fix_bits,
                                    cudaStream_t s);

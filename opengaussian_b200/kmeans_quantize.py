@@ -95,6 +95,42 @@ def kmeans_assign_segmented(a, coarse_ids, seg_centers, seg_k, k2, ids_out=None,
     return ids_out
 
 
+class LloydWorkspace:
+    """Device scratch of the one-launch Lloyd passes (ticket + per-CTA partial tables), zeroed once and reused."""
+
+    def __init__(self, device, k=None, D=None, k1=None, k2=None):
+        L = _lib.lib()
+        n = L.ogs_kmeans_lloyd_workspace_bytes(k, D) if k1 is None else L.ogs_kmeans_lloyd_segmented_workspace_bytes(k1, k2, D)
+        self.buf = torch.zeros((n + 3) // 4, dtype=torch.int32, device=device)
+
+
+def lloyd_pass(a, b, scale_b, centers, counts_state, eps_add, ids_out, ws: LloydWorkspace, comm=None, k=None,
+               select_ids=None, selected=-1, id_offset=0):
+    """One Lloyd iteration in one launch (C ABI ogs_kmeans_lloyd_pass): `centers` [k_out, D] is updated in place from
+    its first k rows; counts_state [k_out] carries the reference's count bookkeeping; comm = PeerReducer.comm when the
+    points are sharded over GPUs."""
+    L = _lib.lib()
+    k_out = centers.shape[0]
+    k = k_out if k is None else k
+    with torch.cuda.device(a.device):
+        rc = L.ogs_kmeans_lloyd_pass(a.shape[0], _lib.ptr(a), a.shape[1], _lib.ptr(b), 0 if b is None else b.shape[1],
+                                     float(scale_b), _lib.ptr(centers), k, k_out, _lib.ptr(select_ids), int(selected),
+                                     int(id_offset), _lib.ptr(ids_out), _lib.ptr(counts_state), float(eps_add), comm,
+                                     _lib.ptr(ws.buf), _stream(a.device))
+    _lib.check(rc, "ogs_kmeans_lloyd_pass")
+
+
+def lloyd_pass_segmented(a, coarse_ids, seg_centers, seg_k, k2, counts_state, ids_out, fix_bits, ws: LloydWorkspace,
+                         comm=None, eps_add=1e-6):
+    """One Lloyd pass of every coarse cluster's fine level in one launch (C ABI ogs_kmeans_lloyd_pass_segmented)."""
+    L = _lib.lib()
+    with torch.cuda.device(a.device):
+        rc = L.ogs_kmeans_lloyd_pass_segmented(a.shape[0], _lib.ptr(a), a.shape[1], _lib.ptr(coarse_ids), _lib.ptr(seg_centers),
+                                               _lib.ptr(seg_k), seg_k.numel(), int(k2), _lib.ptr(ids_out), int(fix_bits),
+                                               _lib.ptr(counts_state), float(eps_add), comm, _lib.ptr(ws.buf), _stream(a.device))
+    _lib.check(rc, "ogs_kmeans_lloyd_pass_segmented")
+
+
 class _GatherStraightThrough(torch.autograd.Function):
     """_ins_feat_q = _ins_feat - _ins_feat.detach() + centres[ids][:, :D]  (reference :273-275)."""
 
