@@ -41,6 +41,7 @@ namespace ogs {
 #define KM_PPT 4                              // points per thread (packed pairs)
 #endif
 #define KM_CTA_POINTS (KM_THREADS * KM_PPT)   // 1024
+#define KM_GROUP 16                           // CTAs per first-level group of the fused reduction
 
 // ---- TMA bulk copy (global -> shared, completion on an mbarrier) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -261,17 +262,36 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
         }
     }
     if (tail.mode && partials) {
+        // Two-level "last arriver" reduction, deterministic (fixed CTA order inside a group, fixed group order):
+        // the last CTA of each group of KM_GROUP CTAs sums the group's partial tables, the last group to finish sums
+        // the group tables -- the reduction runs on ~gridDim/KM_GROUP SMs instead of one.
         __shared__ int s_last;
+        const int n_groups = (gridDim.x + KM_GROUP - 1) / KM_GROUP;
+        const int grp = blockIdx.x / KM_GROUP;
+        const int gsize = min(KM_GROUP, (int)gridDim.x - grp * KM_GROUP);
+        float* gpart = partials + (size_t)gridDim.x * k * ROW;           // [n_groups][k][ROW]
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        if (threadIdx.x == 0) s_last = (atomicAdd(tail.ticket + 1 + grp, 1u) == (unsigned)gsize - 1u) ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int e = threadIdx.x; e < k * ROW; e += KM_THREADS) {
+            float s = 0.f;
+            for (int c = 0; c < gsize; c++) s += __ldcg(partials + (size_t)(grp * KM_GROUP + c) * k * ROW + e);
+            gpart[(size_t)grp * k * ROW + e] = s;
+        }
+        if (threadIdx.x == 0) tail.ticket[1 + grp] = 0u;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(tail.ticket, 1u) == (unsigned)n_groups - 1u) ? 1 : 0;
         __syncthreads();
         if (!s_last) return;
         __threadfence();
         float* vec = s_acc;                                  // [k][ROW]: the per-warp accumulators are done with
         for (int e = threadIdx.x; e < k * ROW; e += KM_THREADS) {
             float s = 0.f;
-            for (unsigned bk = 0; bk < gridDim.x; bk++) s += __ldcg(partials + (size_t)bk * k * ROW + e);
+            for (int g2 = 0; g2 < n_groups; g2++) s += __ldcg(gpart + (size_t)g2 * k * ROW + e);
             vec[e] = s;
         }
         __syncthreads();
@@ -358,8 +378,11 @@ int launch_kmeans_assign(int64_t N, const float* a, int Da, const float* b, int 
 }
 
 // ---- one Lloyd iteration in one launch (assign + centroid sums + [peer all-reduce] + centre update) ----
-// workspace (caller-owned, zero-initialised once): [ticket: 256 B][partials: grid_max * k * (D+1) floats]
-size_t kmeans_lloyd_workspace_bytes(int k, int D) { return 256 + (size_t)OGS_NUM_SMS * 2 * k * (D + 1) * sizeof(float); }
+// workspace (caller-owned, zero-initialised once): [tickets: 256 B][partials: grid_max * k * (D+1) floats][group tables]
+size_t kmeans_lloyd_workspace_bytes(int k, int D) {
+    const size_t grid_max = (size_t)OGS_NUM_SMS * 2;
+    return 256 + (grid_max + (grid_max + KM_GROUP - 1) / KM_GROUP) * k * (D + 1) * sizeof(float);
+}
 
 template <int D>
 static int launch_lloyd_d(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b, float* centers, int k,

@@ -13,7 +13,7 @@
 //
 // Centroid sums are EXACT: every coordinate is converted to a 64-bit fixed-point integer
 // (llrint(x * 2^fix_bits), |x| * 2^fix_bits < 2^32) and accumulated with integer atomics -- shared memory first,
-// one row per (coarse, fine) pair, then per-CTA partial tables reduced in a second tiny kernel.  Integer addition is
+// one row per (coarse, fine) pair, then integer reds into one global table.  Integer addition is
 // associative, so the result does not depend on the order of the atomics, on the grid, or on how the points
 // are sharded over GPUs: a sharded run reproduces the single-GPU centres bit for bit after the (integer)
 // all-reduce.  The kernel is HBM-bound: 4 D + 8 (coarse id) + 8 (fine id) bytes per point.
@@ -28,6 +28,8 @@ namespace ogs {
 #define KS_PPT 4
 #define KS_FLUSH_POINTS 16384    // a CTA folds its 32-bit shared accumulators into its 64-bit partial table this often
 
+// Every CTA adds its sums into ONE global int64 table with red.global.add.u64 (zeros skipped) -- integer reds commute,
+// so neither determinism nor exactness is lost -- about once per KS_FLUSH_POINTS points.
 // Shared memory holds the centre blocks structure-of-arrays, s_c[d][c * k2p + j] with an ODD block stride k2p, so
 // that lanes working on different coarse clusters spread over all 32 banks, and the accumulators as PAIRS of 32-bit
 // words: a fixed-point value q (int64) is split as q = hi * 65536 + lo, lo in [0, 65535], and lo / hi are added
@@ -39,7 +41,7 @@ namespace ogs {
 // [k1*k2][D+1] integers over the peers' memory when the points are sharded, and applies the reference's centre update
 // to every block -- one Lloyd pass of ALL coarse clusters' fine levels is then one launch.
 struct KsTail {
-    int mode;                    // 0: off (partials are ADDED to zeroed tables and reduced by kmeans_seg_reduce_kernel)
+    int mode;                    // 0: off (the sums are only ADDED into the caller's table)
     unsigned int* ticket;
     int has_peer;
     PeerDev peer;
@@ -52,17 +54,17 @@ template <int D>
 __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
     int64_t N, const float* __restrict__ a, const int64_t* __restrict__ coarse_ids, const float* __restrict__ seg_centers,
     const int32_t* __restrict__ seg_k, int k1, int k2, int64_t* __restrict__ ids_out,
-    unsigned long long* __restrict__ partials /* [grid][k1*k2][D+1] (zeroed unless tail.mode) or NULL */, float fix_scale,
-    int vec2_ok, KsTail tail) {
+    unsigned long long* __restrict__ table /* [k1*k2][D+1] global int64 sums, ADDED to; NULL = pure reassign */,
+    float fix_scale, int vec2_ok, KsTail tail) {
     constexpr int ROW = D + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int rows = k1 * k2;
     const int k2p = k2 | 1;
     const int rows_p = k1 * k2p;
     // accumulators first (8-byte aligned: the fused tail re-reads the two 32-bit planes' storage as int64)
-    unsigned int* s_lo = reinterpret_cast<unsigned int*>(smem_raw);       // [rows][ROW]      (if partials)
+    unsigned int* s_lo = reinterpret_cast<unsigned int*>(smem_raw);       // [rows][ROW]      (if table)
     int* s_hi = reinterpret_cast<int*>(s_lo + (size_t)rows * ROW);        // [rows][ROW]
-    float* s_c = reinterpret_cast<float*>(smem_raw + (partials ? (size_t)rows * ROW * 8 : 0));   // [D + 1][rows_p] (last plane: ||c||^2)
+    float* s_c = reinterpret_cast<float*>(smem_raw + (table ? (size_t)rows * ROW * 8 : 0));   // [D + 1][rows_p] (last plane: ||c||^2)
     int* s_k = reinterpret_cast<int*>(s_c + (size_t)ROW * rows_p);        // [k1]
 
     for (int r = threadIdx.x; r < rows; r += KS_THREADS) {
@@ -80,22 +82,19 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
         const int v = seg_k[j];
         s_k[j] = v < 0 ? 0 : (v > k2 ? k2 : v);
     }
-    if (partials)
+    if (table)
         for (int e = threadIdx.x; e < rows * ROW; e += KS_THREADS) { s_lo[e] = 0u; s_hi[e] = 0; }
     __syncthreads();
 
-    bool first_flush = tail.mode != 0;        // fused mode: the table is not pre-zeroed, the first flush overwrites it
+    // fold the CTA's 32-bit pairs into the global int64 table: integer reds, order-independent, zeros skipped
     auto flush = [&]() {
         __syncthreads();
-        unsigned long long* out = partials + (size_t)blockIdx.x * rows * ROW;
         for (int e = threadIdx.x; e < rows * ROW; e += KS_THREADS) {
             const long long v = (long long)s_hi[e] * 65536ll + (long long)s_lo[e];
-            if (first_flush) out[e] = (unsigned long long)v;
-            else if (v != 0) out[e] += (unsigned long long)v;
+            if (v != 0) atomicAdd(table + e, (unsigned long long)v);
             s_lo[e] = 0u;
             s_hi[e] = 0;
         }
-        first_flush = false;
         __syncthreads();
     };
 
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
             }
             const int r = c[q] * k2 + best_j;
             ids_out[i] = (int64_t)r;
-            if (partials) {
+            if (table) {
 #pragma unroll
                 for (int d = 0; d < D; d++) {
                     const long long v = __float2ll_rn(__fmul_rn(x[q][d], fix_scale));
@@ -152,10 +151,10 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
             }
         }
         since_flush += (int)chunk;
-        if (partials && since_flush >= KS_FLUSH_POINTS) { flush(); since_flush = 0; }
+        if (table && since_flush >= KS_FLUSH_POINTS) { flush(); since_flush = 0; }
     }
-    if (partials) flush();
-    if (tail.mode && partials) {
+    if (table) flush();
+    if (tail.mode && table) {
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
@@ -165,9 +164,8 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
         __threadfence();
         long long* vec = reinterpret_cast<long long*>(s_lo);        // [rows][ROW] int64: exactly the two 32-bit planes
         for (int e = threadIdx.x; e < rows * ROW; e += KS_THREADS) {
-            long long sum = 0;
-            for (unsigned bk = 0; bk < gridDim.x; bk++) sum += (long long)__ldcg(partials + (size_t)bk * rows * ROW + e);
-            vec[e] = sum;
+            vec[e] = (long long)__ldcg(table + e);
+            table[e] = 0ull;                                          // ready for the next pass
         }
         __syncthreads();
         bool ok = true;
@@ -183,15 +181,6 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
         }
         if (threadIdx.x == 0) *tail.ticket = 0u;
     }
-}
-
-__global__ void kmeans_seg_reduce_kernel(int nblocks, int n, const unsigned long long* __restrict__ partials,
-                                         unsigned long long* __restrict__ acc) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    unsigned long long s = 0ull;
-    for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * n + e];
-    acc[e] += s;
 }
 
 static int seg_grid(int64_t N, size_t smem) {
@@ -214,23 +203,12 @@ static int launch_seg_d(int64_t N, const float* a, const int64_t* coarse_ids, co
         at.store(smem, std::memory_order_relaxed);
     }
     const int grid = seg_grid(N, smem);
-    AsyncScratch partials(s);
-    if (acc) {
-        OGS_CUDA(partials.alloc((size_t)grid * rows * (D + 1) * 8));
-        OGS_CUDA(cudaMemsetAsync(partials.p, 0, (size_t)grid * rows * (D + 1) * 8, s));
-    }
     KsTail tail;
     memset(&tail, 0, sizeof tail);
     kmeans_assign_seg_kernel<D><<<grid, KS_THREADS, smem, s>>>(N, a, coarse_ids, seg_centers, seg_k, k1, k2, ids_out,
-                                                               (unsigned long long*)partials.p, ldexpf(1.0f, fix_bits),
+                                                               (unsigned long long*)acc, ldexpf(1.0f, fix_bits),
                                                                (((uintptr_t)a & 7) == 0) ? 1 : 0, tail);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && acc) {
-        const int n = rows * (D + 1);
-        kmeans_seg_reduce_kernel<<<(n + 127) / 128, 128, 0, s>>>(grid, n, (const unsigned long long*)partials.p,
-                                                                 (unsigned long long*)acc);
-        e = cudaGetLastError();
-    }
     if (e != cudaSuccess) return cuda_fail(e, "kmeans_assign_segmented");
     return 0;
 }
@@ -249,9 +227,7 @@ int launch_kmeans_assign_segmented(int64_t N, const float* a, int D, const int64
 }
 
 // ---- one Lloyd pass of every coarse cluster's fine level in one launch ----
-size_t kmeans_seg_lloyd_workspace_bytes(int k1, int k2, int D) {
-    return 256 + (size_t)OGS_NUM_SMS * 3 * k1 * k2 * (D + 1) * 8;
-}
+size_t kmeans_seg_lloyd_workspace_bytes(int k1, int k2, int D) { return 256 + (size_t)k1 * k2 * (D + 1) * 8; }
 
 template <int D>
 static int launch_seg_lloyd_d(int64_t N, const float* a, const int64_t* coarse_ids, float* seg_centers, const int32_t* seg_k,
