@@ -325,6 +325,19 @@ __global__ void kmeans_reduce_partials_kernel(int nblocks, int k, int D, const f
     else if (counts) counts[j] += s;
 }
 
+// The dynamic-shared-memory attribute belongs to the KERNEL (per device): ONE cache per instantiation, shared by every
+// launcher of that kernel, and only ever raised -- two launchers with private caches would lower each other's setting.
+template <int D>
+static int ensure_assign_smem(size_t smem) {
+    static std::atomic<size_t> attr[OGS_MAX_DEVICES];        // per device: largest size the attribute was raised to
+    std::atomic<size_t>& at = attr[current_device()];
+    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
+        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        at.store(smem, std::memory_order_relaxed);
+    }
+    return 0;
+}
+
 template <int D>
 static int launch_assign_d(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b,
                            const float* centers, int k, const int64_t* select_ids, int64_t selected,
@@ -333,12 +346,7 @@ static int launch_assign_d(int64_t N, const float* a, int Da, const float* b, in
     size_t smem = (size_t)2 * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
     if (fuse) smem += (size_t)KM_WARPS * k * (D + 1) * sizeof(float);
     if (smem > 220 * 1024) { set_error("kmeans_assign: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
-    static std::atomic<size_t> attr[OGS_MAX_DEVICES];        // per device: largest size the attribute was raised to
-    std::atomic<size_t>& at = attr[current_device()];
-    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
-        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        at.store(smem, std::memory_order_relaxed);
-    }
+    { const int rc_attr = ensure_assign_smem<D>(smem); if (rc_attr) return rc_attr; }
     // bulk copies need 16-byte aligned sources and sizes: tile strides are multiples of 4096 bytes
     const int bulk_ok = (((uintptr_t)a & 15) == 0 && (Db == 0 || ((uintptr_t)b & 15) == 0)) ? 1 : 0;
     int64_t want = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
@@ -395,12 +403,7 @@ static int launch_lloyd_d(int64_t N, const float* a, int Da, const float* b, int
         set_error("kmeans_lloyd_pass: the communicator's slots are too small for k=%d D=%d", k, D);
         return -1;
     }
-    static std::atomic<size_t> attr[OGS_MAX_DEVICES];
-    std::atomic<size_t>& at = attr[current_device()];
-    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
-        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        at.store(smem, std::memory_order_relaxed);
-    }
+    { const int rc_attr = ensure_assign_smem<D>(smem); if (rc_attr) return rc_attr; }
     const int bulk_ok = (((uintptr_t)a & 15) == 0 && (Db == 0 || ((uintptr_t)b & 15) == 0)) ? 1 : 0;
     int64_t want = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
     const int per_sm = smem > 110 * 1024 ? 1 : 2;

@@ -17,6 +17,7 @@
 // associative, so the result does not depend on the order of the atomics, on the grid, or on how the points
 // are sharded over GPUs: a sharded run reproduces the single-GPU centres bit for bit after the (integer)
 // all-reduce.  The kernel is HBM-bound: 4 D + 8 (coarse id) + 8 (fine id) bytes per point.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,7 +25,7 @@
 
 namespace ogs {
 
-#define KS_THREADS 256
+#define KS_THREADS 512
 #define KS_PPT 4
 #define KS_FLUSH_POINTS 16384    // a CTA folds its 32-bit shared accumulators into its 64-bit partial table this often
 
@@ -185,9 +186,25 @@ __global__ void __launch_bounds__(KS_THREADS) kmeans_assign_seg_kernel(
 
 static int seg_grid(int64_t N, size_t smem) {
     const int64_t want = (N + KS_THREADS * KS_PPT - 1) / (KS_THREADS * KS_PPT);
-    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3);
+    // every CTA ends with up to k1*k2*(D+1) integer reds whatever its share of the points: few fat CTAs (512 threads,
+    // 4 points each in flight per thread) keep that fixed cost small without starving the memory system
+    static const int env_per_sm = getenv("OGS_KS_PER_SM") ? atoi(getenv("OGS_KS_PER_SM")) : 0;   // tuning knob
+    const int per_sm = env_per_sm > 0 ? env_per_sm : 2;
+    (void)smem;
     int grid = (int)(want < (int64_t)OGS_NUM_SMS * per_sm ? want : (int64_t)OGS_NUM_SMS * per_sm);
     return grid < 1 ? 1 : grid;
+}
+
+// one attribute cache per kernel instantiation, shared by both launchers (see kmeans.cu)
+template <int D>
+static int ensure_seg_smem(size_t smem) {
+    static std::atomic<size_t> attr[OGS_MAX_DEVICES];
+    std::atomic<size_t>& at = attr[current_device()];
+    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
+        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_seg_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        at.store(smem, std::memory_order_relaxed);
+    }
+    return 0;
 }
 
 template <int D>
@@ -196,12 +213,7 @@ static int launch_seg_d(int64_t N, const float* a, const int64_t* coarse_ids, co
     const int rows = k1 * k2;
     const size_t smem = (acc ? (size_t)rows * (D + 1) * 8 : 0) + (size_t)k1 * (k2 | 1) * (D + 1) * 4 + (size_t)k1 * 4;
     if (smem > 200 * 1024) { set_error("kmeans_assign_segmented: k1*k2=%d D=%d needs %zu B shared memory", rows, D, smem); return -5; }
-    static std::atomic<size_t> attr[OGS_MAX_DEVICES];
-    std::atomic<size_t>& at = attr[current_device()];
-    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
-        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_seg_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        at.store(smem, std::memory_order_relaxed);
-    }
+    { const int rc_attr = ensure_seg_smem<D>(smem); if (rc_attr) return rc_attr; }
     const int grid = seg_grid(N, smem);
     KsTail tail;
     memset(&tail, 0, sizeof tail);
@@ -240,12 +252,7 @@ static int launch_seg_lloyd_d(int64_t N, const float* a, const int64_t* coarse_i
         set_error("kmeans_lloyd_pass_segmented: the communicator's slots are too small");
         return -1;
     }
-    static std::atomic<size_t> attr[OGS_MAX_DEVICES];
-    std::atomic<size_t>& at = attr[current_device()];
-    if (smem > 48 * 1024 && smem > at.load(std::memory_order_relaxed)) {
-        OGS_CUDA(cudaFuncSetAttribute(kmeans_assign_seg_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        at.store(smem, std::memory_order_relaxed);
-    }
+    { const int rc_attr = ensure_seg_smem<D>(smem); if (rc_attr) return rc_attr; }
     const int grid = seg_grid(N, smem);
     KsTail tail;
     memset(&tail, 0, sizeof tail);
