@@ -31,6 +31,8 @@
  *   ogs_kmeans_count             scene/kmeans_quantize.py:89-144 (equalize_cluster_size member counts)
  *   ogs_kmeans_assign_segmented, ogs_kmeans_finalize_fixed
  *                                scene/kmeans_quantize.py:196-214,233-238 (leaf mode) for all coarse clusters at once
+ *   ogs_multimem_allreduce_f32   no reference counterpart: the view-parallel step's gradient all-reduce, reduced inside
+ *                                the NVSwitch
  *   ogs_peer_*                   no reference counterpart (the reference is single-GPU): the all-reduce of the
  *                                sharded k-means' centroid partials over NVLink peer memory
  *   ogs_mask_pair_counts         utils/opengs_utlis.py:90-123 (calculate_iou)
@@ -288,6 +290,16 @@ int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, c
 int64_t ogs_mask_iou_scratch_bytes(int32_t n1, int32_t n2, int64_t HW);
 int ogs_mask_pair_counts(int32_t n1, int32_t n2, int64_t HW, const uint8_t* masks1, const uint8_t* masks2,
                          void* scratch, int32_t* inter, int32_t* counts, void* stream);
+
+/* ---- gradient all-reduce through the NVSwitch multicast mapping ("Gaussian-parameter gradients are
+ * allreduced"; the reference has no distributed code) ----
+ * multicast_ptr: the MULTICAST address of a float32 buffer that every rank of the node maps at the same offset
+ * (e.g. torch.distributed._symmetric_memory: rendezvous(...).multicast_ptr + byte offset), 16-byte aligned;
+ * n_floats a multiple of 4.  Rank r reduces slice r with multimem.ld_reduce (the switch adds the ranks' copies in
+ * flight) and writes the sums to every copy with multimem.st: afterwards all ranks hold the element-wise sum.
+ * The caller must place a cross-rank barrier on the stream before the call (all gradients written) and after it
+ * (all slices stored). */
+int ogs_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world, void* stream);
 
 /* ---- batched single-splat footprints and their SAM-id votes: utils/sam_refinement_utils.py::
  * MultiViewSAMMaskRefiner.get_splat_id_and_weights (:902-913) = render_single_gaussian (:330-403, white

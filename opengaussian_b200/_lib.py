@@ -88,6 +88,7 @@ EXPORTS = {
     "ogs_kmeans_lloyd_segmented_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "ogs_kmeans_lloyd_pass_segmented": (C.c_int, [C.c_int64, _fp, C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, C.c_int32,
                                                   _fp, C.c_float, C.c_void_p, _fp, C.c_void_p]),
+    "ogs_multimem_allreduce_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "ogs_peer_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "ogs_peer_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ogs_peer_allreduce": (C.c_int, [C.c_void_p, _fp, C.c_int64, C.c_int32, C.c_void_p]),

@@ -26,6 +26,7 @@ UNITS = {
     "preprocess_bwd.cu": [],
     "kmeans_seg.cu": [],
     "peer.cu": [],
+    "nvls.cu": [],
     "kmeans.cu": [],
     "mask_stats.cu": [],
     "mask_iou.cu": [],

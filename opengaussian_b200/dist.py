@@ -69,6 +69,12 @@ def allreduce_gradients(params: Iterable[torch.Tensor], group=None, bucket_bytes
         return
     offs, span = _flat_layout(params)
     flat = _coalesced_grads(params, offs, span)
+    arena = _ARENAS.get(params[0].device.index) if params[0].is_cuda else None
+    if arena is not None and arena.owns(flat, span):
+        arena.all_reduce(span)                    # one kernel of ours: the NVSwitch reduces in flight
+        if average:
+            flat.div_(w)
+        return
     packed = flat is None
     if packed:
         flat = torch.zeros(span, dtype=torch.float32, device=params[0].device)
@@ -103,6 +109,78 @@ def _coalesced_grads(params, offs=None, span=None) -> Optional[torch.Tensor]:
     if (base + span) * 4 > st.nbytes():
         return None
     return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, base, (span,))
+
+
+_ARENAS = {}
+
+
+class GradArena:
+    """Symmetric-memory home of the step's gradient buffer + its all-reduce through the NVSwitch multicast mapping.
+
+    The rasterizer's backward carves every parameter gradient out of ONE flat buffer (rasterizer.py); with an arena
+    installed that buffer lives in memory that all ranks of the node map into one multicast address range
+    (torch.distributed._symmetric_memory does the allocation and the rendezvous -- plumbing), and
+    `allreduce_gradients` sums it with ONE kernel of libogs_b200 (csrc/nvls.cu: multimem.ld_reduce / multimem.st,
+    the switch adds the ranks' copies in flight) bracketed by two stream-ordered cross-rank barriers, instead of a
+    library all-reduce.  `kind` says what is in use; without multicast support the arena is not installed and the
+    gradients go through torch.distributed as before."""
+
+    def __init__(self, n_floats: int, group=None, device=None):
+        from . import _lib
+        from .rasterizer import set_grad_arena
+        self._lib = _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = world(group)
+        self.kind = "torch.distributed all_reduce"
+        self.buf = None
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.world == 1:
+            return
+        n = (int(n_floats) + 4 * self.world + 63) // 64 * 64
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(buf, self.group)
+            mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
+            if mc == 0:
+                ok = 0
+        except Exception as e:      # noqa: BLE001  (no symmetric memory / multicast on this box)
+            self.error = repr(e)
+            ok = 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            return
+        buf.zero_()
+        self.buf, self.hdl, self.mc = buf, hdl, mc
+        self.kind = "one kernel: multimem.ld_reduce + multimem.st through the NVSwitch multicast mapping (ogs_multimem_allreduce_f32)"
+        set_grad_arena(buf)
+        _ARENAS[self.device.index] = self
+
+    def owns(self, flat: Optional[torch.Tensor], span: int) -> bool:
+        return (self.buf is not None and flat is not None and flat.data_ptr() == self.buf.data_ptr()
+                and span <= self.buf.numel())
+
+    def all_reduce(self, n_floats: int):
+        """In-place sum over the ranks of the first n_floats of the arena, enqueued on the current stream."""
+        import ctypes as C
+        n = (int(n_floats) + 3) // 4 * 4
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self.hdl.barrier(channel=0)                 # every rank's gradients are written
+        with torch.cuda.device(self.device):
+            rc = self._lib.lib().ogs_multimem_allreduce_f32(C.c_void_p(self.mc), n, self.rank, self.world, stream)
+        self._lib.check(rc, "ogs_multimem_allreduce_f32")
+        self.hdl.barrier(channel=1)                 # every slice has been stored everywhere
+
+    def close(self):
+        from .rasterizer import set_grad_arena
+        if self.buf is not None:
+            set_grad_arena(None)
+            _ARENAS.pop(self.device.index, None)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self.buf = None
 
 
 def shard_kmeans(codebook, group=None, peer_reduce: bool = False):

@@ -116,6 +116,18 @@ def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities,
 
 
 _FUSE_ACCUMULATE = False
+_GRAD_ARENA = {}      # device index -> flat fp32 tensor the backward carves its gradient buffer from (dist.GradArena)
+
+
+def set_grad_arena(t: Optional[torch.Tensor]):
+    """Registers (or, with None, removes) the flat float32 tensor from which the backward of this device carves the
+    step's gradient buffer instead of allocating it -- opengaussian_b200.dist.GradArena passes its symmetric-memory
+    buffer so that the gradient all-reduce can run through the NVSwitch multicast mapping.  The arena is reused by
+    every step: gradients of the previous step that still alias it are overwritten by the next first backward."""
+    if t is None:
+        _GRAD_ARENA.clear()
+    else:
+        _GRAD_ARENA[t.device.index] = t
 
 
 class fuse_grad_accumulation:
@@ -244,37 +256,55 @@ class _RasterizeGaussians(torch.autograd.Function):
         # adopts the views as .grad, and opengaussian_b200.dist.allreduce_gradients then reduces the whole
         # buffer with a single NCCL call instead of one per tensor.
         specs = []
+        sources = []          # the input tensor each requested parameter gradient belongs to
 
-        def want(flag, *shape):
+        def want(flag, src, *shape):
             if not flag:
                 return None
             n = 1
             for d in shape:
                 n *= int(d)
             specs.append((len(specs), tuple(int(d) for d in shape), n))
+            sources.append(src)
             return len(specs) - 1
 
         need_rest = sh_rest is not None and need[11]
-        i_means3D = want(need[0], P, 3)
-        i_opac = want(need[4], *opacities.shape)
-        i_sh = want((need[2] or need_rest) and sh is not None, *(sh.shape if sh is not None else (0,)))
-        i_sh_rest = want(need_rest, *(sh_rest.shape if sh_rest is not None else (0,)))
-        i_colors = want(need[3] and colors_precomp is not None, P, 3)
-        i_scales = want(need[5] and scales is not None, P, 3)
-        i_rot = want(need[6] and rotations is not None, P, 4)
-        i_cov = want(need[7] and cov3Ds_precomp is not None, P, 6)
-        i_extra = want(need[8] and extra is not None, P, max(n_extra, 1))
-        i_means2D = want(need[1], P, 3)            # last: it is a per-view statistic, not all-reduced
+        i_means3D = want(need[0], ctx.inputs_ref[0], P, 3)
+        i_opac = want(need[4], opacities, *opacities.shape)
+        i_sh = want((need[2] or need_rest) and sh is not None, sh, *(sh.shape if sh is not None else (0,)))
+        i_sh_rest = want(need_rest, sh_rest, *(sh_rest.shape if sh_rest is not None else (0,)))
+        i_colors = want(need[3] and colors_precomp is not None, colors_precomp, P, 3)
+        i_scales = want(need[5] and scales is not None, scales, P, 3)
+        i_rot = want(need[6] and rotations is not None, rotations, P, 4)
+        i_cov = want(need[7] and cov3Ds_precomp is not None, cov3Ds_precomp, P, 6)
+        i_extra = want(need[8] and extra is not None, extra, P, max(n_extra, 1))
+        n_param = len(specs)
+        i_means2D = want(need[1], None, P, 3)      # last: it is a per-view statistic, not all-reduced
         offs, total = [], 0
         for _, _, n in specs:
             offs.append(total)
             total += (n + 63) // 64 * 64
-        flat = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+        # Gradient arena (dist.GradArena: symmetric memory for the in-switch all-reduce): the parameter gradients of
+        # the FIRST backward of a step are carved from it -- only when every requested input is a leaf without a
+        # .grad yet, so nothing that still aliases the arena can be overwritten; the per-view means2D gradient never
+        # lives there.
+        arena = _GRAD_ARENA.get(dev.index)
+        param_total = offs[n_param] if i_means2D is not None else total
+        use_arena = (arena is not None and 0 < param_total <= arena.numel() and n_param > 0 and
+                     all(t is not None and t.is_leaf and t.grad is None for t in sources[:n_param]))
+        if use_arena:
+            flat = arena[:param_total]
+            flat2 = torch.empty(P * 3, dtype=torch.float32, device=dev) if i_means2D is not None else None
+        else:
+            flat = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+            flat2 = None
 
         def view(i):
             if i is None:
                 return None
             _, shape, n = specs[i]
+            if flat2 is not None and i == i_means2D:
+                return flat2.view(shape)
             return flat[offs[i]:offs[i] + n].view(shape)
 
         g_means3D, g_opac, g_sh, g_sh_rest = view(i_means3D), view(i_opac), view(i_sh), view(i_sh_rest)
