@@ -70,6 +70,8 @@ def parse():
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events in the timed region")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of `steps` steps each; the median is reported")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 2 and 4 legs")
+    ap.add_argument("--grad-allreduce", default="nvls", choices=["nvls", "nccl"],
+                    help="N > 1: sum the gradients with the library's in-switch kernel (GradArena) or with NCCL")
     return ap.parse_args()
 
 
@@ -274,7 +276,7 @@ class RasterWorkload:
         self._e2e_ready = False
         # N > 1: the step's gradient buffer lives in symmetric memory and is summed by our own in-switch kernel
         self.arena = None
-        if cx.world > 1:
+        if cx.world > 1 and getattr(cx, "grad_allreduce", "nvls") == "nvls":
             from opengaussian_b200 import dist as ogd
             _, span = ogd._flat_layout(self.reduced)
             self.arena = ogd.GradArena(span)
@@ -720,6 +722,7 @@ def comparator_leg(cx, a):
 def run_ours(a):
     quiet_stdout()
     cx = Ctx()
+    cx.grad_allreduce = a.grad_allreduce
     torch, world, rank = cx.torch, cx.world, cx.rank
     from opengaussian_b200 import _lib, dist as ogd
     _lib.lib()   # fails loudly if the CUDA library is missing
@@ -732,7 +735,7 @@ def run_ours(a):
     tile_bits = max(1, (tiles - 1).bit_length())
     h2d, d2h = wl.h2d_bytes_per_step(), 4
     n_cams = len(wl.cams)
-    coll_kind = wl.arena.kind if wl.arena is not None else None
+    coll_kind = wl.arena.kind if wl.arena is not None else "NCCL all_reduce of the flat gradient buffer"
     wl.close()
     del wl
     torch.cuda.empty_cache()

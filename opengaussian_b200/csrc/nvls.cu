@@ -10,12 +10,13 @@
 // Per GPU the links move the buffer once in and once out (the two-shot schedule of a library all-reduce, without its
 // protocol, staging copies and channel bookkeeping).  The caller brackets the launch with a cross-rank barrier on
 // the stream (every rank's gradients written before / every slice stored after).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ogs {
 
 #define NVLS_THREADS 512
-#define NVLS_UNROLL 4
 
 __device__ __forceinline__ void mm_ld_reduce(const float* mc, uint32_t (&v)[4]) {
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -28,6 +29,7 @@ __device__ __forceinline__ void mm_st(float* mc, const uint32_t (&v)[4]) {
                  : "memory");
 }
 
+template <int NVLS_UNROLL>
 __global__ void __launch_bounds__(NVLS_THREADS) multimem_allreduce_f32_kernel(float* __restrict__ mc, size_t n4, int rank, int world) {
     const size_t per = (n4 + (size_t)world - 1) / (size_t)world;
     const size_t lo = (size_t)rank * per;
@@ -54,12 +56,18 @@ extern "C" int ogs_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats,
         return -1;
     }
     if (n_floats == 0) return 0;
+    static const int env_grid = getenv("OGS_NVLS_GRID") ? atoi(getenv("OGS_NVLS_GRID")) : 0;        // tuning knobs
+    static const int env_unroll = getenv("OGS_NVLS_UNROLL") ? atoi(getenv("OGS_NVLS_UNROLL")) : 4;
     const size_t n4 = (size_t)n_floats / 4;
     const size_t per = (n4 + world - 1) / world;
-    size_t want = (per + (size_t)NVLS_THREADS * NVLS_UNROLL - 1) / ((size_t)NVLS_THREADS * NVLS_UNROLL);
-    int grid = (int)(want < (size_t)OGS_NUM_SMS * 2 ? want : (size_t)OGS_NUM_SMS * 2);
+    const size_t want = (per + (size_t)NVLS_THREADS * env_unroll - 1) / ((size_t)NVLS_THREADS * env_unroll);
+    const size_t cap = env_grid > 0 ? (size_t)env_grid : (size_t)OGS_NUM_SMS * 2;
+    int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    multimem_allreduce_f32_kernel<<<grid, NVLS_THREADS, 0, (cudaStream_t)stream_>>>((float*)multicast_ptr, n4, rank, world);
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (env_unroll >= 8) multimem_allreduce_f32_kernel<8><<<grid, NVLS_THREADS, 0, s>>>((float*)multicast_ptr, n4, rank, world);
+    else if (env_unroll <= 2) multimem_allreduce_f32_kernel<2><<<grid, NVLS_THREADS, 0, s>>>((float*)multicast_ptr, n4, rank, world);
+    else multimem_allreduce_f32_kernel<4><<<grid, NVLS_THREADS, 0, s>>>((float*)multicast_ptr, n4, rank, world);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "multimem_allreduce_f32");
     return 0;

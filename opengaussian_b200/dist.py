@@ -162,11 +162,17 @@ class GradArena:
         return (self.buf is not None and flat is not None and flat.data_ptr() == self.buf.data_ptr()
                 and span <= self.buf.numel())
 
-    def all_reduce(self, n_floats: int):
-        """In-place sum over the ranks of the first n_floats of the arena, enqueued on the current stream."""
+    def all_reduce(self, n_floats: int, barriers: bool = True):
+        """In-place sum over the ranks of the first n_floats of the arena, enqueued on the current stream.
+        (barriers=False is a timing aid only: the result is then unordered against the other ranks' writes.)"""
         import ctypes as C
         n = (int(n_floats) + 3) // 4 * 4
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if not barriers:
+            with torch.cuda.device(self.device):
+                rc = self._lib.lib().ogs_multimem_allreduce_f32(C.c_void_p(self.mc), n, self.rank, self.world, stream)
+            self._lib.check(rc, "ogs_multimem_allreduce_f32")
+            return
         self.hdl.barrier(channel=0)                 # every rank's gradients are written
         with torch.cuda.device(self.device):
             rc = self._lib.lib().ogs_multimem_allreduce_f32(C.c_void_p(self.mc), n, self.rank, self.world, stream)

@@ -18,7 +18,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     out = {"world": world}
-    for n in (59_000_320, 177_000_320):                      # 1 M and 3 M Gaussians x 59 floats (+ alignment)
+    out["grid"], out["unroll"] = os.environ.get("OGS_NVLS_GRID"), os.environ.get("OGS_NVLS_UNROLL")
+    for n in (59_000_320, 177_000_320)[:int(os.environ.get("NVLS_CASES", "2"))]:                      # 1 M and 3 M Gaussians x 59 floats (+ alignment)
         arena = ogd.GradArena(n)
         out["kind"] = arena.kind
         if arena.buf is None:
@@ -35,7 +36,8 @@ def main():
         out[f"max_abs_diff_{n}"] = float((got - want).abs().max())
         assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for label, fn in (("nvls", lambda: arena.all_reduce(n)), ("nccl", lambda: dist.all_reduce(want))):
+        for label, fn in (("nvls", lambda: arena.all_reduce(n)), ("nvls_nobarrier", lambda: arena.all_reduce(n, barriers=False)),
+                          ("nccl", lambda: dist.all_reduce(want))):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()

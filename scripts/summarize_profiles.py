@@ -38,8 +38,10 @@ FAMILY = [  # kernel-name substring -> bench.py breakdown family
     ("blend_bwd", "blend_bwd"), ("emit_kernel", "emit"), ("ranges_kernel", "tile_ranges"),
     ("rs_pass_kernel<unsigned short", "tile_sort"), ("rs_tile_hist", "tile_sort"), ("rs_tile_scan", "tile_sort"),
     ("rs_pass_kernel<unsigned int", "depth_sort_scan"), ("rs_hist_kernel", "depth_sort_scan"),
-    ("scan_gather", "depth_sort_scan"), ("kmeans_assign", "kmeans_assign"), ("adam_kernel", "adam"),
+    ("scan_gather", "depth_sort_scan"), ("kmeans_assign_seg", "kmeans_assign_seg"), ("kmeans_assign", "kmeans_assign"),
+    ("adam_kernel", "adam"),
     ("mask_pack_kernel", "mask_iou"), ("mask_pair_kernel", "mask_iou"), ("footprint_vote", "footprint"),
+    ("kmeans_assign_seg", "kmeans_assign_seg"), ("multimem_allreduce", "multimem_allreduce"), ("peer_allreduce", "peer_allreduce"),
 ]
 
 
@@ -100,7 +102,8 @@ def main():
         fam = family(d["kernel"])
         if fam is None:
             continue
-        a = fam_acc.setdefault(fam, {"bytes": 0.0, "time_us": 0.0, "launches": 0, "names": {}})
+        a = fam_acc.setdefault(fam, {"bytes": 0.0, "time_us": 0.0, "launches": 0, "names": {}, "insts": 0.0})
+        a["insts"] += d.get("warp_insts", 0.0)
         a["bytes"] += (d.get("dram_read_MB", 0.0) + d.get("dram_write_MB", 0.0)) * 1e6
         a["time_us"] += d.get("time_us", 0.0)
         a["launches"] += 1
@@ -108,9 +111,10 @@ def main():
     # number of frames captured = launches of blend_fwd (one per frame)
     frames = max(1, fam_acc.get("blend_fwd", {}).get("launches", 1))
     for fam, a in fam_acc.items():
-        per_launch = fam in ("kmeans_assign", "adam", "mask_iou", "footprint")
+        per_launch = fam in ("kmeans_assign", "kmeans_assign_seg", "adam", "mask_iou", "footprint")
         n = max(1, a["launches"]) if per_launch else frames
         traffic[fam] = {"dram_bytes_per_frame": a["bytes"] / n, "ncu_time_us_per_frame": a["time_us"] / n,
+                        "warp_insts_per_frame": a["insts"] / n,
                         "kernels": a["names"], "frames_captured": n}
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
         json.dump({"source": f"ncu --set full, gpurun_out/{tag}_raster.ncu-rep + {tag}_kmeans.ncu-rep "
