@@ -486,8 +486,11 @@ def raster_headline(cx, a):
     value = frames / (ms / 1e3)
     e2e_value = frames / (median(e2e_times) / 1e3)
     if value < e2e_value * 0.98:
-        raise RuntimeError(f"inconsistent timing: resident {value:.1f} frames/s below end-to-end {e2e_value:.1f} "
-                           f"(repeats {times} vs {e2e_times})")
+        msg = (f"inconsistent timing: resident {value:.1f} frames/s below end-to-end {e2e_value:.1f} "
+               f"(repeats {times} vs {e2e_times})")
+        if frames >= 40 * cx.world and R >= 3:       # a real measurement: refuse to print a line that contradicts itself
+            raise RuntimeError(msg)
+        print("bench.py: " + msg + " -- region too short to judge", file=sys.stderr)
     rep = {"repeats": R, "resident_ms": [round(t, 3) for t in times], "e2e_ms": [round(t, 3) for t in e2e_times],
            "value_min": frames / (max(times) / 1e3), "value_max": frames / (min(times) / 1e3),
            "rule": "value and e2e are the MEDIAN of the repeats; every repeat times exactly `steps` steps"}
