@@ -70,8 +70,9 @@ def parse():
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events in the timed region")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of `steps` steps each; the median is reported")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 2 and 4 legs")
-    ap.add_argument("--grad-allreduce", default="nvls", choices=["nvls", "nccl"],
-                    help="N > 1: sum the gradients with the library's in-switch kernel (GradArena) or with NCCL")
+    ap.add_argument("--grad-allreduce", default="auto", choices=["auto", "nvls", "nccl"],
+                    help="N > 1: sum the gradients with the library's in-switch kernel (GradArena), with NCCL, or "
+                         "(auto) time both and keep the faster")
     return ap.parse_args()
 
 
@@ -276,10 +277,12 @@ class RasterWorkload:
         self._e2e_ready = False
         # N > 1: the step's gradient buffer lives in symmetric memory and is summed by our own in-switch kernel
         self.arena = None
-        if cx.world > 1 and getattr(cx, "grad_allreduce", "nvls") == "nvls":
+        if cx.world > 1 and getattr(cx, "grad_allreduce", "auto") != "nccl":
             from opengaussian_b200 import dist as ogd
             _, span = ogd._flat_layout(self.reduced)
             self.arena = ogd.GradArena(span)
+            if self.arena.buf is None:
+                self.arena = None
 
     def close(self):
         self.zero_grads()
@@ -437,6 +440,30 @@ def raster_headline(cx, a):
     gc.disable()                      # no cyclic-GC pause inside the timed regions
     sampler.start()
     # per-kernel events ride along in the timed region (a.no_profile: separate pass)
+    alt = None
+    if wl.arena is not None and a.grad_allreduce == "auto":
+        # both gradient collectives on the same box: the in-switch kernel (arena installed) and NCCL; keep the faster
+        for _ in range(2):
+            wl.step(i)
+            i += 1
+        t_nvls, i = cx.timed_repeats(wl.step, i, K, max(2, R // 2))
+        wl.zero_grads()
+        wl.arena.enable(False)
+        for _ in range(2):
+            wl.step(i)
+            i += 1
+        t_nccl, i = cx.timed_repeats(wl.step, i, K, max(2, R // 2))
+        use_nvls = median(t_nvls) <= median(t_nccl)
+        alt = {"in_switch_kernel_ms_per_step": median(t_nvls) / K, "nccl_ms_per_step": median(t_nccl) / K,
+               "used": "in-switch kernel" if use_nvls else "nccl"}
+        wl.zero_grads()
+        wl.arena.enable(use_nvls)
+        cx.prefer_nvls = use_nvls
+        if not use_nvls:
+            wl.arena_kind_override = "NCCL all_reduce of the flat gradient buffer (faster than the in-switch kernel here)"
+        for _ in range(2):
+            wl.step(i)
+            i += 1
     _lib.profile_enable(not a.no_profile)
     _lib.profile_read()
     times, i = cx.timed_repeats(wl.step, i, K, R)
@@ -494,6 +521,8 @@ def raster_headline(cx, a):
     rep = {"repeats": R, "resident_ms": [round(t, 3) for t in times], "e2e_ms": [round(t, 3) for t in e2e_times],
            "value_min": frames / (max(times) / 1e3), "value_max": frames / (min(times) / 1e3),
            "rule": "value and e2e are the MEDIAN of the repeats; every repeat times exactly `steps` steps"}
+    if alt is not None:
+        rep["gradient_collective_choice"] = alt
     return wl, stats, prof, sampler.result(), ms, value, e2e_value, rep, exposed
 
 
@@ -640,6 +669,8 @@ def named_config_leg(cx, workload, V, fused_feat, K=8, R=3, label=""):
     """One BASELINE config as a view-parallel fwd+bwd run: frames/s resident, with the exposed collective on N > 1."""
     torch = cx.torch
     wl = RasterWorkload(cx, workload, V, fused_feat=fused_feat, n_views=4)
+    if wl.arena is not None and not getattr(cx, "prefer_nvls", True):
+        wl.arena.enable(False)           # the headline leg found NCCL faster on this box
     i = 0
     for _ in range(3):
         wl.step(i)
@@ -655,7 +686,8 @@ def named_config_leg(cx, workload, V, fused_feat, K=8, R=3, label=""):
         wl.allreduce = True
         res["collective_exposed_ms_per_step"] = ms - median(t_no) / K
         res["allreduce_bytes"] = sum(t.numel() for t in wl.reduced) * 4
-        res["collective_kind"] = wl.arena.kind if wl.arena is not None else None
+        res["collective_kind"] = (wl.arena.kind if (wl.arena is not None and getattr(cx, "prefer_nvls", True))
+                                  else "NCCL all_reduce of the flat gradient buffer")
     wl.close()
     del wl
     torch.cuda.empty_cache()
@@ -738,7 +770,8 @@ def run_ours(a):
     tile_bits = max(1, (tiles - 1).bit_length())
     h2d, d2h = wl.h2d_bytes_per_step(), 4
     n_cams = len(wl.cams)
-    coll_kind = wl.arena.kind if wl.arena is not None else "NCCL all_reduce of the flat gradient buffer"
+    coll_kind = getattr(wl, "arena_kind_override", None) or \
+        (wl.arena.kind if wl.arena is not None else "NCCL all_reduce of the flat gradient buffer")
     wl.close()
     del wl
     torch.cuda.empty_cache()

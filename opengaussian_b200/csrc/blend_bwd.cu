@@ -85,7 +85,9 @@ int blend_bwd_stride(int C, int geom) { return geom ? C + 7 : C; }
 // 4 / PAIRS warps.  More pixels per lane amortise the cross-lane reduction and the per-entry loop
 // overhead (about half of the instructions at PAIRS = 1) at the price of coarser culling.
 // Register cap: with the recursion state trimmed to one scalar per pixel the 3- and 4-channel kernels fit 80
-// registers without spills, which lets 12 CTAs of 64 threads share an SM instead of 10 (measured: -3.5 %).
+// registers without spills, which lets 12 CTAs of 64 threads share an SM instead of 10.  Measured on B200 (ncu,
+// profiles/r2_kernels_full.csv): warps active 28 -> 33 %, issue active 67 -> 70 %, but 7 % more instructions
+// (rematerialisation), so the net is small: 0.517 ms capped vs 0.531 ms uncapped in the same bench run.
 constexpr int bwd_min_blocks(int C, int pairs) { return (pairs == 2 && C <= 4) ? 12 : 1; }
 
 template <int C, bool GEOM, int PAIRS>

@@ -14,6 +14,8 @@
 //      each digit run with coalesced stores.
 // The item count is read from DEVICE memory (n_ptr): the grid is sized for a capacity and CTAs
 // past the end exit, which is what lets ogs_raster_forward run without a host round trip.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ogs {
@@ -74,8 +76,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
 #ifndef RS_MINB
 #define RS_MINB 2
 #endif
-template <typename KeyT, bool LOOKBACK, int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
+template <typename KeyT, bool LOOKBACK, int ITEMS, int MINB = RS_MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
                                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                              const uint32_t* __restrict__ n_ptr, uint32_t cap, int shift, int bits,
                                                              const uint32_t* __restrict__ ghist /*[256] of this pass*/,

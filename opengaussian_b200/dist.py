@@ -158,6 +158,18 @@ class GradArena:
         set_grad_arena(buf)
         _ARENAS[self.device.index] = self
 
+    def enable(self, on: bool):
+        """Installs / removes the arena as the home of the gradient buffer (it stays allocated either way)."""
+        from .rasterizer import set_grad_arena
+        if self.buf is None:
+            return
+        if on:
+            set_grad_arena(self.buf)
+            _ARENAS[self.device.index] = self
+        else:
+            set_grad_arena(None)
+            _ARENAS.pop(self.device.index, None)
+
     def owns(self, flat: Optional[torch.Tensor], span: int) -> bool:
         return (self.buf is not None and flat is not None and flat.data_ptr() == self.buf.data_ptr()
                 and span <= self.buf.numel())
