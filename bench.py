@@ -10,9 +10,9 @@ with NCCL all-reduce when N > 1.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes
-through the public Python API with the per-step inputs (camera + the loss-gradient images that
-stand in for the ground-truth image) copied from pinned host memory and the loss scalar read
-back, inside the timed region.  `--impl reference` times the CPU restatement of the reference
+through the public Python API with the per-step inputs -- every view's camera and fp32 [3,H,W]
+ground-truth image, what the reference moves per step at train.py:377 -- copied from pinned host
+memory, an L1 loss against that image (train.py:384) and the loss scalar read back, inside the timed region.  `--impl reference` times the CPU restatement of the reference
 path (oracle/, OpenMP over all host threads) on the same workload.
 """
 import argparse
@@ -245,8 +245,9 @@ class RasterWorkload:
     """fwd + bwd of V views per rank per step through opengaussian_b200.dist.render_views_backward on a synthetic
     scene of synth.SCENES; gradients to every rasterizer input (`fused_feat`: the 6 ins_feat channels are composited
     in the same pass and get gradients too).  Resident step: inputs live in HBM.  End-to-end step: every view's camera
-    and loss-gradient images come from pinned host memory (double-buffered copy stream) and the step's loss scalar is
-    copied back and read by the host."""
+    and ground-truth image (fp32 [3,H,W], train.py:377) come from pinned host memory (double-buffered copy stream),
+    the loss is L1 against that image (+ the fixed weightings of depth / alpha), and the step's loss scalar is copied
+    back and read by the host."""
 
     def __init__(self, cx, workload, V, streams=1, fused_feat=False, n_views=N_VIEWS):
         import torch
@@ -266,8 +267,10 @@ class RasterWorkload:
         self.bg = torch.zeros(3, device=dev)
         self.C = 9 if fused_feat else 3
         gen = torch.Generator().manual_seed(1234 + cx.rank)
-        self.G_host = [torch.randn(self.C + 2, H, W, generator=gen).pin_memory() for _ in range(2)]
-        self.G = self.G_host[0].to(dev)
+        self.G = torch.randn(self.C + 2, H, W, generator=gen).to(dev)      # resident step: fixed N(0,1) loss gradients
+        # end-to-end step: the per-view host input of the reference's training step is the ground-truth image,
+        # fp32 [3,H,W] (`gt_image = viewpoint_cam.original_image.cuda()`, train.py:377), plus the camera
+        self.gt_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(2)]
         self.settings = [GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, self.bg, 1.0, c.world_view_transform,
                                                        c.full_proj_transform, 3, c.camera_center, False, False)
                          for c in self.cams]
@@ -326,7 +329,7 @@ class RasterWorkload:
         self.cam_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
                                     c.camera_center.reshape(-1)]).cpu().pin_memory() for c in self.cams]
         self.copy_stream = torch.cuda.Stream(dev)
-        self.G_dev = [torch.empty(self.C + 2, H, W, device=dev) for _ in range(2)]
+        self.gt_dev = [torch.empty(3, H, W, device=dev) for _ in range(2)]
         self.cam_dev = [torch.empty(35, device=dev) for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
@@ -346,7 +349,7 @@ class RasterWorkload:
         s = j % 2
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[s])
-            self.G_dev[s].copy_(self.G_host[s], non_blocking=True)
+            self.gt_dev[s].copy_(self.gt_host[s], non_blocking=True)
             self.cam_dev[s].copy_(self.cam_host[j % len(self.cam_host)], non_blocking=True)
             self.ready[s].record(self.copy_stream)
 
@@ -361,9 +364,13 @@ class RasterWorkload:
         cd = self.cam_dev[s]
         rs = GaussianRasterizationSettings(self.H, self.W, c.tanfovx, c.tanfovy, self.bg, 1.0, cd[0:16].view(4, 4),
                                            cd[16:32].view(4, 4), 3, cd[32:35], False, False)
-        outs, gouts = self._grad_outputs(self._call(rs), self.G_dev[s])
-        # loss = <render outputs, staged gradient images> (one dot product per output tensor)
-        loss = sum(torch.dot(o.reshape(-1), g.reshape(-1)) for o, g in zip(outs, gouts))
+        outs, gouts = self._grad_outputs(self._call(rs), self.G)
+        # loss = L1(render, staged ground-truth image) (train.py:384 `l1_loss(image, gt_image)`) + the metric's fixed
+        # N(0,1) weightings of the remaining outputs (features / depth / alpha: resident tensors), so that every
+        # gradient path of the rasterizer runs
+        loss = (outs[0] - self.gt_dev[s]).abs().mean()
+        for o, g in zip(outs[1:], gouts[1:]):
+            loss = loss + torch.dot(o.reshape(-1), g.reshape(-1))
         loss.backward()
         self.consumed[s].record()                   # the staged inputs are free again once the backward has used them
         return loss.detach()
@@ -396,7 +403,7 @@ class RasterWorkload:
             del self._pending
 
     def h2d_bytes_per_step(self):
-        return self.V * ((self.C + 2) * self.H * self.W * 4 + 35 * 4)
+        return self.V * (3 * self.H * self.W * 4 + 35 * 4)
 
     def stats(self):
         """Realised workload statistics of view 0 (untimed): N, visible P, list lengths, interaction counts."""
@@ -602,6 +609,27 @@ def kmeans_leg(cx, a):
           "launches_per_pass": 1, "coarse": out["coarse"], "fine": out["fine"],
           # kept at the top level for continuity with round 1
           "ms_per_pass": out["coarse"]["ms_per_pass"], "gpts_per_s": out["coarse"]["gpts_per_s"], "hbm_frac": out["coarse"]["hbm_frac"]}
+    if world > 1:
+        # the same passes with 5 M points PER RANK (weak scaling): the strong-scaling figures above leave each rank
+        # ~30 us of work per pass, where launch + NVLink round trip are a fixed ~25 us
+        del fa, fb, ids, coarse_ids, leaf_ids
+        torch.cuda.empty_cache()
+        Nw = 5_000_000
+        fa = torch.rand(Nw, 6, device=dev, generator=g2)
+        fb = (torch.rand(Nw, 3, device=dev, generator=g2) - 0.5) * 8
+        ids = torch.empty(Nw, dtype=torch.int64, device=dev)
+        kmeans_assign(fa, fb, 1.0, cen0, ids_out=ids)
+        coarse_ids = ids.clone()
+        leaf_ids = torch.empty(Nw, dtype=torch.int64, device=dev)
+        n_eps = (Nw * world) // 10000 + 1
+        weak = {}
+        for name, fn in (("coarse", coarse_pass), ("fine", fine_pass)):
+            for _ in range(3):
+                fn()
+            ts, _ = cx.timed_repeats(lambda _i: fn(), 0, 20, 3)
+            ms = median(ts) / 20
+            weak[name] = {"ms_per_pass": ms, "gpts_per_s": Nw * world / ms / 1e6}
+        km["weak_scaling"] = dict(weak, points=Nw * world, points_per_rank=Nw)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         # CPU port (oracle/kmeans_oracle.c, scalar C, 1 thread) on BASELINE config 1's 200 k points.  The reference
         # file itself (scene/kmeans_quantize.py under torch CPU) is not on the GPU box; in the build container it
