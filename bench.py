@@ -539,7 +539,8 @@ def issue_roofline(stats, fam_ms, traffic, sm_mhz):
     of the warp-issue peak (148 SMs x 4 schedulers x clock) the kernel sustains inside the timed region."""
     out = {}
     peak_issue = 148 * 4 * (sm_mhz or 1965) * 1e6          # warp instructions per second
-    for fam, inter_key in (("blend_fwd", "interactions_listed"), ("blend_bwd", "interactions_to_last_contributor")):
+    # both kernels walk a pixel's list up to (fwd: one 32-entry batch past) its last contributor
+    for fam, inter_key in (("blend_fwd", "interactions_to_last_contributor"), ("blend_bwd", "interactions_to_last_contributor")):
         t = (traffic or {}).get(fam, {})
         wi = t.get("warp_insts_per_frame")
         if fam not in fam_ms or not wi:
@@ -547,7 +548,9 @@ def issue_roofline(stats, fam_ms, traffic, sm_mhz):
         I = stats[inter_key]
         out[fam] = {"interactions": I, "interactions_kind": inter_key, "warp_insts_per_launch": wi,
                     "warp_insts_per_32_interactions": wi / (I / 32.0), "issue_frac_of_peak": wi / (fam_ms[fam] / 1e3) / peak_issue,
+                    # I * (22 + 2C) flop forward, 3x that backward, against the 74.4 TFLOP/s non-tensor FP32 peak
                     "fp32_floor_ms": I * (22 + 2 * 3) * (1 if fam == "blend_fwd" else 3) / 74.4e12 * 1e3}
+        out[fam]["frac_of_fp32_floor"] = out[fam]["fp32_floor_ms"] / fam_ms[fam]
     return out
 
 
