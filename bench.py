@@ -365,13 +365,11 @@ class RasterWorkload:
         rs = GaussianRasterizationSettings(self.H, self.W, c.tanfovx, c.tanfovy, self.bg, 1.0, cd[0:16].view(4, 4),
                                            cd[16:32].view(4, 4), 3, cd[32:35], False, False)
         outs, gouts = self._grad_outputs(self._call(rs), self.G)
-        # loss = L1(render, staged ground-truth image) (train.py:384 `l1_loss(image, gt_image)`) + the metric's fixed
-        # N(0,1) weightings of the remaining outputs (features / depth / alpha: resident tensors), so that every
-        # gradient path of the rasterizer runs
-        loss = (outs[0] - self.gt_dev[s]).abs().mean()
-        for o, g in zip(outs[1:], gouts[1:]):
-            loss = loss + torch.dot(o.reshape(-1), g.reshape(-1))
-        loss.backward()
+        # loss = L1(render, staged ground-truth image) (train.py:384 `l1_loss(image, gt_image)`, utils/loss_utils.py:17);
+        # the remaining outputs (features / depth / alpha) receive the metric's fixed N(0,1) gradients directly, so
+        # that every gradient path of the rasterizer runs; the scalar read back is the L1 loss
+        loss = torch.nn.functional.l1_loss(outs[0], self.gt_dev[s])
+        torch.autograd.backward([loss] + list(outs[1:]), [None] + list(gouts[1:]))
         self.consumed[s].record()                   # the staged inputs are free again once the backward has used them
         return loss.detach()
 

@@ -230,7 +230,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     BinScratch sc;
     memset(&sc, 0, sizeof sc);
     if (P > 0) {
-        const size_t pw = align_up((size_t)P * 4, 256);
+        const size_t pw = align_up((size_t)(P + 1) * 4, 256);      // offsets carries one extra word: the overflow flag
         sc.cub_temp_bytes = align_up(depth_sort_temp_bytes(P), 256);
         OGS_CUDA(scratch1.alloc(pw * 5 + sc.cub_temp_bytes));
         char* s1 = (char*)scratch1.p;
@@ -261,13 +261,14 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         h = pinned_scalar(fc);
         if (!h) { set_error("cudaMallocHost failed"); return 2; }
         n_ptr = sc.offsets + (P - 1);
-        OGS_CUDA(cudaMemcpyAsync(h, n_ptr, 4, cudaMemcpyDeviceToHost, s));
+        OGS_CUDA(cudaMemcpyAsync(h, n_ptr, 8, cudaMemcpyDeviceToHost, s));     // [N, overflow flag]
         // Capacity speculation: the binning buffers are sized from the running estimate cap_hint and
         // the N-dependent kernels take N from device memory, so emit/sort/blend are queued WITHOUT
         // waiting for the scan; the host reads N only after everything is launched (the scan has long
         // finished by then).  If the estimate was too small the binning + blend are redone (rare).
         if (fc.cap_hint == 0 || in->debug) {
             OGS_CUDA(cudaStreamSynchronize(s));
+            if (h[1]) { set_error("more than 2^32 - 1 (Gaussian, tile) duplicates in one frame: 32-bit offsets overflow"); return -7; }
             N = (int64_t)*h;
             cap = N;
         } else {
@@ -317,6 +318,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         OGS_KERNEL_CHECK("blend_forward", in->debug, s);
         if (!speculative) break;
         OGS_CUDA(cudaEventSynchronize(n_event));
+        if (h[1]) { set_error("more than 2^32 - 1 (Gaussian, tile) duplicates in one frame: 32-bit offsets overflow"); return -7; }
         N = (int64_t)*h;
         speculative = false;
         if (N <= cap) break;

@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_gather_kernel(int P, const ui
                                                                  const uint32_t* __restrict__ tiles, uint32_t* __restrict__ out,
                                                                  uint32_t* tile_state, uint32_t* ticket) {
     __shared__ uint32_t s_tile, s_warp[SC_THREADS / 32], s_excl;
+    __shared__ unsigned long long s_excl64;      // the same prefix in 64 bits: detects a total beyond 2^32 - 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -464,19 +465,28 @@ __global__ void __launch_bounds__(SC_THREADS) scan_gather_kernel(int P, const ui
         if (tid == 0) {
             st[tile] = total | RS_FLAG_AGG;
             s_excl = 0;
+            s_excl64 = 0ull;
         }
         __syncthreads();
         uint32_t part = 0;
+        unsigned long long part64 = 0ull;
         for (uint32_t t = tid; t < tile; t += SC_THREADS) {
             uint32_t x;
             do { x = st[t]; } while (!(x & RS_FLAG_AGG));
             part += x & RS_VAL_MASK;
+            part64 += x & RS_VAL_MASK;
         }
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-        if (lane == 0 && part) atomicAdd(&s_excl, part);
+        for (int m = 16; m >= 1; m >>= 1) {
+            part += __shfl_xor_sync(0xffffffffu, part, m);
+            part64 += __shfl_xor_sync(0xffffffffu, part64, m);
+        }
+        if (lane == 0 && part64) { atomicAdd(&s_excl, part); atomicAdd(&s_excl64, part64); }
     }
     __syncthreads();
+    // the duplicate count and every offset are 32-bit (as upstream's): a frame with more than 2^32 - 1 (Gaussian, tile)
+    // pairs would wrap silently -- raise the flag word behind the offsets instead (out[P]; the host reads it with N)
+    if (tid == 0 && tile == gridDim.x - 1) out[P] = (s_excl64 + total > 0xFFFFFFFFull) ? 1u : 0u;
     const uint32_t off = s_excl + woff + (a - sum);
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; i++) {
