@@ -21,7 +21,7 @@
 namespace ogs {
 
 int radix_sort_pairs_u32(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
-                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second);
+                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second, uint32_t* n_valid);
 int tile_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
                         int bits, void* scratch, cudaStream_t s);
 size_t tile_sort_scratch_bytes(uint64_t capacity);
@@ -29,7 +29,8 @@ void tile_sort_plan(int bits, int* passes, int* bits0);
 uint32_t* tile_sort_pass0_counts(void* scratch);
 size_t radix_scratch_bytes(uint64_t capacity, int passes);
 size_t scan_scratch_bytes(int P);
-int scan_gather(int P, const uint32_t* order, const uint32_t* tiles, uint32_t* out, void* scratch, cudaStream_t s);
+int scan_gather(int P, const uint32_t* n_ptr, const uint32_t* order, const uint32_t* tiles, uint32_t* out, void* scratch,
+                cudaStream_t s);
 
 size_t depth_sort_temp_bytes(int P) {
     const size_t a = radix_scratch_bytes((uint64_t)P, 4) + 256, b = scan_scratch_bytes(P);
@@ -38,21 +39,26 @@ size_t depth_sort_temp_bytes(int P) {
 
 size_t tile_sort_temp_bytes(int64_t cap) { return tile_sort_scratch_bytes((uint64_t)cap); }
 
-__global__ void set_scalar_kernel(uint32_t* p, uint32_t v) { *p = v; }
+__global__ void set_scalar_kernel(uint32_t* p, uint32_t v) { p[0] = v; p[1] = 0u; }
 
+// The culled Gaussians (about half of a typical frame) carry the key 0xFFFFFFFF: the first sort pass drops them, so
+// passes 2-4, the scan and the emit kernel's searches run over the VISIBLE count only (kept on the device: sc.nvis_ptr).
 int depth_sort_and_scan(int P, const GeomPtrs& g, BinScratch& sc, cudaStream_t s, int debug) {
-    // the item count of the depth sort is P itself: park it in the word after the sort scratch
+    // the item count of the first pass is P itself: park it in the word after the sort scratch, the visible count behind it
     uint32_t* n_ptr = (uint32_t*)((char*)sc.cub_temp + radix_scratch_bytes((uint64_t)P, 4));
+    uint32_t* nvis = n_ptr + 1;
     int second = 0;
     set_scalar_kernel<<<1, 1, 0, s>>>(n_ptr, (uint32_t)P);   // (the sort's scratch memset stops short of n_ptr)
     int rc = radix_sort_pairs_u32(sc.dkeys_in, sc.dkeys_out, sc.dvals_in, sc.dvals_out, n_ptr, (uint64_t)P, 0, 32,
-                                  sc.cub_temp, s, &second);
+                                  sc.cub_temp, s, &second, nvis);
     if (rc) return rc;
     if (!second) {   // result landed in the *_in buffers: swap the roles
         uint32_t* t = sc.dkeys_in; sc.dkeys_in = sc.dkeys_out; sc.dkeys_out = t;
         t = sc.dvals_in; sc.dvals_in = sc.dvals_out; sc.dvals_out = t;
     }
-    rc = scan_gather(P, sc.dvals_out, g.tiles, sc.offsets, sc.cub_temp, s);
+    // (the scan reuses the sort's scratch from its start; the two parked words lie behind the sort scratch, out of its way)
+    sc.nvis_ptr = nvis;
+    rc = scan_gather(P, nvis, sc.dvals_out, g.tiles, sc.offsets, sc.cub_temp, s);
     if (rc) return rc;
     OGS_KERNEL_CHECK("depth_sort_and_scan", debug, s);
     return 0;
@@ -71,7 +77,8 @@ __device__ __forceinline__ int imax_(int a, int b) { return a > b ? a : b; }
 // of its entries and writes its column of the [digit][chunk] histogram, so the sort's first pass
 // needs no counting sweep.
 #define EMIT_CHUNK 4096
-__global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, const uint32_t* __restrict__ n_ptr, uint32_t cap,
+__global__ void __launch_bounds__(256) emit_kernel(int P_cap, const uint32_t* __restrict__ nvis_ptr, int gx, int gy,
+                                                   const uint32_t* __restrict__ n_ptr, uint32_t cap,
                                                    const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                                                    const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                                                    uint16_t* __restrict__ tkeys, uint32_t* __restrict__ tvals,
@@ -84,6 +91,7 @@ __global__ void __launch_bounds__(256) emit_kernel(int P, int gx, int gy, const 
     __shared__ uint32_t s_round_end;
     const int t = threadIdx.x;
     const uint32_t N = min(*n_ptr, cap);     // never write past the capacity (an overflow is re-run by the host)
+    const int P = (int)min(*nvis_ptr, (uint32_t)P_cap);   // sorted slots in use: the visible Gaussians
     const uint32_t chunk_lo = blockIdx.x * (uint32_t)EMIT_CHUNK;
     const uint32_t dmask = (1u << bits0) - 1u;
     if (chunk_lo >= N) {
@@ -198,7 +206,7 @@ int emit_sort_ranges(int P, int W, int H, const uint32_t* n_ptr, int64_t cap, co
     uint32_t* v0 = passes == 2 ? point_list : tvals_a;
     uint32_t* v1 = passes == 2 ? tvals_a : point_list;
     prof_begin(PF_EMIT, s);
-    emit_kernel<<<(unsigned)((cap + EMIT_CHUNK - 1) / EMIT_CHUNK), 256, 0, s>>>(P, gx, gy, n_ptr, (uint32_t)cap, sc.dvals_out,
+    emit_kernel<<<(unsigned)((cap + EMIT_CHUNK - 1) / EMIT_CHUNK), 256, 0, s>>>(P, sc.nvis_ptr, gx, gy, n_ptr, (uint32_t)cap, sc.dvals_out,
                                                                                 sc.offsets, g.rec0, g.rec1, k0, v0, bits0,
                                                                                 tile_sort_pass0_counts(sc.cub_temp));
     prof_end(PF_EMIT, s);

@@ -230,7 +230,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     BinScratch sc;
     memset(&sc, 0, sizeof sc);
     if (P > 0) {
-        const size_t pw = align_up((size_t)(P + 1) * 4, 256);      // offsets carries one extra word: the overflow flag
+        const size_t pw = align_up((size_t)(P + 2) * 4, 256);      // offsets carries two extra words: N and the overflow flag
         sc.cub_temp_bytes = align_up(depth_sort_temp_bytes(P), 256);
         OGS_CUDA(scratch1.alloc(pw * 5 + sc.cub_temp_bytes));
         char* s1 = (char*)scratch1.p;
@@ -260,7 +260,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         if (rc) return rc;
         h = pinned_scalar(fc);
         if (!h) { set_error("cudaMallocHost failed"); return 2; }
-        n_ptr = sc.offsets + (P - 1);
+        n_ptr = sc.offsets + P;
         OGS_CUDA(cudaMemcpyAsync(h, n_ptr, 8, cudaMemcpyDeviceToHost, s));     // [N, overflow flag]
         // Capacity speculation: the binning buffers are sized from the running estimate cap_hint and
         // the N-dependent kernels take N from device memory, so emit/sort/blend are queued WITHOUT

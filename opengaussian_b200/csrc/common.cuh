@@ -152,7 +152,9 @@ int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t*
 // binning (binning.cu)
 struct BinScratch {
     uint32_t *dkeys_in, *dvals_in, *dkeys_out, *dvals_out;  // [P]
-    uint32_t* offsets;                                      // [P] inclusive scan in depth order
+    uint32_t* offsets;                                      // [P + 2]: inclusive scan in depth order over the visible
+                                                            // slots, then N and the overflow flag
+    const uint32_t* nvis_ptr;                               // device count of visible Gaussians (= sorted slots in use)
     void* cub_temp; size_t cub_temp_bytes;
 };
 size_t binning_temp_bytes(int P, int64_t N_cap);

@@ -38,14 +38,22 @@ struct RsPasses {
     int bits[4];
 };
 
+// n_valid != NULL ("drop" mode of the depth sort): keys equal to 0xFFFFFFFF -- culled Gaussians -- are neither counted
+// in the digit histograms nor sorted; their complement is counted into *n_valid, the item count of passes 2..4.
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
-                                                             uint32_t cap, RsPasses ps, uint32_t* __restrict__ ghist /*[num][256]*/) {
+                                                             uint32_t cap, RsPasses ps, uint32_t* __restrict__ ghist /*[num][256]*/,
+                                                             uint32_t* __restrict__ n_valid) {
     __shared__ uint32_t s_h[4 * RS_RADIX];
     for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS) s_h[e] = 0;
     __syncthreads();
     const uint32_t n = min(*n_ptr, cap);
+    uint32_t nv = 0;
     auto count = [&](uint32_t k) {
+        if (n_valid) {
+            if (k == 0xFFFFFFFFu) return;
+            nv++;
+        }
 #pragma unroll
         for (int p = 0; p < 4; p++)
             if (p < ps.num) atomicAdd(&s_h[p * RS_RADIX + ((k >> ps.shift[p]) & ((1u << ps.bits[p]) - 1u))], 1u);
@@ -67,6 +75,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
     __syncthreads();
     for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS)
         if (s_h[e]) atomicAdd(&ghist[e], s_h[e]);
+    if (n_valid) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, m);
+        if ((threadIdx.x & 31) == 0 && nv) atomicAdd(n_valid, nv);
+    }
 }
 
 // LOOKBACK = true : onesweep (ticketed tiles, decoupled look-back over tile_state[tile][256]).
@@ -76,8 +89,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
 #ifndef RS_MINB
 #define RS_MINB 2
 #endif
-template <typename KeyT, bool LOOKBACK, int ITEMS, int MINB = RS_MINB>
-__global__ void __launch_bounds__(RS_THREADS, MINB) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
+// DROP = true (first pass of the depth sort): items whose key is 0xFFFFFFFF are treated like items past the end -- they
+// get no rank and are not written -- so the output holds the valid items only, in stable order.
+template <typename KeyT, bool LOOKBACK, int ITEMS, bool DROP = false>
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
                                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                              const uint32_t* __restrict__ n_ptr, uint32_t cap, int shift, int bits,
                                                              const uint32_t* __restrict__ ghist /*[256] of this pass*/,
@@ -88,7 +103,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) rs_pass_kernel(const KeyT* _
     __shared__ uint32_t s_gbase[RS_RADIX];           // global position of local sorted slot 0 of the digit
     __shared__ KeyT s_keys[TILE];
     __shared__ uint32_t s_vals[TILE];
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_tile_valid;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (LOOKBACK && tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) rs_pass_kernel(const KeyT* _
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = wbase + i * 32 + lane;
-        const bool valid = idx < n;
+        const bool valid = idx < n && (!DROP || key[i] != 0xFFFFFFFFu);
         const uint32_t d = valid ? ((key[i] >> shift) & dmask) : 0xFFFFFFFFu;
         // lanes holding the same digit: one ballot per digit bit.  (MATCH.ANY costs one round per
         // DISTINCT value in the warp, and here nearly all 32 digits differ.)
@@ -179,6 +194,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) rs_pass_kernel(const KeyT* _
             if (w < warp) { oa += s_wa[w]; ob += s_wb[w]; }
         dstart = oa + a - count;
         dbase = ob + b - gtot;
+        if (DROP && tid == RS_THREADS - 1) s_tile_valid = dstart + count;   // items of this tile that take part
     }
     // ---- global offset of this tile's digit `tid`: precomputed, or decoupled look-back ----
     if (!LOOKBACK) {
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) rs_pass_kernel(const KeyT* _
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = wbase + i * 32 + lane;
-        if (idx < n) {
+        if (idx < n && (!DROP || key[i] != 0xFFFFFFFFu)) {
             const uint32_t d = (key[i] >> shift) & dmask;
             const uint32_t pos = s_dstart[d] + s_wh[warp * RS_RADIX + d] + rank[i];
             s_keys[pos] = (KeyT)key[i];
@@ -230,7 +246,8 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) rs_pass_kernel(const KeyT* _
     }
     __syncthreads();
     // ---- coalesced write-out of the digit runs ----
-    for (uint32_t j = tid; j < tile_n; j += RS_THREADS) {
+    const uint32_t tile_out = DROP ? s_tile_valid : tile_n;
+    for (uint32_t j = tid; j < tile_out; j += RS_THREADS) {
         const KeyT k = s_keys[j];
         const uint32_t d = ((uint32_t)k >> shift) & dmask;
         const uint32_t dst = s_gbase[d] + j;
@@ -245,9 +262,12 @@ size_t radix_scratch_bytes(uint64_t capacity, int passes) {
     return align_up((size_t)4 * RS_RADIX * 4, 256) + 256 + (size_t)passes * tiles * RS_RADIX * 4;
 }
 
+// n_valid != NULL: drop mode -- keys equal to 0xFFFFFFFF are removed by the first pass; *n_valid (zero on entry, device
+// memory) receives the number of remaining items, which is the item count of the later passes and of the result.
 template <typename KeyT>
 static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
-                              int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
+                              int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second,
+                              uint32_t* n_valid = nullptr) {
     RsPasses ps;
     ps.num = 0;
     for (int b = begin_bit; b < end_bit && ps.num < 4; b += 8) {
@@ -273,14 +293,19 @@ static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, co
     int hist_grid = (int)((capacity + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
     if (hist_grid > OGS_NUM_SMS * 4) hist_grid = OGS_NUM_SMS * 4;
     if (hist_grid < 1) hist_grid = 1;
-    rs_hist_kernel<KeyT><<<hist_grid, RS_THREADS, 0, s>>>(k0, n_ptr, (uint32_t)capacity, ps, ghist);
+    rs_hist_kernel<KeyT><<<hist_grid, RS_THREADS, 0, s>>>(k0, n_ptr, (uint32_t)capacity, ps, ghist, n_valid);
     KeyT* ka = k0; KeyT* kb = k1;
     uint32_t* va = v0; uint32_t* vb = v1;
     const unsigned grid = (unsigned)((capacity + TILE - 1) / TILE);
     for (int p = 0; p < ps.num; p++) {
-        rs_pass_kernel<KeyT, true, ITEMS><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_ptr, (uint32_t)capacity, ps.shift[p],
-                                                                      ps.bits[p], ghist + p * RS_RADIX,
-                                                                      states + (size_t)p * tiles * RS_RADIX, tickets + p, 0u);
+        if (n_valid && p == 0)
+            rs_pass_kernel<KeyT, true, ITEMS, true><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_ptr, (uint32_t)capacity, ps.shift[p],
+                                                                                ps.bits[p], ghist + p * RS_RADIX,
+                                                                                states + (size_t)p * tiles * RS_RADIX, tickets + p, 0u);
+        else
+            rs_pass_kernel<KeyT, true, ITEMS><<<grid, RS_THREADS, 0, s>>>(ka, kb, va, vb, n_valid ? n_valid : n_ptr, (uint32_t)capacity,
+                                                                          ps.shift[p], ps.bits[p], ghist + p * RS_RADIX,
+                                                                          states + (size_t)p * tiles * RS_RADIX, tickets + p, 0u);
         KeyT* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;
     }
@@ -291,8 +316,9 @@ static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, co
 }
 
 int radix_sort_pairs_u32(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
-                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second) {
-    return radix_sort_pairs_t<uint32_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second);
+                         int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second, uint32_t* n_valid) {
+    return radix_sort_pairs_t<uint32_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second,
+                                        n_valid);
 }
 // ---------------------------------------------------------------------------------------------
 // Tile sort (N entries, 16-bit tile ids, <= 2 digit passes): counting passes WITHOUT look-back.
@@ -424,22 +450,33 @@ int tile_sort_pairs_u16(uint16_t* k0, uint16_t* k1, uint32_t* v0, uint32_t* v1, 
 #define SC_ITEMS 8
 #define SC_TILE (SC_THREADS * SC_ITEMS)
 
-__global__ void __launch_bounds__(SC_THREADS) scan_gather_kernel(int P, const uint32_t* __restrict__ order,
+// Inclusive scan of tiles[order[i]] over the first n = *n_ptr sorted slots (n <= P: the visible Gaussians).  The grand
+// total -- N, the number of (Gaussian, tile) duplicates -- goes to out[P] and an overflow flag to out[P + 1]: the count
+// and every offset are 32-bit (as upstream's), so a frame with more than 2^32 - 1 duplicates would wrap silently; the
+// prefix is carried in 64 bits as well and the flag is raised instead.
+__global__ void __launch_bounds__(SC_THREADS) scan_gather_kernel(int P, const uint32_t* __restrict__ n_ptr,
+                                                                 const uint32_t* __restrict__ order,
                                                                  const uint32_t* __restrict__ tiles, uint32_t* __restrict__ out,
                                                                  uint32_t* tile_state, uint32_t* ticket) {
     __shared__ uint32_t s_tile, s_warp[SC_THREADS / 32], s_excl;
-    __shared__ unsigned long long s_excl64;      // the same prefix in 64 bits: detects a total beyond 2^32 - 1
+    __shared__ unsigned long long s_excl64;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const int base = (int)tile * SC_TILE + tid * SC_ITEMS;
+    const uint32_t n = min(*n_ptr, (uint32_t)P);
+    if (n == 0) {
+        if (tile == 0 && tid == 0) { out[P] = 0u; out[P + 1] = 0u; }
+        return;
+    }
+    if (tile * (uint32_t)SC_TILE >= n) return;          // tiles are ticketed: nobody ever waits on a tile past the end
+    const uint32_t base = tile * (uint32_t)SC_TILE + tid * SC_ITEMS;
     uint32_t v[SC_ITEMS];
     uint32_t sum = 0;
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; i++) {
-        const int idx = base + i;
-        v[i] = idx < P ? tiles[order[idx]] : 0u;
+        const uint32_t idx = base + i;
+        v[i] = idx < n ? tiles[order[idx]] : 0u;
         sum += v[i];
         v[i] = sum;
     }
@@ -484,26 +521,28 @@ __global__ void __launch_bounds__(SC_THREADS) scan_gather_kernel(int P, const ui
         if (lane == 0 && part64) { atomicAdd(&s_excl, part); atomicAdd(&s_excl64, part64); }
     }
     __syncthreads();
-    // the duplicate count and every offset are 32-bit (as upstream's): a frame with more than 2^32 - 1 (Gaussian, tile)
-    // pairs would wrap silently -- raise the flag word behind the offsets instead (out[P]; the host reads it with N)
-    if (tid == 0 && tile == gridDim.x - 1) out[P] = (s_excl64 + total > 0xFFFFFFFFull) ? 1u : 0u;
+    if (tid == 0 && tile == (n - 1) / (uint32_t)SC_TILE) {
+        out[P] = s_excl + total;
+        out[P + 1] = (s_excl64 + total > 0xFFFFFFFFull) ? 1u : 0u;
+    }
     const uint32_t off = s_excl + woff + (a - sum);
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; i++) {
-        const int idx = base + i;
-        if (idx < P) out[idx] = off + v[i];
+        const uint32_t idx = base + i;
+        if (idx < n) out[idx] = off + v[i];
     }
 }
 
 size_t scan_scratch_bytes(int P) { return ((size_t)(P + SC_TILE - 1) / SC_TILE + 2) * 4 + 256; }
 
-int scan_gather(int P, const uint32_t* order, const uint32_t* tiles, uint32_t* out, void* scratch, cudaStream_t s) {
+int scan_gather(int P, const uint32_t* n_ptr, const uint32_t* order, const uint32_t* tiles, uint32_t* out, void* scratch,
+                cudaStream_t s) {
     if (P <= 0) return 0;
     const int ntiles = (P + SC_TILE - 1) / SC_TILE;
     OGS_CUDA(cudaMemsetAsync(scratch, 0, scan_scratch_bytes(P), s));
     uint32_t* ticket = (uint32_t*)scratch;
     uint32_t* states = (uint32_t*)((char*)scratch + 256);
-    scan_gather_kernel<<<ntiles, SC_THREADS, 0, s>>>(P, order, tiles, out, states, ticket);
+    scan_gather_kernel<<<ntiles, SC_THREADS, 0, s>>>(P, n_ptr, order, tiles, out, states, ticket);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "scan_gather");
     return 0;
