@@ -258,13 +258,13 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_pass_kernel(const KeyT
 
 // scratch layout for one sort: [ghist 4*256][ticket 4 (one per pass) + pad][tile_state passes * tiles * 256]
 size_t radix_scratch_bytes(uint64_t capacity, int passes) {
-    const size_t tiles = (size_t)((capacity + RS_TILE_SMALL - 1) / RS_TILE_SMALL) + 1;
+    const size_t tiles = (size_t)((capacity + RS_THREADS * 4 - 1) / (RS_THREADS * 4)) + 1;      // smallest tile variant
     return align_up((size_t)4 * RS_RADIX * 4, 256) + 256 + (size_t)passes * tiles * RS_RADIX * 4;
 }
 
 // n_valid != NULL: drop mode -- keys equal to 0xFFFFFFFF are removed by the first pass; *n_valid (zero on entry, device
 // memory) receives the number of remaining items, which is the item count of the later passes and of the result.
-template <typename KeyT>
+template <typename KeyT, int ITEMS>
 static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
                               int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second,
                               uint32_t* n_valid = nullptr) {
@@ -282,14 +282,13 @@ static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, co
         ps.shift[ps.num - 1] = ps.shift[ps.num - 2] + ps.bits[ps.num - 2];
         ps.bits[ps.num - 1] = tot - ps.bits[ps.num - 2];
     }
-    constexpr int ITEMS = sizeof(KeyT) == 4 ? RS_ITEMS_SMALL : RS_ITEMS;
     constexpr int TILE = RS_THREADS * ITEMS;
-    const size_t tiles = (size_t)((capacity + RS_TILE_SMALL - 1) / RS_TILE_SMALL) + 1;
+    const size_t tiles = (size_t)((capacity + TILE - 1) / TILE) + 1;
     char* base = (char*)scratch;
     uint32_t* ghist = (uint32_t*)base;
     uint32_t* tickets = (uint32_t*)(base + align_up((size_t)4 * RS_RADIX * 4, 256));
     uint32_t* states = (uint32_t*)(base + align_up((size_t)4 * RS_RADIX * 4, 256) + 256);
-    OGS_CUDA(cudaMemsetAsync(scratch, 0, radix_scratch_bytes(capacity, ps.num), s));
+    OGS_CUDA(cudaMemsetAsync(scratch, 0, align_up((size_t)4 * RS_RADIX * 4, 256) + 256 + (size_t)ps.num * tiles * RS_RADIX * 4, s));
     int hist_grid = (int)((capacity + RS_THREADS * 8 - 1) / (RS_THREADS * 8));
     if (hist_grid > OGS_NUM_SMS * 4) hist_grid = OGS_NUM_SMS * 4;
     if (hist_grid < 1) hist_grid = 1;
@@ -317,8 +316,13 @@ static int radix_sort_pairs_t(KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, co
 
 int radix_sort_pairs_u32(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, const uint32_t* n_ptr, uint64_t capacity,
                          int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* result_in_second, uint32_t* n_valid) {
-    return radix_sort_pairs_t<uint32_t>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second,
-                                        n_valid);
+    static const int env_items = getenv("OGS_RS_ITEMS") ? atoi(getenv("OGS_RS_ITEMS")) : RS_ITEMS_SMALL;   // tuning knob
+    if (env_items == 4)
+        return radix_sort_pairs_t<uint32_t, 4>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second, n_valid);
+    if (env_items == 8)
+        return radix_sort_pairs_t<uint32_t, 8>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second, n_valid);
+    return radix_sort_pairs_t<uint32_t, 16>(k0, k1, v0, v1, n_ptr, capacity, begin_bit, end_bit, scratch, s, result_in_second,
+                                            n_valid);
 }
 // ---------------------------------------------------------------------------------------------
 // Tile sort (N entries, 16-bit tile ids, <= 2 digit passes): counting passes WITHOUT look-back.

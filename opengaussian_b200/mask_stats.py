@@ -81,7 +81,9 @@ class _MaskMean(torch.autograd.Function):
 
 def mask_feature_mean(feat_map, gt_masks, image_mask=None, return_var=False):
     """Average instance feature inside each mask: ``[num_mask, C]``; with ``return_var`` also the
-    per-mask variance ``[num_mask]`` and pixel count ``[num_mask]`` (reference :240-283)."""
+    per-mask variance ``[num_mask]`` and pixel count ``[num_mask]`` (reference :240-283).  The mean is
+    differentiable; the variance carries NO gradient (the reference's only ``return_var=True`` call site,
+    train.py:689, runs inside the ``torch.no_grad()`` block of train.py:297)."""
     mean, counts = _MaskMean.apply(feat_map, gt_masks, image_mask)
     if not return_var:
         return mean

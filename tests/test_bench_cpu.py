@@ -47,3 +47,31 @@ def test_algorithmic_bytes_worked_example():
     assert d["tile_sort"] == 8_000_000 * 12 * 2
     total = sum(d.values())
     assert 1.5e9 < total < 3.2e9                      # the survey's 3.0 GB uses 6 passes of a 64-bit sort
+
+
+def test_bench_helpers_and_flat_layout():
+    """Pure-host pieces of the bench and of the multi-GPU plumbing: the median, the issue roofline arithmetic, the
+    rank-invariant gradient layout and the fixed-point bit budget of the exact centroid sums."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import bench
+    from opengaussian_b200 import dist as ogd
+    from opengaussian_b200.kmeans_quantize import fixed_point_bits
+    assert bench.median([3.0, 1.0, 2.0]) == 2.0 and bench.median([4.0, 1.0, 2.0, 3.0]) == 2.5
+    stats = {"interactions_to_last_contributor": 3_200_000, "interactions_listed": 9_000_000}
+    traffic = {"blend_bwd": {"warp_insts_per_frame": 3.2e6}, "blend_fwd": {"warp_insts_per_frame": 1.6e6}}
+    iss = bench.issue_roofline(stats, {"blend_bwd": 0.5, "blend_fwd": 0.25}, traffic, 2000)
+    assert abs(iss["blend_bwd"]["warp_insts_per_32_interactions"] - 32.0) < 1e-9
+    assert abs(iss["blend_bwd"]["issue_frac_of_peak"] - 3.2e6 / 0.5e-3 / (148 * 4 * 2000e6)) < 1e-12
+    assert abs(iss["blend_fwd"]["fp32_floor_ms"] * 3 - iss["blend_bwd"]["fp32_floor_ms"]) < 1e-12
+    # gradient layout: a function of the shapes only, 64-float aligned slices, span ends with the last tensor
+    ps = [torch.zeros(10, 3), torch.zeros(7), torch.zeros(5, 16, 3)]
+    offs, span = ogd._flat_layout(ps)
+    assert offs == [0, 64, 128] and span == 128 + 240
+    # fixed-point budget: |x| * 2^bits < 2^31 and N * |x| * 2^bits < 2^62
+    assert fixed_point_bits(5_000_000, 0.999) == 30
+    assert fixed_point_bits(5_000_000, 1.0) == 30 and fixed_point_bits(5_000_000, 2.5) == 29
+    assert fixed_point_bits(2 ** 31, 1000.0) == 20
+    for n, m in ((10, 1e-3), (5_000_000, 7.3), (2 ** 33, 100.0)):
+        b = fixed_point_bits(n, m)
+        assert m * 2.0 ** b < 2.0 ** 31 and n * m * 2.0 ** b < 2.0 ** 62
