@@ -772,9 +772,9 @@ def comparator_leg(cx, a):
     if not os.path.exists(cmp.COMPARATOR):
         return {"unavailable": "baseline/_build/libogs_upstream_structure.so not built (python baseline/build_comparator.py)"}
     gs, cams = synth.make_scene(a.workload, n_views=2)
-    frame = cmp.frame_comparison(gs, cams[0], cx.dev, iters=5, warmup=2)
+    frame = cmp.frame_comparison(gs, cams[0], cx.dev, iters=10, warmup=3)
     gs, cams = synth.make_scene("scannet_1m_1296x968", n_views=2)
-    st1 = cmp.stage1_comparison(gs, cams[0], cx.dev, iters=5, warmup=2)
+    st1 = cmp.stage1_comparison(gs, cams[0], cx.dev, iters=8, warmup=2)
     return {"frames_per_s": frame["upstream_structure"]["frames_per_s"], "product_frames_per_s_same_driver": frame["product"]["frames_per_s"],
             "ratio": frame["speedup"], "workload": a.workload,
             "stage1_step_rasterizer_work": dict(st1, workload="scannet_1m_1296x968",
