@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libogs_b200.so")
+LIB_PATH = os.environ.get("OGS_LIB_PATH") or os.path.join(_HERE, "csrc", "libogs_b200.so")   # env: developer A/B builds
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p)
 _fp = C.c_void_p

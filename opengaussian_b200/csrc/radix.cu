@@ -30,7 +30,9 @@ namespace ogs {
 #define RS_FLAG_AGG 0x40000000u
 #define RS_FLAG_INC 0x80000000u
 #define RS_VAL_MASK 0x3FFFFFFFu
+#ifndef RS_LB
 #define RS_LB 32   // predecessor tiles read per look-back round trip (independent loads in flight)
+#endif
 
 struct RsPasses {
     int num;
@@ -48,12 +50,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
     for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS) s_h[e] = 0;
     __syncthreads();
     const uint32_t n = min(*n_ptr, cap);
-    uint32_t nv = 0;
+    // drop mode: dropped keys are counted like any other (their digit is 0xFF in every pass) and taken out of the
+    // 0xFF bins once per CTA at the end -- the hot loop only gains a compare and an add
+    uint32_t ndrop = 0;
     auto count = [&](uint32_t k) {
-        if (n_valid) {
-            if (k == 0xFFFFFFFFu) return;
-            nv++;
-        }
+        ndrop += (k == 0xFFFFFFFFu) ? 1u : 0u;
 #pragma unroll
         for (int p = 0; p < 4; p++)
             if (p < ps.num) atomicAdd(&s_h[p * RS_RADIX + ((k >> ps.shift[p]) & ((1u << ps.bits[p]) - 1u))], 1u);
@@ -73,13 +74,21 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
         for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) count((uint32_t)keys[i]);
     }
     __syncthreads();
+    if (n_valid) {
+        __shared__ uint32_t s_drop;
+        if (threadIdx.x == 0) s_drop = 0;
+        __syncthreads();
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) ndrop += __shfl_xor_sync(0xffffffffu, ndrop, m);
+        if ((threadIdx.x & 31) == 0 && ndrop) atomicAdd(&s_drop, ndrop);
+        __syncthreads();
+        if ((int)threadIdx.x < ps.num) s_h[threadIdx.x * RS_RADIX + ((1u << ps.bits[threadIdx.x]) - 1u)] -= s_drop;
+        // *n_valid = n - (all dropped keys): CTA 0 contributes n, every CTA takes its dropped keys off (mod 2^32)
+        if (threadIdx.x == 0) atomicAdd(n_valid, (blockIdx.x == 0 ? n : 0u) - s_drop);
+        __syncthreads();
+    }
     for (int e = threadIdx.x; e < ps.num * RS_RADIX; e += RS_THREADS)
         if (s_h[e]) atomicAdd(&ghist[e], s_h[e]);
-    if (n_valid) {
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, m);
-        if ((threadIdx.x & 31) == 0 && nv) atomicAdd(n_valid, nv);
-    }
 }
 
 // LOOKBACK = true : onesweep (ticketed tiles, decoupled look-back over tile_state[tile][256]).

@@ -294,3 +294,39 @@ def test_fused_lloyd_pass_equals_separate_kernels():
             assert float((ids != ref_ids).float().mean()) <= 1e-4
         assert torch.allclose(cen, ref_c, rtol=1e-5, atol=1e-6)
         assert torch.allclose(state, ref_state, rtol=1e-5, atol=1e-7)
+
+
+def test_peer_comm_single_rank_and_empty_shard():
+    """The NVLink peer all-reduce with ONE rank is the identity (push into the own inbox, wait on the own flag, sum one
+    slot) -- this runs the very kernel the multi-GPU path uses; and a Lloyd pass over an EMPTY shard still takes part
+    in the collective and applies the centre update (0 members -> centre 0 / eps)."""
+    import ctypes as C
+    from opengaussian_b200 import _lib
+    L = _lib.lib()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    comm, handle = C.c_void_p(), (C.c_char * 64)()
+    _lib.check(L.ogs_peer_comm_create(0, 1, 4480 * 8 + 256, C.byref(comm), handle), "ogs_peer_comm_create")
+    _lib.check(L.ogs_peer_comm_connect(comm, bytes(handle)), "ogs_peer_comm_connect")
+    try:
+        x = torch.randn(640, device="cuda")
+        y = torch.randint(-2 ** 40, 2 ** 40, (4480,), device="cuda")
+        x0, y0 = x.clone(), y.clone()
+        for _ in range(5):                                   # consecutive calls alternate the inbox parity
+            _lib.check(L.ogs_peer_allreduce(comm, x.data_ptr(), x.numel(), 0, stream), "ogs_peer_allreduce")
+            _lib.check(L.ogs_peer_allreduce(comm, y.data_ptr(), y.numel(), 1, stream), "ogs_peer_allreduce")
+        assert L.ogs_peer_comm_error(comm, stream) == 0
+        assert torch.equal(x, x0) and torch.equal(y, y0)
+        assert L.ogs_peer_allreduce(comm, x.data_ptr(), 1 << 20, 0, stream) != 0      # larger than the slots: refused
+        # empty shard through the fused pass, with the communicator in the loop
+        k, D = 8, 9
+        cen = torch.rand(k, D, device="cuda")
+        state = torch.full((k,), 1e-6, device="cuda")
+        ws = torch.zeros((L.ogs_kmeans_lloyd_workspace_bytes(k, D) + 3) // 4, dtype=torch.int32, device="cuda")
+        rc = L.ogs_kmeans_lloyd_pass(0, None, 6, None, 3, 1.0, cen.data_ptr(), k, k, None, -1, 0, None, state.data_ptr(),
+                                     2e-6, comm, ws.data_ptr(), stream)
+        _lib.check(rc, "ogs_kmeans_lloyd_pass")
+        torch.cuda.synchronize()
+        assert float(cen.abs().max()) == 0.0 and torch.allclose(state, torch.full((k,), 3e-6, device="cuda"))
+        assert L.ogs_peer_comm_error(comm, stream) == 0
+    finally:
+        L.ogs_peer_comm_destroy(comm)
