@@ -270,7 +270,8 @@ class RasterWorkload:
         self.G = torch.randn(self.C + 2, H, W, generator=gen).to(dev)      # resident step: fixed N(0,1) loss gradients
         # end-to-end step: the per-view host input of the reference's training step is the ground-truth image,
         # fp32 [3,H,W] (`gt_image = viewpoint_cam.original_image.cuda()`, train.py:377), plus the camera
-        self.gt_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(2)]
+        self.NS = 3          # staging slots: with the step's one-view lookahead two views are in flight
+        self.gt_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(self.NS)]
         self.settings = [GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, self.bg, 1.0, c.world_view_transform,
                                                        c.full_proj_transform, 3, c.camera_center, False, False)
                          for c in self.cams]
@@ -326,27 +327,28 @@ class RasterWorkload:
     # ---- end to end ----
     def _e2e_setup(self):
         torch, dev, H, W = self.cx.torch, self.cx.dev, self.H, self.W
+        NS = self.NS
         self.cam_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
                                     c.camera_center.reshape(-1)]).cpu().pin_memory() for c in self.cams]
         self.copy_stream = torch.cuda.Stream(dev)
-        self.gt_dev = [torch.empty(3, H, W, device=dev) for _ in range(2)]
-        self.cam_dev = [torch.empty(35, device=dev) for _ in range(2)]
-        self.ready = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.gt_dev = [torch.empty(3, H, W, device=dev) for _ in range(NS)]
+        self.cam_dev = [torch.empty(35, device=dev) for _ in range(NS)]
+        self.ready = [torch.cuda.Event() for _ in range(NS)]
+        self.consumed = [torch.cuda.Event() for _ in range(NS)]
         self.loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.loss_ready = [torch.cuda.Event() for _ in range(2)]
         self.losses = []
-        for s in range(2):
+        for s in range(NS):
             self.consumed[s].record()
         self._staged_upto = -1
         self._e2e_ready = True
 
-    def _stage(self, j):        # async H2D of view j's inputs on the copy stream (double buffered)
+    def _stage(self, j):        # async H2D of view j's inputs on the copy stream (NS rotating slots)
         torch = self.cx.torch
         if j <= self._staged_upto:
             return
         self._staged_upto = j
-        s = j % 2
+        s = j % self.NS
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[s])
             self.gt_dev[s].copy_(self.gt_host[s], non_blocking=True)
@@ -354,9 +356,10 @@ class RasterWorkload:
             self.ready[s].record(self.copy_stream)
 
     def _e2e_view(self, j):
+        """Forward of view j from staged inputs; the backward is issued by render_views_backward (one view later)."""
         from opengaussian_b200.rasterizer import GaussianRasterizationSettings
         torch = self.cx.torch
-        s = j % 2
+        s = j % self.NS
         self._stage(j)
         torch.cuda.current_stream().wait_event(self.ready[s])
         self._stage(j + 1)                          # the next view's inputs travel while this one is rendered
@@ -369,9 +372,8 @@ class RasterWorkload:
         # the remaining outputs (features / depth / alpha) receive the metric's fixed N(0,1) gradients directly, so
         # that every gradient path of the rasterizer runs; the scalar read back is the L1 loss
         loss = torch.nn.functional.l1_loss(outs[0], self.gt_dev[s])
-        torch.autograd.backward([loss] + list(outs[1:]), [None] + list(gouts[1:]))
-        self.consumed[s].record()                   # the staged inputs are free again once the backward has used them
-        return loss.detach()
+        return {"outputs": [loss] + list(outs[1:]), "grads": [None] + list(gouts[1:]), "loss": loss.detach(),
+                "after": self.consumed[s].record}   # the staged inputs are free again once the backward has used them
 
     def e2e_step(self, i):
         """V views from pinned host inputs, one gradient all-reduce, and the step's loss copied to pinned host

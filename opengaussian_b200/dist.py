@@ -377,7 +377,7 @@ def _side_streams(device, n):
 
 def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.Tensor], group=None,
                           already_split: bool = False, streams: int = 1,
-                          fuse_accumulate: bool = True, reduce: bool = True) -> Optional[torch.Tensor]:
+                          fuse_accumulate: bool = True, reduce: bool = True, lookahead: int = 1) -> Optional[torch.Tensor]:
     """One view-parallel step: this rank renders ITS views (`render_loss(view) -> scalar loss`),
     backpropagates, and the parameter gradients of all ranks are summed.  Equivalent to one
     process rendering every view and summing the losses.
@@ -389,22 +389,35 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
     across streams); the caller's stream waits for every side stream before the all-reduce.
     ``fuse_accumulate`` lets the rasterizer's backward add the 2nd..Vth view's gradients straight into the
     parameters' existing ``.grad`` inside its kernel (rasterizer.fuse_grad_accumulation) when the parameters
-    are fed to the rasterizer directly (leaf inputs, e.g. the raw-parameter path)."""
+    are fed to the rasterizer directly (leaf inputs, e.g. the raw-parameter path).
+    ``lookahead = 1`` (default) issues the forward of view v+1 BEFORE the backward of view v (forwards and backwards
+    each stay in view order, so the gradients are summed in the same order): the rasterizer's forward makes the host
+    wait for the frame's duplicate count, and with the previous view's backward still to be queued behind it the GPU
+    always has more than a millisecond of work in its queue while the host catches up (without it the queue holds
+    0.45 ms at that point and runs dry whenever the host needs longer).  Costs one extra forward state in memory."""
     from .rasterizer import fuse_grad_accumulation
     mine = views if already_split else split_views(views, group)
     params = list(params)
     total = None
 
-    def run(v):
-        """render_loss may return a scalar loss, (outputs, grad_outputs) to be back-propagated as is, or
-        an already back-propagated (detached) loss."""
-        res = render_loss(v)
+    def finish(res):
+        """render_loss may return a scalar loss, (outputs, grad_outputs) to be back-propagated as is, an already
+        back-propagated (detached) loss, or a dict {"outputs", "grads", "loss" (detached, optional), "after"
+        (callable run once the backward has been queued, optional)}."""
+        if isinstance(res, dict):
+            torch.autograd.backward(res["outputs"], res["grads"])
+            if res.get("after") is not None:
+                res["after"]()
+            return res.get("loss")
         if isinstance(res, tuple):
             torch.autograd.backward(res[0], res[1])
             return None
         if res.requires_grad:
             res.backward()
         return res.detach()
+
+    def run(v):
+        return finish(render_loss(v))
 
     use_streams = streams > 1 and len(mine) > 1 and params and params[0].is_cuda
     if use_streams:
@@ -426,11 +439,19 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
             p_.record_stream(cur)
             total = p_ if total is None else total + p_
     else:
-        for v in mine:
-            with fuse_grad_accumulation(fuse_accumulate):
-                part = run(v)
-            if part is not None:
-                total = part if total is None else total + part
+        pending = []                      # forwards whose backward has not been issued yet (at most `lookahead`)
+        with fuse_grad_accumulation(fuse_accumulate):
+            for v in list(mine) + [None] * max(0, lookahead):
+                if v is not None:
+                    pending.append(render_loss(v))
+                if pending and (v is None or len(pending) > max(0, lookahead)):
+                    part = finish(pending.pop(0))
+                    if part is not None:
+                        total = part if total is None else total + part
+            while pending:
+                part = finish(pending.pop(0))
+                if part is not None:
+                    total = part if total is None else total + part
     r, w = world(group)
     if not reduce:          # measurement aid: the step without its collectives (bench.py's exposed-collective figure)
         return total
