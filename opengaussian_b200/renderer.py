@@ -84,11 +84,22 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
            fused=True):
     """Render the scene.  Background tensor (bg_color) must be on GPU!"""
     xyz = pc.get_xyz
-    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    # Screen-space gradient sink (reference :45): its .grad feeds the densification statistics (train.py:598,
+    # scene/gaussian_model.py:512-514), which only exist while the geometry trains.  From stage 1 on OpenGaussian
+    # detaches the geometry (train.py:431-436); asking the rasterizer for dL/dmeans2D there forces the FULL geometry
+    # backward (blend moments + preprocess chain, ~0.45 ms per step at 1 M Gaussians) for a tensor nobody reads.  So the
+    # sink tracks gradients only when the positions do (or when pipe.viewspace_grad = True); otherwise it is a plain
+    # zero tensor whose .grad is zeros, so that code reading viewspace_points.grad keeps working.
+    track_vs = bool(xyz.requires_grad or getattr(pipe, "viewspace_grad", False))
+    if track_vs:
+        screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
+    else:
+        screenspace_points = torch.zeros_like(xyz)
+        screenspace_points.grad = torch.zeros_like(xyz)
 
     tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
     tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)

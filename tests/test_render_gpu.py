@@ -304,3 +304,29 @@ def test_render_vs_reference_golden(name):
         frac, worst = grad_violations(model._ins_feat.grad.cpu().numpy(), gold[f"{name}/grad_ins_feat"])
         print(f"{name}: dL/d_ins_feat vs the reference's autograd: violating fraction {frac:.2e}, worst {worst:.3f}")
         assert frac == 0.0
+
+
+def test_frozen_geometry_skips_the_screen_space_gradient():
+    """Stages 1+ (geometry detached, train.py:431-436): render() does not ask the rasterizer for dL/dmeans2D -- the
+    densification statistic nobody reads there -- so the backward is the colour-only one; viewspace_points.grad is a
+    zero tensor (code that reads it keeps working), the feature gradient is unchanged, and pipe.viewspace_grad = True
+    restores the reference behaviour."""
+    from opengaussian_b200.renderer import render
+    dev = "cuda"
+    gs, cams = synth.make_scene("plumbing_10k_256", n_views=2)
+    cam = _cam(cams[0], dev)
+    bg = torch.zeros(3, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    G = torch.randn(6, cam.image_height, cam.image_width, device=dev, generator=gen)
+    res = {}
+    for force in (False, True):
+        pc = synth.SynthModel(gs, dev, stage0=False)
+        pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False, viewspace_grad=force)
+        out = render(cam, pc, pipe, bg, 100, rescale=False)
+        (out["ins_feat"] * G).sum().backward()
+        res[force] = (out["viewspace_points"], pc._ins_feat.grad.clone())
+    vs0, g0 = res[False]
+    vs1, g1 = res[True]
+    assert not vs0.requires_grad and vs0.grad is not None and float(vs0.grad.abs().max()) == 0.0
+    assert vs1.grad is not None and float(vs1.grad.abs().max()) > 0.0
+    assert float((g0 - g1).abs().max()) <= 1e-5 * float(g1.abs().max())
