@@ -44,6 +44,7 @@
  *                                :184-201 (pair_mask_feature_mean)
  *   ogs_cohesion_forward/backward
  *                                train.py:102-121 (cohesion_loss)
+ *   ogs_separation_loss          train.py:123-155 (separation_loss)
  */
 #ifndef OGS_B200_H
 #define OGS_B200_H
@@ -281,6 +282,15 @@ int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, co
 int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
                           const float* mean, const float* coef, float* dfeat, float* dmean,
                           void* stream);
+
+/* ---- inter-mask contrastive loss of Stage 1: train.py:123-155 (separation_loss), value AND gradient in two launches ----
+ * mean [N,C] (the per-mask feature means, N >= 2, C <= 16); small_weights != 0 is the reference's `iteration > 35000`
+ * branch (weights below 0.9 become 0.1).  loss_out [1] receives sum_{i != j} w_ij / (|m_i - m_j|^2 + 1) / (N (N - 1)) with
+ * w_ij = rank_ij / (N - 1) * 0.9 + 0.1, rank_ij = position of the term inside row i in ascending order (ties by column);
+ * dmean [N,C] its gradient w.r.t. mean (the weights are constants, as in the reference's autograd graph).
+ * scratch: N * N + N floats of device memory. */
+int ogs_separation_loss(int32_t N, int32_t C, const float* mean, int32_t small_weights, float* scratch,
+                        float* loss_out, float* dmean, void* stream);
 
 /* ---- pairwise mask intersections: utils/opengs_utlis.py::calculate_iou (:90-123) ----
  * masks1 [n1,H*W], masks2 [n2,H*W] bytes (torch.bool storage, non-zero = inside), device pointers.

@@ -29,6 +29,7 @@ UNITS = {
     "nvls.cu": [],
     "kmeans.cu": [],
     "mask_stats.cu": [],
+    "separation.cu": [],
     "mask_iou.cu": [],
     "adam.cu": [],
     "footprint.cu": [],

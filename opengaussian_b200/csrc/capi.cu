@@ -596,6 +596,14 @@ int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, c
     return 0;
 }
 
+int ogs_separation_loss(int32_t N, int32_t C, const float* mean, int32_t small_weights, float* scratch, float* loss_out,
+                        float* dmean, void* stream_) {
+    if (N < 2 || !mean || !scratch || !loss_out || !dmean) { set_error("separation_loss: needs N >= 2 and all pointers"); return -1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    return launch_separation_loss(N, C, mean, small_weights, scratch, loss_out, dmean, s);
+}
+
 int64_t ogs_mask_iou_scratch_bytes(int32_t n1, int32_t n2, int64_t HW) {
     if (n1 < 0 || n2 < 0 || HW < 0) return -1;
     return mask_iou_scratch_bytes(n1, n2, HW);

@@ -314,6 +314,10 @@ int launch_cohesion_backward(int M, int C, int64_t HW, const float* feat, const 
                              float* dfeat, float* dmean, cudaStream_t s);
 
 
+// inter-mask contrastive loss (separation.cu)
+int launch_separation_loss(int N, int C, const float* mean, int small_weights, float* scratch, float* loss_out, float* dmean,
+                           cudaStream_t s);
+
 // pairwise mask intersections (mask_iou.cu)
 int64_t mask_iou_scratch_bytes(int n1, int n2, int64_t HW);
 int launch_mask_pair_counts(int n1, int n2, int64_t HW, const uint8_t* masks1, const uint8_t* masks2, uint32_t* scratch,

@@ -131,9 +131,36 @@ def cohesion_loss(feat_map, gt_mask, feat_mean_stack):
     return _Cohesion.apply(feat_map, gt_mask, feat_mean_stack)
 
 
+class _Separation(torch.autograd.Function):
+    """separation_loss value + gradient in two kernel launches (C ABI ogs_separation_loss)."""
+
+    @staticmethod
+    def forward(ctx, mean, small_weights):
+        m = mean.detach().float().contiguous()
+        N, Cn = m.shape
+        dev = m.device
+        buf = torch.empty(N * N + N + 1 + N * Cn, dtype=torch.float32, device=dev)
+        loss = buf[N * N + N:N * N + N + 1]
+        dmean = buf[N * N + N + 1:].view(N, Cn)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ogs_separation_loss(N, Cn, _lib.ptr(m), int(bool(small_weights)), _lib.ptr(buf), _lib.ptr(loss),
+                                                _lib.ptr(dmean), _stream(dev))
+        _lib.check(rc, "ogs_separation_loss")
+        ctx.save_for_backward(dmean)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dmean,) = ctx.saved_tensors
+        return dmean * g, None
+
+
 def separation_loss(feat_mean_stack, iteration=None):
-    """Inter-mask contrastive loss, Eq. (2) (reference train.py:123-147).  O(M^2 C) on [M,C]: plain torch."""
+    """Inter-mask contrastive loss, Eq. (2) (reference train.py:123-155).  On CUDA with 2 <= N: two kernel launches for
+    value and gradient (csrc/separation.cu) instead of ~40 tiny torch kernels; otherwise the reference's expression."""
     N = feat_mean_stack.shape[0]
+    if feat_mean_stack.is_cuda and N >= 2 and feat_mean_stack.shape[1] <= 16:
+        return _Separation.apply(feat_mean_stack, iteration is not None and iteration > 35000)
     diff_squared = (feat_mean_stack.unsqueeze(1) - feat_mean_stack.unsqueeze(0)).pow(2).sum(2)
     inverse_distance = 1.0 / (diff_squared + 1)
     mask = torch.eye(N, device=feat_mean_stack.device).bool()
