@@ -353,7 +353,7 @@ int ups_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
                         const ogs_raster_grads_out* go, void* stream_) {
     int rc = check_inputs(in);
     if (rc) return rc;
-    if (!st || !gin || !go || !gin->dL_dcolor || !go->scratch) { set_error("state/grads/scratch must be set"); return -1; }
+    if (!st || !gin || !go || !gin->dL_dcolor || gin->dL_dfeat || !go->scratch) { set_error("state/grads/scratch must be set"); return -1; }
     if (go->accumulate || go->dL_dshs_rest || go->dL_dextra) { set_error("upstream-structure comparator: plain gradients only"); return -1; }
     cudaStream_t s = (cudaStream_t)stream_;
     const int P = in->P, W = in->W, H = in->H, C = 3;

@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define OGS_ABI_VERSION 3
+#define OGS_ABI_VERSION 4
 #define OGS_TILE 16
 #define OGS_MAX_CHANNELS 16 /* 3 colour channels + n_extra <= OGS_MAX_CHANNELS */
 
@@ -119,9 +119,12 @@ typedef struct ogs_raster_state {
 } ogs_raster_state;
 
 typedef struct ogs_raster_grads_in {
-    const float* dL_dcolor;  /* [3 + n_extra, H, W] */
+    const float* dL_dcolor;  /* [3 + n_extra, H, W]; with dL_dfeat set: [3, H, W] or NULL (= zero) */
     const float* dL_ddepth;  /* [H, W] or NULL */
     const float* dL_dalpha;  /* [H, W] or NULL */
+    const float* dL_dfeat;   /* NULL, or [n_extra, H, W]: the gradient of the extra channels as a separate image (the two
+                                images an autograd graph hands back for the colour and the feature map need not be
+                                copied into one; Stage 1 has no colour gradient at all) */
 } ogs_raster_grads_in;
 
 /* Any output pointer may be NULL: that gradient is then not produced.  If all of the geometry

@@ -38,7 +38,7 @@ class RasterState(C.Structure):
 
 
 class RasterGradsIn(C.Structure):
-    _fields_ = [("dL_dcolor", _fp), ("dL_ddepth", _fp), ("dL_dalpha", _fp)]
+    _fields_ = [("dL_dcolor", _fp), ("dL_ddepth", _fp), ("dL_dalpha", _fp), ("dL_dfeat", _fp)]
 
 
 class RasterGradsOut(C.Structure):
@@ -126,7 +126,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ogs_abi_version() != 3:
+        if L.ogs_abi_version() != 4:
             raise OgsError("libogs_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
             Tf[k] = inside ? a.final_T[pix] : 0.f;
 #pragma unroll
             for (int c = 0; c < C; c++) {
-                gv[k][c] = inside ? __ldg(a.dL_dcolor + c * HW + pix) : 0.f;
+                const float* plane = (a.dL_dfeat && c >= 3) ? a.dL_dfeat + (size_t)(c - 3) * HW
+                                                            : (a.dL_dcolor ? a.dL_dcolor + (size_t)c * HW : nullptr);
+                gv[k][c] = (inside && plane) ? __ldg(plane + pix) : 0.f;
                 if (GEOM) bgd[k] = fmaf(__ldg(a.bg + c), gv[k][c], bgd[k]);
             }
             if (GEOM) {

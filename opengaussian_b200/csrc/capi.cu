@@ -338,7 +338,8 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
                         const ogs_raster_grads_out* go, void* stream_) {
     int rc = validate_inputs(in);
     if (rc) return rc;
-    if (!st || !gin || !go || !gin->dL_dcolor || !go->scratch) { set_error("state/grads/scratch must be set"); return -1; }
+    if (!st || !gin || !go || (!gin->dL_dcolor && !gin->dL_dfeat) || !go->scratch) { set_error("state/grads/scratch must be set"); return -1; }
+    if (gin->dL_dfeat && in->n_extra <= 0) { set_error("dL_dfeat needs n_extra > 0"); return -1; }
     cudaStream_t s = (cudaStream_t)stream_;
     const int P = in->P, W = in->W, H = in->H, C = 3 + in->n_extra;
     if (P == 0) return 0;
@@ -362,7 +363,7 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
     ba.extra = n_feat_act ? g.feat : in->extra; ba.bg = in->bg;
     ba.final_T = (const float*)((char*)st->image + il.final_T);
     ba.n_contrib = (const uint32_t*)((char*)st->image + il.n_contrib);
-    ba.dL_dcolor = gin->dL_dcolor; ba.dL_ddepth = gin->dL_ddepth; ba.dL_dalpha = gin->dL_dalpha;
+    ba.dL_dcolor = gin->dL_dcolor; ba.dL_ddepth = gin->dL_ddepth; ba.dL_dalpha = gin->dL_dalpha; ba.dL_dfeat = gin->dL_dfeat;
     ba.geom = geom;
     ba.acc = (float*)go->scratch;
     ba.stride = blend_bwd_stride(C, geom);

@@ -184,6 +184,7 @@ struct BlendBwdArgs {
     const float* base; const float* extra; const float* bg;
     const float* final_T; const uint32_t* n_contrib;
     const float *dL_dcolor, *dL_ddepth, *dL_dalpha;
+    const float* dL_dfeat;      // NULL: dL_dcolor holds all C planes; else dL_dcolor = 3 planes (or NULL = 0), this = C - 3 planes
     int geom;                   // 1: all gradients, 0: colour/feature gradients only
     float* acc;                 // [P][stride] accumulators (zeroed by the launcher)
     int stride;                 // floats per Gaussian in acc

@@ -230,13 +230,16 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.act_flags = act_flags
         ctx.inputs_ref = (means3D, means2D_in)
         ctx.save_for_backward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra, sh_rest)
+        # colour and feature map are handed to autograd as TWO outputs (views of the one planar buffer the kernel
+        # wrote): their gradients then arrive separately and go to the kernel as two pointers -- slicing one output
+        # instead costs a zero-filled [C,H,W] gradient plus copies in the backward of every step
+        color = color_all[:3]
+        feat = color_all[3:3 + n_extra_user] if n_extra_user else color_all.new_empty(0, H, W)
         ctx.mark_non_differentiable(radii)
-        if n_extra != n_extra_user:
-            color_all = color_all[:3 + n_extra_user]
-        return color_all, radii, depth, alpha
+        return color, radii, depth, alpha, feat
 
     @staticmethod
-    def backward(ctx, grad_color_all, _grad_radii, grad_depth, grad_alpha):
+    def backward(ctx, grad_color, _grad_radii, grad_depth, grad_alpha, grad_feat):
         L = _lib.lib()
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra, sh_rest = ctx.saved_tensors
         rs = ctx.rs
@@ -246,9 +249,16 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         need = ctx.needs_input_grad   # means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3D, extra
 
-        gc = _f32c(grad_color_all)
-        if gc.shape[0] != 3 + n_extra:
-            gc = torch.cat([gc, gc.new_zeros(3 + n_extra - gc.shape[0], H, W)], 0)
+        gc = _f32c(grad_color) if grad_color is not None else None
+        gf = None
+        if n_extra and grad_feat is not None and grad_feat.shape[0] > 0:
+            gf = _f32c(grad_feat)
+            if gf.shape[0] != n_extra:        # zero planes for the padding channels
+                gf = torch.cat([gf, gf.new_zeros(n_extra - gf.shape[0], H, W)], 0)
+        if n_extra and gf is None:            # features rendered but not in the loss: the split form needs their planes
+            gf = torch.zeros(n_extra, H, W, dtype=torch.float32, device=dev)
+        if gc is None and gf is None:
+            gc = torch.zeros(3, H, W, dtype=torch.float32, device=dev)
         gd = _f32c(grad_depth) if grad_depth is not None else None
         ga = _f32c(grad_alpha) if grad_alpha is not None else None
 
@@ -337,7 +347,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         ri = _fill_inputs(rs, ctx.bg_full, means3D, opacities, sh, colors_precomp, scales, rotations,
                           cov3Ds_precomp, extra, n_extra, sh_rest, ctx.act_flags)
-        gi = _lib.RasterGradsIn(_lib.ptr(gc), _lib.ptr(gd), _lib.ptr(ga))
+        gi = _lib.RasterGradsIn(_lib.ptr(gc), _lib.ptr(gd), _lib.ptr(ga), _lib.ptr(gf))
         go = _lib.RasterGradsOut(_lib.ptr(g_means3D), _lib.ptr(g_means2D), _lib.ptr(g_opac), _lib.ptr(g_sh),
                                  _lib.ptr(g_colors), _lib.ptr(g_scales), _lib.ptr(g_rot), _lib.ptr(g_cov),
                                  _lib.ptr(g_extra), _lib.ptr(g_sh_rest), _lib.ptr(scratch), accumulate, 0)
@@ -387,12 +397,12 @@ class GaussianRasterizer(nn.Module):
         flags = _lib.ACT_SCALE_EXP | _lib.ACT_ROT_NORMALIZE | _lib.ACT_OPACITY_SIGMOID
         if raw_ins_feat is not None:
             flags |= _lib.ACT_EXTRA_UNIT_HALF
-        color_all, radii, depth, alpha = rasterize_gaussians(
+        color, radii, depth, alpha, feat = rasterize_gaussians(
             means3D, means2D, features_dc, None, opacity_logits, log_scales, raw_rotations, None, self.raster_settings,
             raw_ins_feat, extra_bg, features_rest, flags)
         if raw_ins_feat is None:
-            return color_all, radii, depth, alpha
-        return color_all[:3], radii, depth, alpha, color_all[3:]
+            return color, radii, depth, alpha
+        return color, radii, depth, alpha, feat
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None, extra_feats=None, extra_bg=None):
@@ -409,9 +419,9 @@ class GaussianRasterizer(nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
-        color_all, radii, depth, alpha = rasterize_gaussians(
+        color, radii, depth, alpha, feat = rasterize_gaussians(
             means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs, extra_feats,
             extra_bg)
         if extra_feats is None:
-            return color_all, radii, depth, alpha
-        return color_all[:3], radii, depth, alpha, color_all[3:]
+            return color, radii, depth, alpha
+        return color, radii, depth, alpha, feat
