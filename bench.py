@@ -656,12 +656,12 @@ def kmeans_leg(cx, a):
 def stage1_leg(cx, iters=10):
     """BASELINE config 3 -- OpenGaussian's own training step (stage 1, train.py:352-456) on the synthetic ScanNet-like
     scene, one view per rank per step: ONE fused render (RGB + 6 feature channels + depth + alpha, raw parameters),
-    per-mask feature means over 120 SAM-like masks, cohesion + separation losses, backward to `_ins_feat`, and on
+    the view's 120 SAM masks built from its id map (get_SAM_mask_and_feat), per-mask feature means, cohesion + separation losses, backward to `_ins_feat`, and on
     N > 1 GPUs the all-reduce of the 24 MB ins_feat gradient."""
     import types
     torch, dev = cx.torch, cx.dev
     from opengaussian_b200 import dist as ogd, synth
-    from opengaussian_b200.mask_stats import cohesion_loss, mask_feature_mean, separation_loss
+    from opengaussian_b200.mask_stats import cohesion_loss, get_SAM_mask_and_feat, mask_feature_mean, separation_loss
     from opengaussian_b200.renderer import render
     name = "scannet_1m_1296x968"
     gs, cams = synth.make_scene(name, n_views=4 * cx.world)
@@ -673,11 +673,14 @@ def stage1_leg(cx, iters=10):
                                     full_proj_transform=c.full_proj_transform.to(dev),
                                     camera_center=c.camera_center.to(dev), bClusterOccur=None) for c in cams]
     H, W = cams[0].image_height, cams[0].image_width
-    masks = synth.sam_like_masks(120, H, W, 4).to(dev)
+    # every view's own 4-level SAM id map, resident like view.original_sam_mask.cuda() (train.py:686)
+    sam_maps = [synth.sam_like_id_map(120, H, W, 4 + v).to(dev) for v in range(len(cam_ns))]
     bg = torch.zeros(3, device=dev)
 
     def view_loss(i):
         out = render(cam_ns[i % len(cam_ns)], pc, pipe, bg, 1000, rescale=False)
+        # train.py:441 -- the [120,H,W] masks are rebuilt from the id map every step, the mask count known from load time
+        _, masks, _ = get_SAM_mask_and_feat(sam_maps[i % len(cam_ns)], level=0, num_mask=120)
         mean = mask_feature_mean(out["ins_feat"], masks, image_mask=out["silhouette"])
         return separation_loss(mean, 1000) + 0.1 * cohesion_loss(out["ins_feat"], masks, mean)
 

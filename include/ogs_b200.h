@@ -39,6 +39,8 @@
  *   ogs_splat_footprint_votes    utils/sam_refinement_utils.py:902-913 (get_splat_id_and_weights, batched)
  *   ogs_adam_step                train.py:609 (gaussians.optimizer.step(), the torch.optim.Adam of
  *                                scene/gaussian_model.py:215-230)
+ *   ogs_sam_masks                utils/opengs_utlis.py:125-182 (get_SAM_mask_and_feat: id map -> mask_id, one-hot masks, invalid_pix)
+ *   ogs_mask_id_map              the inverse (one-hot masks -> id map) for mask sets that arrive as [M,H,W] tensors
  *   ogs_mask_mean_forward/backward, ogs_mask_var_forward
  *                                utils/opengs_utlis.py:240-283 (mask_feature_mean incl. return_var) and
  *                                :184-201 (pair_mask_feature_mean)
@@ -56,7 +58,7 @@
 extern "C" {
 #endif
 
-#define OGS_ABI_VERSION 4
+#define OGS_ABI_VERSION 5
 #define OGS_TILE 16
 #define OGS_MAX_CHANNELS 16 /* 3 colour channels + n_extra <= OGS_MAX_CHANNELS */
 
@@ -91,7 +93,7 @@ typedef struct ogs_raster_inputs {
      * scene/gaussian_model.py:122-169 folded into preprocess.  act_flags == 0 and shs_rest == NULL:
      * every tensor is ACTIVATED, as the reference rasterizer receives them. ---- */
     int32_t act_flags;      /* OGS_ACT_* bits */
-    int32_t reserved_;
+    int32_t defer_capacity_check; /* != 0: do not wait for this frame's duplicate count (see ogs_raster_capacity_check) */
     const float* shs_rest;  /* if != NULL: `shs` is _features_dc [P,1,3] and this is _features_rest [P,M-1,3]
                                (get_features' torch.cat is never materialised) */
 } ogs_raster_inputs;
@@ -165,6 +167,21 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
 int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* state,
                         const ogs_raster_grads_in* gin, const ogs_raster_grads_out* gout,
                         void* stream);
+
+/* Deferred capacity check.  ogs_raster_forward sizes the (Gaussian, tile) buffers from a running estimate of N and, by
+ * default, waits for the frame's real N before it returns -- the one host<->device synchronisation of a frame (the
+ * reference's rasterizer has the same one: a blocking read of num_rendered).  With in->defer_capacity_check != 0 the
+ * forward returns as soon as its kernels are queued (state->num_rendered = -1) and remembers the frame; the caller
+ * MUST call ogs_raster_capacity_check from the same host thread, with the same current device, before it trusts
+ * anything computed from those frames.  Returns 0: every deferred frame fitted; 1: at least one did not -- its outputs
+ * are truncated, and so is everything derived from them: discard and redo the work (the estimate has been raised);
+ * < 0: error (ogs_last_error).  A step-level transaction built on this: opengaussian_b200/dist.py::render_views_backward.
+ * At most 64 frames can be pending per thread and device; further forwards fall back to the synchronous check. */
+int ogs_raster_capacity_check(void);
+/* The calling thread's running estimate of N on the current device (entries the next speculative forward is sized
+ * for); new_hint >= 0 replaces it (0: forget -- the next forward waits for its count and re-seeds the estimate, e.g.
+ * after switching scenes), new_hint < 0 only reads.  Returns the previous value. */
+int64_t ogs_raster_capacity_hint(int64_t new_hint);
 
 size_t ogs_raster_backward_scratch_floats(int32_t P, int32_t n_extra);
 
@@ -272,19 +289,37 @@ int ogs_peer_comm_destroy(ogs_peer_comm* comm);
  *                  writes dfeat [C,H*W] and (if image_mask) dimg [H*W]
  *   var forward  : sq [M,C] = sum_p mask * (feat * image_mask - mean)^2
  *   cohesion fwd : dsum [M] = sum_p mask * ||feat[:,p] - mean[m]||_2, npix [M] = sum_p mask
- *   cohesion bwd : coef [M] = dL/dloss / (M * max(npix,1)); writes dfeat [C,H*W], dmean [M,C] */
-int ogs_mask_mean_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+ *   cohesion bwd : coef [M] = dL/dloss / (M * max(npix,1)); writes dfeat [C,H*W], dmean [M,C]
+ * ids / ids_overlap (both NULL, or both set): the id map of ogs_mask_id_map for THESE masks.  SAM masks are a partition
+ * of the image (get_SAM_mask_and_feat one-hot-encodes an id map, utils/opengs_utlis.py:144-148); when *ids_overlap == 0
+ * the passes read 2 B per pixel from ids instead of M B from masks, with identical results up to summation order.  When
+ * the flag is 1 (overlapping masks) ids is ignored.  The flag is read on the device: no host synchronisation. */
+int ogs_mask_mean_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                           const float* image_mask, float* sums, float* counts, void* stream);
-int ogs_mask_mean_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_mask_mean_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                            const float* image_mask, const float* G, const float* K, float* dfeat,
                            float* dimg, void* stream);
-int ogs_mask_var_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_mask_var_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                          const float* image_mask, const float* mean, float* sq, void* stream);
-int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                          const float* mean, float* dsum, float* npix, void* stream);
-int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                           const float* mean, const float* coef, float* dfeat, float* dmean,
                           void* stream);
+/* get_SAM_mask_and_feat (utils/opengs_utlis.py:125-182) for one level of a view's SAM id map: level_ids [H*W] int32
+ * (gt_sam_mask[level]), offset = previous level's largest id + 1 (0 at level 0).  Per pixel v = max(level_id - offset, -1):
+ * mask_id [H*W] int64 = v + 1 (0 = invalid), invalid_pix [H*W] bytes = (v < 0), ids [H*W] int16 = v (the id map of
+ * the passes above), masks [M,H*W] bytes = the one-hot expansion (mask m = pixels with v == m).  At most 32767 masks. */
+int ogs_sam_masks(int32_t M, int64_t HW, const int32_t* level_ids, int32_t offset, int64_t* mask_id,
+                  uint8_t* invalid_pix, int16_t* ids, uint8_t* masks, void* stream);
+/* Per-pixel id map of a mask set: ids [H*W] int16 = the (last) mask that holds the pixel, -1 = none; *ids_overlap
+ * (device int32) = 1 when some pixel lies in two or more masks, else 0.  At most 32767 masks. */
+int ogs_mask_id_map(int32_t M, int64_t HW, const uint8_t* masks, int16_t* ids, int32_t* ids_overlap, void* stream);
 
 /* ---- inter-mask contrastive loss of Stage 1: train.py:123-155 (separation_loss), value AND gradient in two launches ----
  * mean [N,C] (the per-mask feature means, N >= 2, C <= 16); small_weights != 0 is the reference's `iteration > 35000`

@@ -21,7 +21,7 @@ class RasterInputs(C.Structure):
         ("bg", _fp), ("viewmatrix", _fp), ("projmatrix", _fp), ("campos", _fp),
         ("means3D", _fp), ("opacities", _fp), ("shs", _fp), ("colors_precomp", _fp),
         ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp), ("extra", _fp),
-        ("act_flags", C.c_int32), ("reserved_", C.c_int32), ("shs_rest", _fp),
+        ("act_flags", C.c_int32), ("defer_capacity_check", C.c_int32), ("shs_rest", _fp),
     ]
 
 
@@ -71,6 +71,8 @@ EXPORTS = {
                                      C.POINTER(RasterState), C.c_void_p]),
     "ogs_raster_backward": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterState), C.POINTER(RasterGradsIn),
                                       C.POINTER(RasterGradsOut), C.c_void_p]),
+    "ogs_raster_capacity_check": (C.c_int, []),
+    "ogs_raster_capacity_hint": (C.c_int64, [C.c_int64]),
     "ogs_raster_backward_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
     "ogs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_void_p]),
     "ogs_raster_export": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterState)] + [_fp] * 10 + [C.c_void_p]),
@@ -94,11 +96,13 @@ EXPORTS = {
     "ogs_peer_allreduce": (C.c_int, [C.c_void_p, _fp, C.c_int64, C.c_int32, C.c_void_p]),
     "ogs_peer_comm_error": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ogs_peer_comm_destroy": (C.c_int, [C.c_void_p]),
-    "ogs_mask_mean_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
-    "ogs_mask_mean_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
-    "ogs_mask_var_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
-    "ogs_cohesion_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
-    "ogs_cohesion_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_mask_mean_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_mask_mean_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_mask_var_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_cohesion_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_cohesion_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_sam_masks": (C.c_int, [C.c_int32, C.c_int64, _fp, C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "ogs_mask_id_map": (C.c_int, [C.c_int32, C.c_int64, _fp, _fp, _fp, C.c_void_p]),
     "ogs_separation_loss": (C.c_int, [C.c_int32, C.c_int32, _fp, C.c_int32, _fp, _fp, _fp, C.c_void_p]),
     "ogs_splat_footprint_votes": (C.c_int, [C.POINTER(FootprintInputs), _fp, _fp, _fp, _fp, _fp, C.POINTER(C.c_int32),
                                             C.c_void_p]),
@@ -126,7 +130,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ogs_abi_version() != 4:
+        if L.ogs_abi_version() != 5:
             raise OgsError("libogs_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

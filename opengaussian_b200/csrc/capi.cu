@@ -73,10 +73,22 @@ static int ensure_pool(void) {
 // Per host thread AND per device: running estimate of num_rendered (+25 %, see ogs_raster_forward), the pinned
 // word the scan total is copied to, and the event that marks that copy.  (Events and pinned allocations belong to
 // the device/context that was current when they were made.)
+#define OGS_MAX_PENDING 64
+struct PendingFrame {
+    cudaEvent_t ev = nullptr;      // marks the copy of [N, overflow flag] into the slot's pinned words
+    int64_t cap = 0;               // the capacity the frame was binned with
+    bool live = false;
+};
 struct ForwardCtx {
     uint64_t cap_hint = 0;
-    uint32_t* pinned = nullptr;
+    uint32_t* pinned = nullptr;    // 2 words for the synchronous check + 2 per pending slot
     cudaEvent_t ev = nullptr;
+    PendingFrame pending[OGS_MAX_PENDING];
+    void grow_hint(int64_t N) {
+        const uint64_t want = (uint64_t)N + (uint64_t)N / 4 + 65536;
+        const uint64_t decay = cap_hint - cap_hint / 32;
+        cap_hint = want > decay ? want : decay;
+    }
 };
 static ForwardCtx& forward_ctx(void) {
     static thread_local ForwardCtx ctx[OGS_MAX_DEVICES];
@@ -85,7 +97,7 @@ static ForwardCtx& forward_ctx(void) {
 
 static uint32_t* pinned_scalar(ForwardCtx& fc) {
     if (!fc.pinned) {
-        if (cudaMallocHost((void**)&fc.pinned, 64) != cudaSuccess) fc.pinned = nullptr;
+        if (cudaMallocHost((void**)&fc.pinned, 8 * (1 + OGS_MAX_PENDING)) != cudaSuccess) fc.pinned = nullptr;
     }
     return fc.pinned;
 }
@@ -226,6 +238,7 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     const uint32_t* n_ptr = nullptr;
     cudaEvent_t n_event = nullptr;
     ForwardCtx& fc = forward_ctx();
+    PendingFrame* deferred = nullptr;
     AsyncScratch scratch1(s);          // freed (stream-ordered) on every exit path
     BinScratch sc;
     memset(&sc, 0, sizeof sc);
@@ -260,6 +273,11 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         if (rc) return rc;
         h = pinned_scalar(fc);
         if (!h) { set_error("cudaMallocHost failed"); return 2; }
+        if (in->defer_capacity_check && fc.cap_hint != 0 && !in->debug) {
+            for (int k = 0; k < OGS_MAX_PENDING && !deferred; k++)
+                if (!fc.pending[k].live) deferred = &fc.pending[k];
+            if (deferred) h += 2 * (1 + (deferred - fc.pending));
+        }
         n_ptr = sc.offsets + P;
         OGS_CUDA(cudaMemcpyAsync(h, n_ptr, 8, cudaMemcpyDeviceToHost, s));     // [N, overflow flag]
         // Capacity speculation: the binning buffers are sized from the running estimate cap_hint and
@@ -271,6 +289,13 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
             if (h[1]) { set_error("more than 2^32 - 1 (Gaussian, tile) duplicates in one frame: 32-bit offsets overflow"); return -7; }
             N = (int64_t)*h;
             cap = N;
+        } else if (deferred) {
+            if (!deferred->ev) OGS_CUDA(cudaEventCreateWithFlags(&deferred->ev, cudaEventDisableTiming));
+            OGS_CUDA(cudaEventRecord(deferred->ev, s));
+            cap = (int64_t)fc.cap_hint;
+            deferred->cap = cap;
+            deferred->live = true;
+            speculative = true;
         } else {
             if (!fc.ev) OGS_CUDA(cudaEventCreateWithFlags(&fc.ev, cudaEventDisableTiming));
             OGS_CUDA(cudaEventRecord(fc.ev, s));
@@ -317,6 +342,10 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         if (rc) return rc;
         OGS_KERNEL_CHECK("blend_forward", in->debug, s);
         if (!speculative) break;
+        if (deferred) {                // the caller resolves this frame in ogs_raster_capacity_check
+            N = -1;
+            break;
+        }
         OGS_CUDA(cudaEventSynchronize(n_event));
         if (h[1]) { set_error("more than 2^32 - 1 (Gaussian, tile) duplicates in one frame: 32-bit offsets overflow"); return -7; }
         N = (int64_t)*h;
@@ -325,13 +354,38 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
         cap = N;                       // estimate too small: redo binning + blend with the exact size
     }
     scratch1.release();
-    if (P > 0) {
-        const uint64_t want = (uint64_t)N + (uint64_t)N / 4 + 65536;
-        const uint64_t decay = fc.cap_hint - fc.cap_hint / 32;
-        fc.cap_hint = want > decay ? want : decay;
-    }
+    if (P > 0 && N >= 0) fc.grow_hint(N);
     st->num_rendered = N;
     return 0;
+}
+
+int64_t ogs_raster_capacity_hint(int64_t new_hint) {
+    ForwardCtx& fc = forward_ctx();
+    const int64_t old = (int64_t)fc.cap_hint;
+    if (new_hint >= 0) fc.cap_hint = (uint64_t)new_hint;
+    return old;
+}
+
+int ogs_raster_capacity_check(void) {
+    ForwardCtx& fc = forward_ctx();
+    int result = 0;
+    for (int k = 0; k < OGS_MAX_PENDING; k++) {
+        PendingFrame& pf = fc.pending[k];
+        if (!pf.live) continue;
+        pf.live = false;
+        cudaError_t e = cudaEventSynchronize(pf.ev);
+        if (e != cudaSuccess) { result = cuda_fail(e, "capacity check"); continue; }
+        const uint32_t* h = fc.pinned + 2 * (1 + k);
+        if (h[1]) {
+            set_error("more than 2^32 - 1 (Gaussian, tile) duplicates in one frame: 32-bit offsets overflow");
+            result = -7;
+            continue;
+        }
+        const int64_t N = (int64_t)h[0];
+        fc.grow_hint(N);
+        if (N > pf.cap && result == 0) result = 1;
+    }
+    return result;
 }
 
 int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st, const ogs_raster_grads_in* gin,
@@ -531,69 +585,102 @@ int ogs_kmeans_finalize_fixed(int32_t rows, int32_t D, const int64_t* acc, int32
 }
 
 #define OGS_MASK_ARGS_OK(what)                                                                          \
-    if (M < 0 || HW < 0 || ((M > 0 || HW > 0) && !feat) || (M > 0 && HW > 0 && !masks)) {                \
+    if (M < 0 || HW < 0 || ((M > 0 || HW > 0) && !feat) || (M > 0 && HW > 0 && !masks) ||                \
+        (ids && !ids_overlap)) {                                                                         \
         set_error(what ": bad arguments");                                                               \
         return -1;                                                                                       \
     }
 
-int ogs_mask_mean_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_mask_mean_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                           const float* image_mask, float* sums, float* counts, void* stream_) {
     OGS_MASK_ARGS_OK("mask_mean_forward");
     if (M > 0 && (!sums || !counts)) { set_error("mask_mean_forward: outputs must be set"); return -1; }
     cudaStream_t s = (cudaStream_t)stream_;
     ProfScope ps(PF_MASK_STATS, s);
-    int rc = launch_mask_mean_forward(M, C, HW, feat, masks, image_mask, sums, counts, s);
+    int rc = launch_mask_mean_forward(M, C, HW, feat, masks, ids, ids_overlap, image_mask, sums, counts, s);
     if (rc) return rc;
     OGS_KERNEL_CHECK("mask_mean_forward", 0, s);
     return 0;
 }
 
-int ogs_mask_mean_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_mask_mean_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                            const float* image_mask, const float* G, const float* K, float* dfeat,
                            float* dimg, void* stream_) {
     OGS_MASK_ARGS_OK("mask_mean_backward");
     if ((M > 0 && (!G || !K)) || (HW > 0 && !dfeat)) { set_error("mask_mean_backward: G/K/dfeat must be set"); return -1; }
     cudaStream_t s = (cudaStream_t)stream_;
     ProfScope ps(PF_MASK_STATS, s);
-    int rc = launch_mask_mean_backward(M, C, HW, feat, masks, image_mask, G, K, dfeat, image_mask ? dimg : nullptr, s);
+    int rc = launch_mask_mean_backward(M, C, HW, feat, masks, ids, ids_overlap, image_mask, G, K, dfeat, image_mask ? dimg : nullptr, s);
     if (rc) return rc;
     OGS_KERNEL_CHECK("mask_mean_backward", 0, s);
     return 0;
 }
 
-int ogs_mask_var_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_mask_var_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                          const float* image_mask, const float* mean, float* sq, void* stream_) {
     OGS_MASK_ARGS_OK("mask_var_forward");
     if (M > 0 && (!mean || !sq)) { set_error("mask_var_forward: mean/sq must be set"); return -1; }
     cudaStream_t s = (cudaStream_t)stream_;
     ProfScope ps(PF_MASK_STATS, s);
-    int rc = launch_mask_var_forward(M, C, HW, feat, masks, image_mask, mean, sq, s);
+    int rc = launch_mask_var_forward(M, C, HW, feat, masks, ids, ids_overlap, image_mask, mean, sq, s);
     if (rc) return rc;
     OGS_KERNEL_CHECK("mask_var_forward", 0, s);
     return 0;
 }
 
-int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_cohesion_forward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                          const float* mean, float* dsum, float* npix, void* stream_) {
     OGS_MASK_ARGS_OK("cohesion_forward");
     if (M > 0 && (!mean || !dsum || !npix)) { set_error("cohesion_forward: mean/outputs must be set"); return -1; }
     cudaStream_t s = (cudaStream_t)stream_;
     ProfScope ps(PF_MASK_STATS, s);
-    int rc = launch_cohesion_forward(M, C, HW, feat, masks, mean, dsum, npix, s);
+    int rc = launch_cohesion_forward(M, C, HW, feat, masks, ids, ids_overlap, mean, dsum, npix, s);
     if (rc) return rc;
     OGS_KERNEL_CHECK("cohesion_forward", 0, s);
     return 0;
 }
 
-int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks,
+int ogs_cohesion_backward(int32_t M, int32_t C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids,
+        const int32_t* ids_overlap,
                           const float* mean, const float* coef, float* dfeat, float* dmean, void* stream_) {
     OGS_MASK_ARGS_OK("cohesion_backward");
     if ((M > 0 && (!mean || !coef || !dmean)) || (HW > 0 && !dfeat)) { set_error("cohesion_backward: inputs/outputs must be set"); return -1; }
     cudaStream_t s = (cudaStream_t)stream_;
     ProfScope ps(PF_MASK_STATS, s);
-    int rc = launch_cohesion_backward(M, C, HW, feat, masks, mean, coef, dfeat, dmean, s);
+    int rc = launch_cohesion_backward(M, C, HW, feat, masks, ids, ids_overlap, mean, coef, dfeat, dmean, s);
     if (rc) return rc;
     OGS_KERNEL_CHECK("cohesion_backward", 0, s);
+    return 0;
+}
+
+int ogs_sam_masks(int32_t M, int64_t HW, const int32_t* level_ids, int32_t offset, int64_t* mask_id, uint8_t* invalid_pix,
+                  int16_t* ids, uint8_t* masks, void* stream_) {
+    if (M < 0 || HW < 0 || (HW > 0 && (!level_ids || !mask_id || !invalid_pix || !ids || (M > 0 && !masks)))) {
+        set_error("sam_masks: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_sam_masks(M, HW, level_ids, offset, mask_id, invalid_pix, ids, masks, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("sam_masks", 0, s);
+    return 0;
+}
+
+int ogs_mask_id_map(int32_t M, int64_t HW, const uint8_t* masks, int16_t* ids, int32_t* ids_overlap, void* stream_) {
+    if (M < 0 || HW < 0 || (M > 0 && HW > 0 && !masks) || (HW > 0 && !ids) || !ids_overlap) {
+        set_error("mask_id_map: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    ProfScope ps(PF_MASK_STATS, s);
+    int rc = launch_mask_id_map(M, HW, masks, ids, ids_overlap, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("mask_id_map", 0, s);
     return 0;
 }
 

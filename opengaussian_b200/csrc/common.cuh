@@ -303,17 +303,21 @@ int launch_kmeans_seg_finalize(int rows, int D, const int64_t* acc, int fix_bits
 
 
 // mask statistics (mask_stats.cu)
-int launch_mask_mean_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, float* sums,
+int launch_mask_mean_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* img, float* sums,
                              float* counts, cudaStream_t s);
-int launch_mask_mean_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, const float* G,
+int launch_mask_mean_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* img, const float* G,
                               const float* K, float* dfeat, float* dimg, cudaStream_t s);
-int launch_mask_var_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, const float* mean,
+int launch_mask_var_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* img, const float* mean,
                             float* sq, cudaStream_t s);
-int launch_cohesion_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* mean, float* dsum,
+int launch_cohesion_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* mean, float* dsum,
                             float* npix, cudaStream_t s);
-int launch_cohesion_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* mean, const float* coef,
+int launch_cohesion_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* mean, const float* coef,
                              float* dfeat, float* dmean, cudaStream_t s);
 
+
+int launch_sam_masks(int M, int64_t HW, const int32_t* level_ids, int offset, int64_t* mask_id, uint8_t* invalid_pix,
+                     int16_t* ids, uint8_t* masks, cudaStream_t s);
+int launch_mask_id_map(int M, int64_t HW, const uint8_t* masks, int16_t* ids, int32_t* overlap, cudaStream_t s);
 
 // inter-mask contrastive loss (separation.cu)
 int launch_separation_loss(int N, int C, const float* mean, int small_weights, float* scratch, float* loss_out, float* dmean,

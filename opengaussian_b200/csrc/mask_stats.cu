@@ -49,18 +49,55 @@ __device__ __forceinline__ bool in_mask(uint32_t bits, int j) { return ((bits >>
 
 // Walks the masks MS_UNROLL at a time: the (independent, coalesced) mask-word loads of a group are all
 // issued before the first vote, so the walk is bound by bandwidth and not by one load latency per mask.
-// The body runs for masks that have at least one pixel among the warp's 128; close with MS_END_FOR.
+// body(m, bits) runs for masks that have at least one pixel among the warp's 128.
+//
+// When the masks are a PARTITION of the image (every pixel in at most one mask -- what get_SAM_mask_and_feat builds
+// from a SAM id map, utils/opengs_utlis.py:125-182), a per-pixel id map (int16, -1 = no mask) replaces the M mask
+// rows: the warp reads 2 B per pixel instead of M, and visits only the ids that occur among its 128 pixels.
 #define MS_UNROLL 8
-#define MS_FOR_EACH_PRESENT_MASK(m, bits)                                                     \
-    for (int m##_0 = 0; m##_0 < M; m##_0 += MS_UNROLL) {                                      \
-        uint32_t bits##_g[MS_UNROLL];                                                         \
-        _Pragma("unroll") for (int u = 0; u < MS_UNROLL; u++)                                 \
-            bits##_g[u] = (m##_0 + u < M) ? load_mask4(masks + (size_t)(m##_0 + u) * HW, b, aligned) : 0u; \
-        _Pragma("unroll") for (int u = 0; u < MS_UNROLL; u++) {                               \
-            const uint32_t bits = bits##_g[u];                                                \
-            const int m = m##_0 + u;                                                          \
-            if (!__any_sync(0xffffffffu, bits != 0)) continue;
-#define MS_END_FOR }
+template <typename Body>
+__device__ __forceinline__ void for_each_present_mask(int M, int64_t HW, const uint8_t* __restrict__ masks,
+                                                      const int16_t* __restrict__ ids, const PixelBlock& b, bool aligned,
+                                                      Body body) {
+    if (ids) {
+        int id0 = -1, id1 = -1, id2 = -1, id3 = -1;
+        if (b.valid == MS_PPL) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(ids + b.p0));      // p0 is a multiple of 4: 8-byte aligned
+            id0 = (int16_t)(v.x & 0xFFFFu); id1 = (int16_t)(v.x >> 16);
+            id2 = (int16_t)(v.y & 0xFFFFu); id3 = (int16_t)(v.y >> 16);
+        } else {
+            if (b.valid > 0) id0 = ids[b.p0];
+            if (b.valid > 1) id1 = ids[b.p0 + 1];
+            if (b.valid > 2) id2 = ids[b.p0 + 2];
+        }
+        uint32_t todo = (id0 >= 0 ? 1u : 0u) | (id1 >= 0 ? 2u : 0u) | (id2 >= 0 ? 4u : 0u) | (id3 >= 0 ? 8u : 0u);
+        for (;;) {
+            const unsigned ball = __ballot_sync(0xffffffffu, todo != 0);
+            if (!ball) break;
+            const int mine = (todo & 1u) ? id0 : (todo & 2u) ? id1 : (todo & 4u) ? id2 : id3;
+            const int m = __shfl_sync(0xffffffffu, mine, __ffs(ball) - 1);
+            uint32_t bits = 0;
+            if ((todo & 1u) && id0 == m) { bits |= 1u; todo &= ~1u; }
+            if ((todo & 2u) && id1 == m) { bits |= 1u << 8; todo &= ~2u; }
+            if ((todo & 4u) && id2 == m) { bits |= 1u << 16; todo &= ~4u; }
+            if ((todo & 8u) && id3 == m) { bits |= 1u << 24; todo &= ~8u; }
+            if (m < M) body(m, bits);
+        }
+        return;
+    }
+    for (int m0 = 0; m0 < M; m0 += MS_UNROLL) {
+        uint32_t g[MS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MS_UNROLL; u++) g[u] = (m0 + u < M) ? load_mask4(masks + (size_t)(m0 + u) * HW, b, aligned) : 0u;
+#pragma unroll
+        for (int u = 0; u < MS_UNROLL; u++)
+            if (__any_sync(0xffffffffu, g[u] != 0)) body(m0 + u, g[u]);
+    }
+}
+// the id map is used only when the device-side flag says the masks it was built from did not overlap
+__device__ __forceinline__ const int16_t* usable_ids(const int16_t* ids, const int32_t* overlap) {
+    return (ids && overlap && *overlap == 0) ? ids : nullptr;
+}
 
 template <int C>
 __device__ __forceinline__ void load_feat(const float* __restrict__ feat, const float* __restrict__ img, int64_t HW,
@@ -85,7 +122,8 @@ __device__ __forceinline__ void warp_sum(float (&v)[NV]) {
 // ---------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(MS_THREADS) mask_mean_fwd_kernel(int M, int64_t HW, const float* __restrict__ feat,
-                                                                   const uint8_t* __restrict__ masks, const float* __restrict__ img,
+                                                                   const uint8_t* __restrict__ masks, const int16_t* __restrict__ ids,
+        const int32_t* __restrict__ overlap, const float* __restrict__ img,
                                                                    float* __restrict__ sums, float* __restrict__ counts) {
     extern __shared__ float s_acc[];   // [M][C+1]
     for (int e = threadIdx.x; e < M * (C + 1); e += MS_THREADS) s_acc[e] = 0.f;
@@ -95,7 +133,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_mean_fwd_kernel(int M, int64_
     float f[MS_PPL][C], w[MS_PPL];
     load_feat<C>(feat, img, HW, b, f, w);
     const int lane = threadIdx.x & 31;
-    MS_FOR_EACH_PRESENT_MASK(m, bits)
+    for_each_present_mask(M, HW, masks, usable_ids(ids, overlap), b, aligned, [&](int m, uint32_t bits) {
         float v[C + 1];
 #pragma unroll
         for (int k = 0; k <= C; k++) v[k] = 0.f;
@@ -111,8 +149,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_mean_fwd_kernel(int M, int64_
 #pragma unroll
             for (int k = 0; k <= C; k++) atomicAdd(&s_acc[m * (C + 1) + k], v[k]);
         }
-    }
-    MS_END_FOR
+    });
     __syncthreads();
     for (int e = threadIdx.x; e < M * (C + 1); e += MS_THREADS) {
         const float s = s_acc[e];
@@ -127,7 +164,8 @@ __global__ void __launch_bounds__(MS_THREADS) mask_mean_fwd_kernel(int M, int64_
 // G[m][c] = dL/dmean[m][c] / max(count[m], 1);  K[m] = (count[m] > 1) ? sum_c G[m][c] mean[m][c] : 0
 template <int C>
 __global__ void __launch_bounds__(MS_THREADS) mask_mean_bwd_kernel(int M, int64_t HW, const float* __restrict__ feat,
-                                                                   const uint8_t* __restrict__ masks, const float* __restrict__ img,
+                                                                   const uint8_t* __restrict__ masks, const int16_t* __restrict__ ids,
+        const int32_t* __restrict__ overlap, const float* __restrict__ img,
                                                                    const float* __restrict__ G, const float* __restrict__ K,
                                                                    float* __restrict__ dfeat, float* __restrict__ dimg) {
     extern __shared__ float s_g[];   // [M][C+1]: G then K
@@ -147,7 +185,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_mean_bwd_kernel(int M, int64_
 #pragma unroll
         for (int c = 0; c < C; c++) acc[j][c] = 0.f;
     }
-    MS_FOR_EACH_PRESENT_MASK(m, bits)
+    for_each_present_mask(M, HW, masks, usable_ids(ids, overlap), b, aligned, [&](int m, uint32_t bits) {
         const float* g = s_g + m * (C + 1);
 #pragma unroll
         for (int j = 0; j < MS_PPL; j++) {
@@ -161,8 +199,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_mean_bwd_kernel(int M, int64_
                 ai[j] += dot;
             }
         }
-    }
-    MS_END_FOR
+    });
 #pragma unroll
     for (int j = 0; j < MS_PPL; j++) {
         if (j < b.valid) {
@@ -176,7 +213,8 @@ __global__ void __launch_bounds__(MS_THREADS) mask_mean_bwd_kernel(int M, int64_
 // sq[m][c] = sum_p mask (feat w - mean[m][c])^2   (the reference squares masked_feats - mean inside the mask)
 template <int C>
 __global__ void __launch_bounds__(MS_THREADS) mask_var_fwd_kernel(int M, int64_t HW, const float* __restrict__ feat,
-                                                                  const uint8_t* __restrict__ masks, const float* __restrict__ img,
+                                                                  const uint8_t* __restrict__ masks, const int16_t* __restrict__ ids,
+        const int32_t* __restrict__ overlap, const float* __restrict__ img,
                                                                   const float* __restrict__ mean, float* __restrict__ sq) {
     extern __shared__ float s_mem[];   // [M][C] mean, [M][C] acc
     float* s_mean = s_mem;
@@ -188,7 +226,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_var_fwd_kernel(int M, int64_t
     float f[MS_PPL][C], w[MS_PPL];
     load_feat<C>(feat, img, HW, b, f, w);
     const int lane = threadIdx.x & 31;
-    MS_FOR_EACH_PRESENT_MASK(m, bits)
+    for_each_present_mask(M, HW, masks, usable_ids(ids, overlap), b, aligned, [&](int m, uint32_t bits) {
         float v[C];
 #pragma unroll
         for (int c = 0; c < C; c++) v[c] = 0.f;
@@ -207,8 +245,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_var_fwd_kernel(int M, int64_t
 #pragma unroll
             for (int c = 0; c < C; c++) atomicAdd(&s_acc[m * C + c], v[c]);
         }
-    }
-    MS_END_FOR
+    });
     __syncthreads();
     for (int e = threadIdx.x; e < M * C; e += MS_THREADS)
         if (s_acc[e] != 0.f) atomicAdd(sq + e, s_acc[e]);
@@ -216,7 +253,8 @@ __global__ void __launch_bounds__(MS_THREADS) mask_var_fwd_kernel(int M, int64_t
 
 template <int C>
 __global__ void __launch_bounds__(MS_THREADS) cohesion_fwd_kernel(int M, int64_t HW, const float* __restrict__ feat,
-                                                                  const uint8_t* __restrict__ masks, const float* __restrict__ mean,
+                                                                  const uint8_t* __restrict__ masks, const int16_t* __restrict__ ids,
+        const int32_t* __restrict__ overlap, const float* __restrict__ mean,
                                                                   float* __restrict__ dsum, float* __restrict__ npix) {
     extern __shared__ float s_mem[];   // [M][C] mean, [M][2] acc
     float* s_mean = s_mem;
@@ -229,7 +267,7 @@ __global__ void __launch_bounds__(MS_THREADS) cohesion_fwd_kernel(int M, int64_t
     float f[MS_PPL][C], w[MS_PPL];
     load_feat<C>(feat, nullptr, HW, b, f, w);
     const int lane = threadIdx.x & 31;
-    MS_FOR_EACH_PRESENT_MASK(m, bits)
+    for_each_present_mask(M, HW, masks, usable_ids(ids, overlap), b, aligned, [&](int m, uint32_t bits) {
         float v[2] = {0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < MS_PPL; j++) {
@@ -249,8 +287,7 @@ __global__ void __launch_bounds__(MS_THREADS) cohesion_fwd_kernel(int M, int64_t
             atomicAdd(&s_acc[2 * m], v[0]);
             atomicAdd(&s_acc[2 * m + 1], v[1]);
         }
-    }
-    MS_END_FOR
+    });
     __syncthreads();
     for (int e = threadIdx.x; e < M; e += MS_THREADS) {
         if (s_acc[2 * e + 1] != 0.f) {
@@ -263,7 +300,8 @@ __global__ void __launch_bounds__(MS_THREADS) cohesion_fwd_kernel(int M, int64_t
 // coef[m] = dL/dloss / (M max(n[m], 1)).  dfeat is WRITTEN (every pixel), dmean is accumulated (zeroed by the launcher).
 template <int C>
 __global__ void __launch_bounds__(MS_THREADS) cohesion_bwd_kernel(int M, int64_t HW, const float* __restrict__ feat,
-                                                                  const uint8_t* __restrict__ masks, const float* __restrict__ mean,
+                                                                  const uint8_t* __restrict__ masks, const int16_t* __restrict__ ids,
+        const int32_t* __restrict__ overlap, const float* __restrict__ mean,
                                                                   const float* __restrict__ coef, float* __restrict__ dfeat,
                                                                   float* __restrict__ dmean) {
     extern __shared__ float s_mem[];   // [M][C+1] mean | coef, [M][C] acc
@@ -285,7 +323,7 @@ __global__ void __launch_bounds__(MS_THREADS) cohesion_bwd_kernel(int M, int64_t
 #pragma unroll
         for (int c = 0; c < C; c++) acc[j][c] = 0.f;
     const int lane = threadIdx.x & 31;
-    MS_FOR_EACH_PRESENT_MASK(m, bits)
+    for_each_present_mask(M, HW, masks, usable_ids(ids, overlap), b, aligned, [&](int m, uint32_t bits) {
         const float* mu = s_mean + m * (C + 1);
         float v[C];
 #pragma unroll
@@ -310,8 +348,7 @@ __global__ void __launch_bounds__(MS_THREADS) cohesion_bwd_kernel(int M, int64_t
 #pragma unroll
             for (int c = 0; c < C; c++) atomicAdd(&s_acc[m * C + c], v[c]);
         }
-    }
-    MS_END_FOR
+    });
 #pragma unroll
     for (int j = 0; j < MS_PPL; j++)
         if (j < b.valid) {
@@ -321,6 +358,66 @@ __global__ void __launch_bounds__(MS_THREADS) cohesion_bwd_kernel(int M, int64_t
     __syncthreads();
     for (int e = threadIdx.x; e < M * C; e += MS_THREADS)
         if (s_acc[e] != 0.f) atomicAdd(dmean + e, s_acc[e]);
+}
+
+// ids[p] = the mask that holds pixel p (-1: none); *overlap is set when some pixel sits in two or more masks, in which
+// case the statistics kernels ignore the id map and walk the mask rows.
+__global__ void __launch_bounds__(MS_THREADS) mask_id_map_kernel(int M, int64_t HW, const uint8_t* __restrict__ masks,
+                                                                 int16_t* __restrict__ ids, int32_t* __restrict__ overlap) {
+    const PixelBlock b = lane_pixels(HW);
+    const bool aligned = (HW & 3) == 0;
+    int id[MS_PPL], n[MS_PPL];
+#pragma unroll
+    for (int j = 0; j < MS_PPL; j++) { id[j] = -1; n[j] = 0; }
+    for_each_present_mask(M, HW, masks, nullptr, b, aligned, [&](int m, uint32_t bits) {
+#pragma unroll
+        for (int j = 0; j < MS_PPL; j++)
+            if (in_mask(bits, j)) { id[j] = m; n[j]++; }
+    });
+    bool clash = false;
+#pragma unroll
+    for (int j = 0; j < MS_PPL; j++) {
+        if (j < b.valid) ids[b.p0 + j] = (int16_t)id[j];
+        clash |= n[j] > 1;
+    }
+    if (__any_sync(0xffffffffu, clash) && (threadIdx.x & 31) == 0) atomicOr(overlap, 1);
+}
+
+// get_SAM_mask_and_feat (utils/opengs_utlis.py:134-148,168-169) per pixel: v = max(level_id - offset, -1);
+// mask_id = v + 1 (0 = invalid), invalid_pix = (v < 0), ids = v (or -1 when v >= M: in none of the M masks)
+__global__ void __launch_bounds__(256) sam_ids_kernel(int M, int64_t HW, const int32_t* __restrict__ level_ids, int offset,
+                                                      int64_t* __restrict__ mask_id, uint8_t* __restrict__ invalid_pix,
+                                                      int16_t* __restrict__ ids) {
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= HW) return;
+    int v = __ldg(level_ids + p) - offset;
+    v = v < -1 ? -1 : v;
+    mask_id[p] = (int64_t)v + 1;
+    invalid_pix[p] = v < 0;
+    ids[p] = (int16_t)(v < M ? v : -1);
+}
+
+// masks[m][p] = (ids[p] == m): the one-hot expansion, 16 pixels per thread (one 16-byte store when rows are aligned)
+__global__ void __launch_bounds__(256) mask_expand_kernel(int64_t HW, const int16_t* __restrict__ ids, uint8_t* __restrict__ masks) {
+    const int64_t p = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 16;
+    if (p >= HW) return;
+    const int m = blockIdx.y;
+    uint8_t* row = masks + (size_t)m * HW;
+    if (p + 16 <= HW && (HW & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(ids + p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(ids + p) + 1);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t lo = w[2 * k], hi = w[2 * k + 1];
+            o[k] = ((int)(int16_t)(lo & 0xFFFFu) == m ? 1u : 0u) | ((int)(int16_t)(lo >> 16) == m ? 1u << 8 : 0u) |
+                   ((int)(int16_t)(hi & 0xFFFFu) == m ? 1u << 16 : 0u) | ((int)(int16_t)(hi >> 16) == m ? 1u << 24 : 0u);
+        }
+        *reinterpret_cast<uint4*>(row + p) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int64_t q = p; q < p + 16 && q < HW; q++) row[q] = (int)ids[q] == m;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -344,7 +441,7 @@ static int set_smem(Kern k, size_t bytes) {
         else { CALL6; }           \
     } while (0)
 
-int launch_mask_mean_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, float* sums,
+int launch_mask_mean_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* img, float* sums,
                              float* counts, cudaStream_t s) {
     const size_t sm = (size_t)M * (C + 1);
     int rc = check_shapes(M, C, HW, sm, "mask_mean_forward");
@@ -352,35 +449,35 @@ int launch_mask_mean_forward(int M, int C, int64_t HW, const float* feat, const 
     OGS_CUDA(cudaMemsetAsync(sums, 0, (size_t)M * C * 4, s));
     OGS_CUDA(cudaMemsetAsync(counts, 0, (size_t)M * 4, s));
     if (M == 0 || HW == 0) return 0;
-    MS_DISPATCH((rc = set_smem(mask_mean_fwd_kernel<3>, sm * 4), mask_mean_fwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, img, sums, counts)),
-                (rc = set_smem(mask_mean_fwd_kernel<6>, sm * 4), mask_mean_fwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, img, sums, counts)));
+    MS_DISPATCH((rc = set_smem(mask_mean_fwd_kernel<3>, sm * 4), mask_mean_fwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, img, sums, counts)),
+                (rc = set_smem(mask_mean_fwd_kernel<6>, sm * 4), mask_mean_fwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, img, sums, counts)));
     return rc;
 }
 
-int launch_mask_mean_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, const float* G,
+int launch_mask_mean_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* img, const float* G,
                               const float* K, float* dfeat, float* dimg, cudaStream_t s) {
     const size_t sm = (size_t)M * (C + 1);
     int rc = check_shapes(M, C, HW, sm, "mask_mean_backward");
     if (rc) return rc;
     if (HW == 0) return 0;
-    MS_DISPATCH((rc = set_smem(mask_mean_bwd_kernel<3>, sm * 4), mask_mean_bwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, img, G, K, dfeat, dimg)),
-                (rc = set_smem(mask_mean_bwd_kernel<6>, sm * 4), mask_mean_bwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, img, G, K, dfeat, dimg)));
+    MS_DISPATCH((rc = set_smem(mask_mean_bwd_kernel<3>, sm * 4), mask_mean_bwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, img, G, K, dfeat, dimg)),
+                (rc = set_smem(mask_mean_bwd_kernel<6>, sm * 4), mask_mean_bwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, img, G, K, dfeat, dimg)));
     return rc;
 }
 
-int launch_mask_var_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* img, const float* mean,
+int launch_mask_var_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* img, const float* mean,
                             float* sq, cudaStream_t s) {
     const size_t sm = (size_t)M * C * 2;
     int rc = check_shapes(M, C, HW, sm, "mask_var_forward");
     if (rc) return rc;
     OGS_CUDA(cudaMemsetAsync(sq, 0, (size_t)M * C * 4, s));
     if (M == 0 || HW == 0) return 0;
-    MS_DISPATCH((rc = set_smem(mask_var_fwd_kernel<3>, sm * 4), mask_var_fwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, img, mean, sq)),
-                (rc = set_smem(mask_var_fwd_kernel<6>, sm * 4), mask_var_fwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, img, mean, sq)));
+    MS_DISPATCH((rc = set_smem(mask_var_fwd_kernel<3>, sm * 4), mask_var_fwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, img, mean, sq)),
+                (rc = set_smem(mask_var_fwd_kernel<6>, sm * 4), mask_var_fwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, img, mean, sq)));
     return rc;
 }
 
-int launch_cohesion_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* mean, float* dsum,
+int launch_cohesion_forward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* mean, float* dsum,
                             float* npix, cudaStream_t s) {
     const size_t sm = (size_t)M * (C + 2);
     int rc = check_shapes(M, C, HW, sm, "cohesion_forward");
@@ -388,21 +485,41 @@ int launch_cohesion_forward(int M, int C, int64_t HW, const float* feat, const u
     OGS_CUDA(cudaMemsetAsync(dsum, 0, (size_t)M * 4, s));
     OGS_CUDA(cudaMemsetAsync(npix, 0, (size_t)M * 4, s));
     if (M == 0 || HW == 0) return 0;
-    MS_DISPATCH((rc = set_smem(cohesion_fwd_kernel<3>, sm * 4), cohesion_fwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, mean, dsum, npix)),
-                (rc = set_smem(cohesion_fwd_kernel<6>, sm * 4), cohesion_fwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, mean, dsum, npix)));
+    MS_DISPATCH((rc = set_smem(cohesion_fwd_kernel<3>, sm * 4), cohesion_fwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, mean, dsum, npix)),
+                (rc = set_smem(cohesion_fwd_kernel<6>, sm * 4), cohesion_fwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, mean, dsum, npix)));
     return rc;
 }
 
-int launch_cohesion_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const float* mean, const float* coef,
+int launch_cohesion_backward(int M, int C, int64_t HW, const float* feat, const uint8_t* masks, const int16_t* ids, const int32_t* overlap, const float* mean, const float* coef,
                              float* dfeat, float* dmean, cudaStream_t s) {
     const size_t sm = (size_t)M * (2 * C + 1);
     int rc = check_shapes(M, C, HW, sm, "cohesion_backward");
     if (rc) return rc;
     OGS_CUDA(cudaMemsetAsync(dmean, 0, (size_t)M * C * 4, s));
     if (HW == 0) return 0;
-    MS_DISPATCH((rc = set_smem(cohesion_bwd_kernel<3>, sm * 4), cohesion_bwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, mean, coef, dfeat, dmean)),
-                (rc = set_smem(cohesion_bwd_kernel<6>, sm * 4), cohesion_bwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, mean, coef, dfeat, dmean)));
+    MS_DISPATCH((rc = set_smem(cohesion_bwd_kernel<3>, sm * 4), cohesion_bwd_kernel<3><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, mean, coef, dfeat, dmean)),
+                (rc = set_smem(cohesion_bwd_kernel<6>, sm * 4), cohesion_bwd_kernel<6><<<MS_GRID(HW), MS_THREADS, sm * 4, s>>>(M, HW, feat, masks, ids, overlap, mean, coef, dfeat, dmean)));
     return rc;
+}
+
+int launch_mask_id_map(int M, int64_t HW, const uint8_t* masks, int16_t* ids, int32_t* overlap, cudaStream_t s) {
+    if (M < 0 || HW < 0 || M > 32767) { set_error("mask_id_map: bad sizes M=%d HW=%lld (at most 32767 masks)", M, (long long)HW); return -1; }
+    OGS_CUDA(cudaMemsetAsync(overlap, 0, 4, s));
+    if (HW == 0) return 0;
+    mask_id_map_kernel<<<MS_GRID(HW), MS_THREADS, 0, s>>>(M, HW, masks, ids, overlap);
+    return 0;
+}
+
+int launch_sam_masks(int M, int64_t HW, const int32_t* level_ids, int offset, int64_t* mask_id, uint8_t* invalid_pix,
+                     int16_t* ids, uint8_t* masks, cudaStream_t s) {
+    if (M < 0 || HW < 0 || M > 32767) { set_error("sam_masks: bad sizes M=%d HW=%lld (at most 32767 masks)", M, (long long)HW); return -1; }
+    if (HW == 0) return 0;
+    sam_ids_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, s>>>(M, HW, level_ids, offset, mask_id, invalid_pix, ids);
+    if (M > 0) {
+        const dim3 grid((unsigned)((HW + 16 * 256 - 1) / (16 * 256)), (unsigned)M);
+        mask_expand_kernel<<<grid, 256, 0, s>>>(HW, ids, masks);
+    }
+    return 0;
 }
 
 }  // namespace ogs

@@ -377,7 +377,8 @@ def _side_streams(device, n):
 
 def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.Tensor], group=None,
                           already_split: bool = False, streams: int = 1,
-                          fuse_accumulate: bool = True, reduce: bool = True, lookahead: int = 1) -> Optional[torch.Tensor]:
+                          fuse_accumulate: bool = True, reduce: bool = True, lookahead: int = 1,
+                          defer_capacity_check: bool = True) -> Optional[torch.Tensor]:
     """One view-parallel step: this rank renders ITS views (`render_loss(view) -> scalar loss`),
     backpropagates, and the parameter gradients of all ranks are summed.  Equivalent to one
     process rendering every view and summing the losses.
@@ -394,8 +395,15 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
     each stay in view order, so the gradients are summed in the same order): the rasterizer's forward makes the host
     wait for the frame's duplicate count, and with the previous view's backward still to be queued behind it the GPU
     always has more than a millisecond of work in its queue while the host catches up (without it the queue holds
-    0.45 ms at that point and runs dry whenever the host needs longer).  Costs one extra forward state in memory."""
-    from .rasterizer import fuse_grad_accumulation
+    0.45 ms at that point and runs dry whenever the host needs longer).  Costs one extra forward state in memory.
+    ``defer_capacity_check`` (default) removes that wait altogether by treating the step as a transaction: when no
+    parameter holds a ``.grad`` on entry, the forwards run under ``rasterizer.deferred_capacity_check`` (buffers sized
+    from the running estimate, nothing read back), and once every backward has been queued -- BEFORE the gradients
+    meet any collective -- the frames' real counts are checked.  If one did not fit (a view with over 25 % more
+    duplicates than any recent one: rare), the gradients are dropped and the rank's views are rendered again with the
+    ordinary synchronous check; ``render_loss`` is then called a second time for those views, so it must be a function
+    of the parameters and the view only (side effects happen twice)."""
+    from .rasterizer import capacity_overflowed, deferred_capacity_check, fuse_grad_accumulation
     mine = views if already_split else split_views(views, group)
     params = list(params)
     total = None
@@ -439,19 +447,30 @@ def render_views_backward(render_loss, views: Sequence, params: Iterable[torch.T
             p_.record_stream(cur)
             total = p_ if total is None else total + p_
     else:
-        pending = []                      # forwards whose backward has not been issued yet (at most `lookahead`)
-        with fuse_grad_accumulation(fuse_accumulate):
-            for v in list(mine) + [None] * max(0, lookahead):
-                if v is not None:
-                    pending.append(render_loss(v))
-                if pending and (v is None or len(pending) > max(0, lookahead)):
+        def local_pass(defer):
+            tot = None
+            pending = []                  # forwards whose backward has not been issued yet (at most `lookahead`)
+            with fuse_grad_accumulation(fuse_accumulate), deferred_capacity_check(defer):
+                for v in list(mine) + [None] * max(0, lookahead):
+                    if v is not None:
+                        pending.append(render_loss(v))
+                    if pending and (v is None or len(pending) > max(0, lookahead)):
+                        part = finish(pending.pop(0))
+                        if part is not None:
+                            tot = part if tot is None else tot + part
+                while pending:
                     part = finish(pending.pop(0))
                     if part is not None:
-                        total = part if total is None else total + part
-            while pending:
-                part = finish(pending.pop(0))
-                if part is not None:
-                    total = part if total is None else total + part
+                        tot = part if tot is None else tot + part
+            return tot
+
+        defer = bool(defer_capacity_check and mine and params and params[0].is_cuda
+                     and all(p.grad is None for p in params))
+        total = local_pass(defer)
+        if defer and capacity_overflowed(params[0].device):
+            for p in params:
+                p.grad = None
+            total = local_pass(False)
     r, w = world(group)
     if not reduce:          # measurement aid: the step without its collectives (bench.py's exposed-collective figure)
         return total

@@ -24,6 +24,58 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+ID_MAP_MIN_MASKS = 16     # below this the M mask bytes per pixel are as cheap as building the id map
+
+
+class _MaskSet:
+    """Device-side forms of one ``gt_masks`` tensor: ``bytes`` [M,H*W] uint8 and, for M >= ID_MAP_MIN_MASKS, the id map
+    ``ids`` [H*W] int16 with its device-side ``overlap`` flag (C ABI ogs_mask_id_map).  SAM masks are a partition of
+    the image, so the four passes of a Stage-1 step read 2 B per pixel instead of M B; overlapping masks set the
+    flag and the kernels walk the mask rows as before -- no host synchronisation either way."""
+    __slots__ = ("bytes", "ids", "overlap")
+
+    def __init__(self, gt_masks, ids=None):
+        masks = gt_masks.detach()
+        if masks.dtype != torch.bool:
+            masks = masks != 0
+        M = masks.shape[0]
+        HW = masks.shape[1] * masks.shape[2]
+        self.bytes = masks.contiguous().view(torch.uint8).view(M, HW)
+        self.ids = self.overlap = None
+        dev = masks.device
+        if ids is not None and M <= 32767:
+            self.ids = ids.detach().to(torch.int16).contiguous().view(HW)
+            self.overlap = torch.zeros(1, dtype=torch.int32, device=dev)
+        elif ID_MAP_MIN_MASKS <= M <= 32767 and HW > 0:
+            self.ids = torch.empty(HW, dtype=torch.int16, device=dev)
+            self.overlap = torch.empty(1, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                rc = _lib.lib().ogs_mask_id_map(M, HW, _lib.ptr(self.bytes), _lib.ptr(self.ids), _lib.ptr(self.overlap),
+                                                _stream(dev))
+            _lib.check(rc, "ogs_mask_id_map")
+
+
+# The mask set of the LAST gt_masks tensor seen: mask_feature_mean and cohesion_loss of one training step receive the
+# same tensor (train.py:450-452).  The entry holds a strong reference to that tensor, so `is` cannot match a new
+# tensor at a recycled address; an in-place edit bumps `_version` and misses.
+_last = {"src": None, "version": -1, "set": None}
+
+
+def register_mask_ids(gt_masks, ids):
+    """Declare that ``gt_masks`` [M,H,W] is the one-hot expansion of ``ids`` [H,W] (-1 = no mask): the statistics
+    passes on ``gt_masks`` then read the id map.  ``get_SAM_mask_and_feat`` below calls this."""
+    if gt_masks.is_cuda:
+        _last.update(src=gt_masks, version=gt_masks._version, set=_MaskSet(gt_masks, ids))
+
+
+def _mask_set(gt_masks):
+    if _last["src"] is gt_masks and _last["version"] == gt_masks._version:
+        return _last["set"]
+    ms = _MaskSet(gt_masks)
+    _last.update(src=gt_masks, version=gt_masks._version, set=ms)
+    return ms
+
+
 def _prep(feat_map, gt_masks, image_mask=None):
     if not feat_map.is_cuda:
         raise _lib.OgsError("mask statistics need CUDA tensors (no CPU path)")
@@ -31,28 +83,30 @@ def _prep(feat_map, gt_masks, image_mask=None):
     M = gt_masks.shape[0]
     assert tuple(gt_masks.shape[1:]) == (H, W), "gt_masks must be [num_mask, H, W]"
     feat = feat_map.detach().float().contiguous()
-    masks = gt_masks.detach()
-    if masks.dtype != torch.bool:
-        masks = masks != 0
-    masks = masks.contiguous().view(torch.uint8)
+    ms = _mask_set(gt_masks)
     img = None
     if image_mask is not None:
         img = image_mask.detach().float().expand(1, H, W).contiguous().view(H * W)
-    return feat, masks, img, M, Cn, H * W
+    return feat, ms, img, M, Cn, H * W
+
+
+def _mask_ptrs(ms):
+    return _lib.ptr(ms.bytes), _lib.ptr(ms.ids), _lib.ptr(ms.overlap)
 
 
 class _MaskMean(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat_map, gt_masks, image_mask):
-        feat, masks, img, M, Cn, HW = _prep(feat_map, gt_masks, image_mask)
+        feat, ms, img, M, Cn, HW = _prep(feat_map, gt_masks, image_mask)
         dev = feat.device
         sums = torch.empty(M, Cn, device=dev)
         counts = torch.empty(M, device=dev)
-        _lib.check(_lib.lib().ogs_mask_mean_forward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(img),
+        _lib.check(_lib.lib().ogs_mask_mean_forward(M, Cn, HW, _lib.ptr(feat), *_mask_ptrs(ms), _lib.ptr(img),
                                                    _lib.ptr(sums), _lib.ptr(counts), _stream(dev)), "ogs_mask_mean_forward")
         cnt = counts.clamp(min=1)
         mean = sums / cnt[:, None]
-        ctx.save_for_backward(feat, masks, img if img is not None else torch.empty(0, device=dev), counts, mean)
+        ctx.save_for_backward(feat, img if img is not None else torch.empty(0, device=dev), counts, mean)
+        ctx.ms = ms
         ctx.has_img = img is not None
         ctx.shape = feat_map.shape
         ctx.img_shape = None if image_mask is None else image_mask.shape
@@ -61,7 +115,7 @@ class _MaskMean(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_mean, _g_counts):
-        feat, masks, img, counts, mean = ctx.saved_tensors
+        feat, img, counts, mean = ctx.saved_tensors
         img = img if ctx.has_img else None
         M, Cn = mean.shape
         HW = feat.shape[1] * feat.shape[2]
@@ -70,7 +124,7 @@ class _MaskMean(torch.autograd.Function):
         K = torch.where(counts > 1, (G * mean).sum(1), torch.zeros_like(counts)).contiguous()
         dfeat = torch.empty_like(feat)
         dimg = torch.empty(HW, device=dev) if img is not None else None
-        _lib.check(_lib.lib().ogs_mask_mean_backward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(img), _lib.ptr(G),
+        _lib.check(_lib.lib().ogs_mask_mean_backward(M, Cn, HW, _lib.ptr(feat), *_mask_ptrs(ctx.ms), _lib.ptr(img), _lib.ptr(G),
                                                     _lib.ptr(K), _lib.ptr(dfeat), _lib.ptr(dimg), _stream(dev)),
                    "ogs_mask_mean_backward")
         g_img = None
@@ -87,10 +141,10 @@ def mask_feature_mean(feat_map, gt_masks, image_mask=None, return_var=False):
     mean, counts = _MaskMean.apply(feat_map, gt_masks, image_mask)
     if not return_var:
         return mean
-    feat, masks, img, M, Cn, HW = _prep(feat_map, gt_masks, image_mask)
+    feat, ms, img, M, Cn, HW = _prep(feat_map, gt_masks, image_mask)
     sq = torch.empty(M, Cn, device=feat.device)
     mean_d = mean.detach().contiguous()
-    _lib.check(_lib.lib().ogs_mask_var_forward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(img), _lib.ptr(mean_d),
+    _lib.check(_lib.lib().ogs_mask_var_forward(M, Cn, HW, _lib.ptr(feat), *_mask_ptrs(ms), _lib.ptr(img), _lib.ptr(mean_d),
                                               _lib.ptr(sq), _stream(feat.device)), "ogs_mask_var_forward")
     cnt = counts.clamp(min=1)
     variance = (sq / cnt[:, None]).mean(dim=1)
@@ -100,27 +154,28 @@ def mask_feature_mean(feat_map, gt_masks, image_mask=None, return_var=False):
 class _Cohesion(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat_map, gt_mask, feat_mean_stack):
-        feat, masks, _, M, Cn, HW = _prep(feat_map, gt_mask)
+        feat, ms, _, M, Cn, HW = _prep(feat_map, gt_mask)
         dev = feat.device
         mean = feat_mean_stack.detach().float().contiguous()
         dsum = torch.empty(M, device=dev)
         npix = torch.empty(M, device=dev)
-        _lib.check(_lib.lib().ogs_cohesion_forward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(mean), _lib.ptr(dsum),
+        _lib.check(_lib.lib().ogs_cohesion_forward(M, Cn, HW, _lib.ptr(feat), *_mask_ptrs(ms), _lib.ptr(mean), _lib.ptr(dsum),
                                                   _lib.ptr(npix), _stream(dev)), "ogs_cohesion_forward")
-        ctx.save_for_backward(feat, masks, mean, npix)
+        ctx.save_for_backward(feat, mean, npix)
+        ctx.ms = ms
         ctx.shape = feat_map.shape
         return (dsum / npix.clamp(min=1)).mean() if M > 0 else feat.new_zeros(())
 
     @staticmethod
     def backward(ctx, g):
-        feat, masks, mean, npix = ctx.saved_tensors
+        feat, mean, npix = ctx.saved_tensors
         M, Cn = mean.shape
         HW = feat.shape[1] * feat.shape[2]
         dev = feat.device
         coef = (g.float() / (max(M, 1) * npix.clamp(min=1))).contiguous()
         dfeat = torch.empty_like(feat)
         dmean = torch.empty(M, Cn, device=dev)
-        _lib.check(_lib.lib().ogs_cohesion_backward(M, Cn, HW, _lib.ptr(feat), _lib.ptr(masks), _lib.ptr(mean), _lib.ptr(coef),
+        _lib.check(_lib.lib().ogs_cohesion_backward(M, Cn, HW, _lib.ptr(feat), *_mask_ptrs(ctx.ms), _lib.ptr(mean), _lib.ptr(coef),
                                                    _lib.ptr(dfeat), _lib.ptr(dmean), _stream(dev)), "ogs_cohesion_backward")
         return dfeat.view(ctx.shape), None, dmean
 
@@ -178,15 +233,56 @@ def pair_mask_feature_mean(feat_map, masks):
     One single-mask streaming pass per pair."""
     outs = []
     for i in range(feat_map.shape[0]):
-        m = masks[i:i + 1]
-        feat, mk, _, M, Cn, HW = _prep(feat_map[i], m)
+        if not feat_map.is_cuda:
+            raise _lib.OgsError("mask statistics need CUDA tensors (no CPU path)")
+        feat = feat_map[i].detach().float().contiguous()
+        Cn, HW = feat.shape[0], feat.shape[1] * feat.shape[2]
+        mk = _MaskSet(masks[i:i + 1])              # one mask: no id map, and the step's cached mask set stays
         sums = torch.empty(1, Cn, device=feat.device)
         counts = torch.empty(1, device=feat.device)
         w = masks[i].detach().float().contiguous().view(HW)     # the reference multiplies by masks.float()
-        _lib.check(_lib.lib().ogs_mask_mean_forward(1, Cn, HW, _lib.ptr(feat), _lib.ptr(mk), _lib.ptr(w), _lib.ptr(sums),
+        _lib.check(_lib.lib().ogs_mask_mean_forward(1, Cn, HW, _lib.ptr(feat), *_mask_ptrs(mk), _lib.ptr(w), _lib.ptr(sums),
                                                    _lib.ptr(counts), _stream(feat.device)), "ogs_mask_mean_forward")
         outs.append(sums[0] / (counts[0] + 1e-6))
     return torch.stack(outs) if outs else feat_map.new_zeros(0, feat_map.shape[1])
+
+
+def get_SAM_mask_and_feat(gt_sam_mask, level=3, filter_th=50, original_mask_feat=None, sample_mask=False, num_mask=None,
+                          prev_max=None):
+    """Per-view SAM masks from the 4-level id map ``gt_sam_mask`` [4,H,W] (reference utils/opengs_utlis.py:125-182):
+    returns ``mask_id`` [H,W] (0 = invalid pixel, 1..num_mask), ``mask_bool`` [num_mask,H,W] (mask 0, the invalid pixels,
+    excluded), optionally the masks' language features, and ``invalid_pix`` [H,W].  ``filter_th`` / ``sample_mask`` are
+    unused, as in the reference.  Differences: ``mask_bool`` is a torch.bool tensor written by one kernel (C ABI
+    ogs_sam_masks; the reference materialises an int64 one-hot, 8x the bytes, and re-derives mask_id with an argmax that
+    returns it unchanged), and the id map is registered for the Stage-1 statistics passes (``register_mask_ids``).  ``num_mask`` (this level's mask
+    count) and ``prev_max`` (the previous level's largest id) are properties of the view's SAM file: a trainer that
+    stores them at load time passes them here and the call makes no device-to-host read (the reference does two per
+    step, :138 and :146)."""
+    if not gt_sam_mask.is_cuda:
+        raise _lib.OgsError("get_SAM_mask_and_feat needs a CUDA id map (no CPU path)")
+    dev = gt_sam_mask.device
+    H, W = gt_sam_mask.shape[1:]
+    HW = H * W
+    level_ids = gt_sam_mask[level].to(torch.int32).contiguous()
+    offset = 0
+    if level > 0:
+        offset = int(gt_sam_mask[level - 1].max().item() if prev_max is None else prev_max) + 1
+    num = int((level_ids.max().item() - offset + 1) if num_mask is None else num_mask)
+    num = max(num, 0)
+    mask_id = torch.empty(H, W, dtype=torch.int64, device=dev)
+    invalid_pix = torch.empty(H, W, dtype=torch.bool, device=dev)
+    ids = torch.empty(HW, dtype=torch.int16, device=dev)
+    mask_bool = torch.empty(num, H, W, dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ogs_sam_masks(num, HW, _lib.ptr(level_ids), offset, _lib.ptr(mask_id), _lib.ptr(invalid_pix),
+                                      _lib.ptr(ids), _lib.ptr(mask_bool), _stream(dev))
+    _lib.check(rc, "ogs_sam_masks")
+    register_mask_ids(mask_bool, ids)
+    if original_mask_feat is not None:
+        max_ind = int(gt_sam_mask[level].max()) + 1
+        min_ind = int(gt_sam_mask[level - 1].max()) + 1 if level > 0 else 0
+        return mask_id, mask_bool, original_mask_feat.clone()[min_ind:max_ind, :], invalid_pix
+    return mask_id, mask_bool, invalid_pix
 
 
 def _as_mask_bytes(masks):

@@ -91,6 +91,7 @@ def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities,
     ri.sh_degree = int(rs.sh_degree)
     ri.M = 0 if shs is None else int(shs.shape[1]) + (0 if shs_rest is None else int(shs_rest.shape[1]))
     ri.act_flags = int(act_flags)
+    ri.defer_capacity_check = int(_DEFER_CAPACITY)
     ri.shs_rest = _lib.ptr(shs_rest)
     ri.n_extra = n_extra
     ri.W = int(rs.image_width)
@@ -116,6 +117,7 @@ def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities,
 
 
 _FUSE_ACCUMULATE = False
+_DEFER_CAPACITY = False
 _GRAD_ARENA = {}      # device index -> flat fp32 tensor the backward carves its gradient buffer from (dist.GradArena)
 
 
@@ -128,6 +130,45 @@ def set_grad_arena(t: Optional[torch.Tensor]):
         _GRAD_ARENA.clear()
     else:
         _GRAD_ARENA[t.device.index] = t
+
+
+class deferred_capacity_check:
+    """Context manager: forwards issued inside do NOT wait for their frame's (Gaussian, tile) duplicate count -- the one
+    host<->device synchronisation of a frame (C ABI in->defer_capacity_check).  The caller must call
+    ``capacity_overflowed(device)`` afterwards, from the same thread, and discard and redo everything computed from
+    those frames when it returns True (the buffers were sized from a running estimate that proved too small; the
+    estimate has been raised).  opengaussian_b200.dist.render_views_backward wraps a whole step this way."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global _DEFER_CAPACITY
+        self.prev = _DEFER_CAPACITY
+        _DEFER_CAPACITY = self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFER_CAPACITY
+        _DEFER_CAPACITY = self.prev
+        return False
+
+
+def capacity_overflowed(device) -> bool:
+    """Resolves every forward this thread issued on ``device`` under ``deferred_capacity_check``: True when at least
+    one frame needed more (Gaussian, tile) entries than its buffers held -- its outputs are truncated."""
+    with torch.cuda.device(device):
+        rc = _lib.lib().ogs_raster_capacity_check()
+    if rc < 0:
+        _lib.check(rc, "ogs_raster_capacity_check")
+    return rc == 1
+
+
+def capacity_hint(device, new_hint: int = -1) -> int:
+    """Reads (and with ``new_hint >= 0`` replaces; 0 = forget) this thread's running estimate of the number of
+    (Gaussian, tile) entries per frame on ``device`` (C ABI ogs_raster_capacity_hint)."""
+    with torch.cuda.device(device):
+        return int(_lib.lib().ogs_raster_capacity_hint(int(new_hint)))
 
 
 class fuse_grad_accumulation:

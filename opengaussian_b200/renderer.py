@@ -117,7 +117,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
 
     # probabilistically rescale (same RNG draws as the reference, :121-124)
     prob = torch.rand(1)
-    rescale_factor = torch.tensor(1.0, dtype=torch.float32, device=xyz.device)
+    rescale_factor = None         # 1.0: the reference builds a device scalar here every call (:122, a host->device copy)
     rescaled = False
     if prob > 0.5 and rescale:
         rescale_factor = torch.rand(1).to(xyz.device)

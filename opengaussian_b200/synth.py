@@ -196,15 +196,34 @@ class SynthModel:
         return torch.nn.functional.normalize(f, dim=1)
 
 
-def sam_like_masks(M: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
-    """[M,H,W] bool: a partition-like set of compact regions (rectangles painted in order), mask 0 = rest."""
+def sam_like_ids(M: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
+    """[H,W] int64 in [0, M): compact regions (rectangles painted in order), id 0 = the rest of the image."""
     g = torch.Generator().manual_seed(seed)
     ids = torch.zeros(H, W, dtype=torch.int64)
     for m in range(1, M):
         y0, x0 = int(torch.randint(0, H - 8, (1,), generator=g)), int(torch.randint(0, W - 8, (1,), generator=g))
         h, w = int(torch.randint(8, H // 3, (1,), generator=g)), int(torch.randint(8, W // 3, (1,), generator=g))
         ids[y0:y0 + h, x0:x0 + w] = m
+    return ids
+
+
+def sam_like_masks(M: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
+    """[M,H,W] bool: the one-hot expansion of sam_like_ids (a partition of the image)."""
+    ids = sam_like_ids(M, H, W, seed)
     return torch.stack([(ids == m) for m in range(M)])
+
+
+def sam_like_id_map(M: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
+    """[4,H,W] int32 in the dataset's layout (the `original_sam_mask` of a view, utils/opengs_utlis.py:125-148): level 0
+    holds sam_like_ids (ids 0..M-1), the other levels coarser partitions whose ids continue after the previous level's
+    maximum.  get_SAM_mask_and_feat(level=0) of it returns exactly sam_like_masks(M, H, W, seed)."""
+    l0 = sam_like_ids(M, H, W, seed)
+    levels, base = [l0], M
+    for k in (2, 3, 4):
+        lv = sam_like_ids(max(M // k, 2), H, W, seed + k) + base
+        levels.append(lv)
+        base = int(lv.max()) + 1
+    return torch.stack(levels).to(torch.int32)
 
 
 def blob_labels(gs, n_blobs: int, seed: int = 0) -> torch.Tensor:

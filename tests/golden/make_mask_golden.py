@@ -8,6 +8,10 @@
   imported here (pytorch3d, plyfile, a CUDA device ...), so the two function definitions are taken
   from its source with `ast` and executed unchanged.
 
+* utils/opengs_utlis.py::get_SAM_mask_and_feat (:125-182) on a synthetic 4-level SAM id map (`sam_inputs`), at levels 0
+  and 3; the masks it returns (a PARTITION of the image, 20+ masks: the id-map path of csrc/mask_stats.cu) then go
+  through the same Stage-1 loss.
+
 Stored: the reference outputs and the autograd gradients of the Stage-1 loss
 (train.py:450-456: loss = separation + 0.1 * cohesion) w.r.t. feat_map and image_mask.
 Run in the build container only:  python tests/golden/make_mask_golden.py
@@ -56,6 +60,24 @@ def iou_inputs(name):
     return masks, other
 
 
+def sam_inputs():
+    """A 4-level SAM id map [4,H,W] (int32) as the dataset stores it: level l's ids continue after level l-1's maximum,
+    -1 marks pixels without a mask; plus a feature map and a silhouette for the Stage-1 loss."""
+    H, W = 40, 52
+    rs = np.random.RandomState(41)
+    levels, base = [], 0
+    for l, (gy, gx) in enumerate(((3, 4), (4, 5), (2, 3), (5, 5))):
+        yy, xx = np.mgrid[0:H, 0:W]
+        ids = (yy * gy // H) * gx + (xx * gx // W) + base
+        ids = np.where(rs.rand(H, W) < 0.07, -1, ids)                 # invalid pixels
+        ids[yy + xx * (l + 1) % 7 == 3] = -1
+        levels.append(ids.astype(np.int32))
+        base = int(ids.max()) + 1
+    feat = rs.rand(6, H, W).astype(np.float32)
+    img = ((rs.rand(1, H, W) > 0.1) * rs.rand(1, H, W)).astype(np.float32)
+    return np.stack(levels), feat, img
+
+
 def load_reference():
     sys.modules.setdefault("bitarray", types.SimpleNamespace(bitarray=object))
     spec = importlib.util.spec_from_file_location("ref_opengs_utlis", os.path.join(REF, "utils/opengs_utlis.py"))
@@ -101,6 +123,29 @@ def main():
                 # int32 inputs exercise the reference's .to(torch.bool) branch (:100-103)
                 iou = ref.calculate_iou(torch.from_numpy(m1), torch.from_numpy(m2.astype(np.int32)), base=base)
                 out[f"{name}/iou_{base}"] = iou.numpy()
+    sam, feat_np, img_np = sam_inputs()
+    for level in (0, 3):
+        mask_id, mask_bool, invalid = ref.get_SAM_mask_and_feat(torch.from_numpy(sam), level=level)
+        feat = torch.from_numpy(feat_np).requires_grad_(True)
+        img = torch.from_numpy(img_np).requires_grad_(True)
+        mean = ref.mask_feature_mean(feat, mask_bool, image_mask=img)
+        loss_c = cohesion_loss(feat, mask_bool, mean)
+        loss_s = separation_loss(mean, 1000)
+        (loss_s + 0.1 * loss_c).backward()
+        k = f"sam_l{level}"
+        out[f"{k}/mask_id"] = mask_id.numpy()
+        out[f"{k}/mask_bool"] = np.packbits(mask_bool.numpy().astype(bool), axis=None)
+        out[f"{k}/mask_bool_shape"] = np.array(mask_bool.shape)
+        out[f"{k}/invalid_pix"] = invalid.numpy()
+        out[f"{k}/mean"] = mean.detach().numpy()
+        out[f"{k}/cohesion"] = loss_c.detach().numpy()
+        out[f"{k}/separation"] = loss_s.detach().numpy()
+        out[f"{k}/dfeat"] = feat.grad.numpy()
+        out[f"{k}/dimg"] = img.grad.numpy()
+        with torch.no_grad():
+            _, var, cnt = ref.mask_feature_mean(feat.detach(), mask_bool, return_var=True)
+            out[f"{k}/var"] = var.numpy()
+            out[f"{k}/cnt"] = cnt.numpy()
     path = os.path.join(HERE, "mask_stats_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, sorted(out)[:8])

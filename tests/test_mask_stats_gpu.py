@@ -51,6 +51,105 @@ def test_stage1_loss_vs_reference_golden(name):
     _close(pm.cpu(), gold[f"{name}/pair_mean"], 1e-5, "pair_mean")
 
 
+@pytest.mark.parametrize("level", [0, 3])
+@pytest.mark.parametrize("how", ["registered", "derived", "int64_onehot"])
+def test_sam_partition_vs_reference_golden(level, how):
+    """The reference's get_SAM_mask_and_feat -> mask_feature_mean -> cohesion/separation chain on a 4-level SAM id map
+    (level 0: 12 masks, the mask-row walk; level 3: 25 masks, the id-map walk), with the id map registered by the
+    drop-in get_SAM_mask_and_feat, derived on the device from bool masks, or from the reference's int64 one-hot."""
+    from opengaussian_b200 import mask_stats as ms
+    m, gold = _gm(), np.load(GOLD)
+    sam, feat_np, img_np = m.sam_inputs()
+    k = f"sam_l{level}"
+    mask_id, mask_bool, invalid = ms.get_SAM_mask_and_feat(torch.from_numpy(sam).cuda(), level=level)
+    shape = tuple(int(v) for v in gold[f"{k}/mask_bool_shape"])
+    gold_bool = np.unpackbits(gold[f"{k}/mask_bool"])[: int(np.prod(shape))].reshape(shape).astype(bool)
+    assert mask_bool.dtype == torch.bool and np.array_equal(mask_bool.cpu().numpy(), gold_bool)
+    assert np.array_equal(mask_id.cpu().numpy(), gold[f"{k}/mask_id"])
+    assert np.array_equal(invalid.cpu().numpy(), gold[f"{k}/invalid_pix"])
+    if how == "registered":
+        assert ms._last["src"] is mask_bool and ms._last["set"].ids is not None
+    elif how == "derived":
+        mask_bool = mask_bool.clone()                      # a new tensor: the id map is rebuilt by ogs_mask_id_map
+    else:
+        mask_bool = torch.nn.functional.one_hot(mask_id, shape[0] + 1).permute(2, 0, 1)[1:]   # reference :146-148,182
+    feat = torch.from_numpy(feat_np).cuda().requires_grad_(True)
+    img = torch.from_numpy(img_np).cuda().requires_grad_(True)
+    mean = ms.mask_feature_mean(feat, mask_bool, image_mask=img)
+    used = ms._last["set"]
+    assert ms._last["src"] is mask_bool
+    if shape[0] >= ms.ID_MAP_MIN_MASKS or how == "registered":
+        assert used.ids is not None and int(used.overlap.item()) == 0
+        assert np.array_equal(used.ids.cpu().numpy().reshape(shape[1:]), gold[f"{k}/mask_id"] - 1)
+    lc = ms.cohesion_loss(feat, mask_bool, mean)
+    assert ms._last["set"] is used                         # the second pass reuses the step's mask set
+    ls = ms.separation_loss(mean, 1000)
+    (ls + 0.1 * lc).backward()
+    _close(mean.detach().cpu(), gold[f"{k}/mean"], 1e-5, "mean")
+    _close(lc.detach().cpu(), gold[f"{k}/cohesion"], 1e-5, "cohesion")
+    _close(ls.detach().cpu(), gold[f"{k}/separation"], 1e-5, "separation")
+    _close(feat.grad.cpu(), gold[f"{k}/dfeat"], 1e-4, "dfeat")
+    _close(img.grad.cpu(), gold[f"{k}/dimg"], 1e-4, "dimg")
+    _, var, cnt = ms.mask_feature_mean(feat.detach(), mask_bool, return_var=True)
+    _close(var.cpu(), gold[f"{k}/var"], 1e-5, "var")
+    assert np.array_equal(cnt.cpu().numpy(), gold[f"{k}/cnt"])
+
+
+def test_overlapping_masks_ignore_the_id_map():
+    """24 masks of which two overlap: the device-side flag sends every pass down the mask-row walk (vs the CPU oracle);
+    an in-place edit of the masks invalidates the cached mask set."""
+    from opengaussian_b200 import mask_stats as ms
+    from oracle import mask_stats as oms
+    C, H, W, M = 6, 70, 93, 24
+    g = torch.Generator().manual_seed(8)
+    masks = _sam_like_masks(M, H, W, 9)
+    masks[5] |= masks[3]
+    masks[7, 10:30, 10:40] = True
+    feat0 = torch.rand(C, H, W, generator=g)
+    res = {}
+    for dev in ("cpu", "cuda"):
+        feat = feat0.clone().to(dev).requires_grad_(True)
+        mk = masks.to(dev)
+        fm, fc = (oms.mask_feature_mean, oms.cohesion_loss) if dev == "cpu" else (ms.mask_feature_mean, ms.cohesion_loss)
+        mean = fm(feat, mk)
+        (mean.pow(2).sum() + fc(feat, mk, mean)).backward()
+        res[dev] = (mean.detach().cpu(), feat.grad.cpu())
+        if dev == "cuda":
+            assert int(ms._last["set"].overlap.item()) == 1
+            first = ms._last["set"]
+            mk[5] &= ~mk[3]
+            mk[7, 10:30, 10:40] = False
+            mk[7] &= ~(mk.sum(0) > 1)
+            ms.mask_feature_mean(feat.detach(), mk)
+            assert ms._last["set"] is not first
+    _close(res["cuda"][0], res["cpu"][0], 2e-5, "mean")
+    _close(res["cuda"][1], res["cpu"][1], 1e-4, "dfeat")
+
+
+def test_id_map_walk_equals_mask_row_walk(monkeypatch):
+    """Same partition masks through both walks (the id-map threshold forced out of reach for the second run)."""
+    from opengaussian_b200 import mask_stats as ms
+    C, H, W, M = 3, 211, 307, 40                         # H*W odd: ragged last lane, unaligned rows
+    masks = _sam_like_masks(M, H, W, 5).cuda()
+    masks[0] = False                                     # pixels in no mask at all
+    g = torch.Generator().manual_seed(2)
+    feat0 = torch.rand(C, H, W, generator=g).cuda()
+    img0 = torch.rand(1, H, W, generator=g).cuda()
+    out = []
+    for thresh in (16, 10 ** 6):
+        monkeypatch.setattr(ms, "ID_MAP_MIN_MASKS", thresh)
+        ms._last.update(src=None, set=None)
+        feat, img = feat0.clone().requires_grad_(True), img0.clone().requires_grad_(True)
+        mean = ms.mask_feature_mean(feat, masks, image_mask=img)
+        assert (ms._last["set"].ids is not None) == (thresh == 16)
+        lc = ms.cohesion_loss(feat, masks, mean)
+        (mean.pow(2).sum() + lc).backward()
+        _, var, cnt = ms.mask_feature_mean(feat.detach(), masks, image_mask=img.detach(), return_var=True)
+        out.append([t.detach().cpu() for t in (mean, lc, feat.grad, img.grad, var, cnt)])
+    for a, b, what in zip(out[0], out[1], ("mean", "cohesion", "dfeat", "dimg", "var", "cnt")):
+        _close(a, b, 2e-5, what)
+
+
 def _sam_like_masks(M, H, W, seed):
     from opengaussian_b200 import synth
     return synth.sam_like_masks(M, H, W, seed)

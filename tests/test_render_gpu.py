@@ -330,3 +330,64 @@ def test_frozen_geometry_skips_the_screen_space_gradient():
     assert not vs0.requires_grad and vs0.grad is not None and float(vs0.grad.abs().max()) == 0.0
     assert vs1.grad is not None and float(vs1.grad.abs().max()) > 0.0
     assert float((g0 - g1).abs().max()) <= 1e-5 * float(g1.abs().max())
+
+
+def test_deferred_capacity_check_transaction():
+    """render_views_backward treats a step as a transaction: the forwards do not wait for their duplicate counts
+    (rasterizer.deferred_capacity_check); when a frame did not fit the estimated capacity the step's gradients are
+    dropped and the views rendered again.  Same gradients as the synchronous path in both cases."""
+    from opengaussian_b200 import dist as ogd, rasterizer as rz
+    from opengaussian_b200.renderer import render
+    dev = torch.device("cuda")
+    gs, cams = synth.make_scene("plumbing_10k_256", n_views=3)
+    cam_ns = [_cam(c, dev) for c in cams]
+    bg = torch.zeros(3, device=dev)
+    pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    G = torch.randn(9, cam_ns[0].image_height, cam_ns[0].image_width, device=dev, generator=gen)
+    pc = synth.SynthModel(gs, dev, stage0=True)
+    params = [pc._xyz, pc._opacity, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation, pc._ins_feat]
+    params = [p for p in params if p.requires_grad]
+    calls = []
+
+    def view_loss(i):
+        calls.append(i)
+        out = render(cam_ns[i], pc, pipe, bg, 100, rescale=False)
+        return (torch.cat([out["render"], out["ins_feat"]]) * G).sum()
+
+    def step(**kw):
+        for p in params:
+            p.grad = None
+        calls.clear()
+        loss = ogd.render_views_backward(view_loss, [0, 1, 2], params, already_split=True, **kw)
+        return float(loss), [p.grad.clone() for p in params], list(calls)
+
+    def same(a, b):
+        for x, y in zip(a, b):
+            assert float((x - y).abs().max()) <= 2e-4 * float(y.abs().max()) + 1e-9
+
+    l_ref, g_ref, c_ref = step(defer_capacity_check=False)
+    assert c_ref == [0, 1, 2]
+    n_est = rz.capacity_hint(dev)
+    assert n_est > 0
+    # (1) estimate large enough: nothing is redone, nothing waited for
+    l1, g1, c1 = step()
+    assert c1 == [0, 1, 2] and abs(l1 - l_ref) <= 1e-4 * abs(l_ref)
+    same(g1, g_ref)
+    assert not rz.capacity_overflowed(dev)                   # nothing left pending
+    # (2) estimate far too small: the deferred frames are truncated, detected, and the step is redone
+    rz.capacity_hint(dev, 1024)
+    l2, g2, c2 = step()
+    assert c2 == [0, 1, 2, 0, 1, 2] and abs(l2 - l_ref) <= 1e-4 * abs(l_ref)
+    same(g2, g_ref)
+    assert rz.capacity_hint(dev) >= n_est // 2               # the check raised the estimate from the real counts
+    # (3) with a .grad already present the step is not a transaction: synchronous path, one pass
+    calls.clear()
+    ogd.render_views_backward(view_loss, [0], params, already_split=True)
+    assert calls == [0]
+    # (4) a forgotten estimate (0) makes the next forward synchronous even inside the context
+    rz.capacity_hint(dev, 0)
+    with rz.deferred_capacity_check():
+        out = render(cam_ns[0], pc, pipe, bg, 100, rescale=False)
+    assert not rz.capacity_overflowed(dev) and rz.capacity_hint(dev) > 0
+    assert float(out["render"].abs().sum()) > 0
