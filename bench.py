@@ -653,14 +653,21 @@ def kmeans_leg(cx, a):
     return km
 
 
-def stage1_leg(cx, iters=10):
+def stage1_leg(cx, iters=10, view_cache=False, graph=False):
     """BASELINE config 3 -- OpenGaussian's own training step (stage 1, train.py:352-456) on the synthetic ScanNet-like
     scene, one view per rank per step: ONE fused render (RGB + 6 feature channels + depth + alpha, raw parameters),
     the view's 120 SAM masks built from its id map (get_SAM_mask_and_feat), per-mask feature means, cohesion + separation losses, backward to `_ins_feat`, and on
-    N > 1 GPUs the all-reduce of the 24 MB ins_feat gradient."""
+    N > 1 GPUs the all-reduce of the 24 MB ins_feat gradient.
+    view_cache=False: every step projects, duplicates and sorts its view again, as the reference does.
+    view_cache=True: the geometry is frozen in this stage (train.py:431-436), so after a camera's first visit its
+    records and tile lists stay resident in HBM (rasterizer.ViewCache) and a step runs the feature activation, the
+    blend kernels, the mask statistics and the colour-only backward; every view is resident when the timing starts.
+    graph=True (needs view_cache): each camera's step is additionally captured as ONE CUDA graph on its second visit
+    (graphs.GraphedViewStep) and replayed afterwards -- the ~1 ms of Python / ctypes / autograd per step no longer bounds
+    it; the gradient all-reduce of N > 1 stays an ordinary call after the replay."""
     import types
     torch, dev = cx.torch, cx.dev
-    from opengaussian_b200 import dist as ogd, synth
+    from opengaussian_b200 import dist as ogd, rasterizer as rz, synth
     from opengaussian_b200.mask_stats import cohesion_loss, get_SAM_mask_and_feat, mask_feature_mean, separation_loss
     from opengaussian_b200.renderer import render
     name = "scannet_1m_1296x968"
@@ -688,15 +695,43 @@ def stage1_leg(cx, iters=10):
         pc._ins_feat.grad = None
         ogd.render_views_backward(view_loss, [i], [pc._ins_feat], already_split=True)
 
-    for i in range(3):
-        step(i)
-    ts, _ = cx.timed_repeats(step, 3, iters, 3)
+    gstep = None
+    if graph:
+        from opengaussian_b200.graphs import GraphedViewStep, geometry_guard
+        gstep = GraphedViewStep(view_loss, [pc._ins_feat], guard=geometry_guard(pc), key=lambda i: i % len(cam_ns))
+
+        def step(i):       # noqa: F811
+            gstep(i)
+            if cx.world > 1:
+                ogd.allreduce_gradients([pc._ins_feat])
+
+    rz.view_cache.clear()
+    rz.view_cache.enabled = bool(view_cache)
+    n_warm = (3 if graph else 1) * len(cam_ns) + 2
+    try:
+        for i in range(n_warm):
+            step(i)
+        ts, _ = cx.timed_repeats(step, n_warm, iters, 3)
+        vc = rz.view_cache.stats()
+    finally:
+        rz.view_cache.enabled = False
+        rz.view_cache.clear()
     ms = median(ts) / iters
-    return {"metric": "Stage-1 training steps/s (fused render + mask means + cohesion/separation losses, fwd+bwd"
-                      + (", ins_feat gradient all-reduce)" if cx.world > 1 else ")"),
-            "workload": name, "masks": 120, "views_per_step": cx.world, "ms_per_step": ms,
-            "steps_per_s": 1000.0 / ms, "views_per_s": cx.world * 1000.0 / ms,
-            "note": "the reference does 4 forward + 2 backward rasterizations and [M,6,H,W] mask tensors per step"}
+    res = {"metric": "Stage-1 training steps/s (fused render + mask means + cohesion/separation losses, fwd+bwd"
+                     + (", ins_feat gradient all-reduce)" if cx.world > 1 else ")"),
+           "workload": name, "masks": 120, "views_per_step": cx.world, "ms_per_step": ms,
+           "steps_per_s": 1000.0 / ms, "views_per_s": cx.world * 1000.0 / ms,
+           "note": "the reference does 4 forward + 2 backward rasterizations and [M,6,H,W] mask tensors per step"}
+    if view_cache:
+        res["view_cache"] = {"resident_views": vc["entries"], "bytes_per_view": vc["bytes"] // max(vc["entries"], 1),
+                             "hits": vc["hits"], "misses": vc["misses"],
+                             "what": "frozen geometry: per-camera records + depth-sorted tile lists kept in HBM after the "
+                                     "first visit; a step = feature activation + blend fwd + mask statistics + colour-only "
+                                     "bwd.  Images bit-identical to the uncached step (tests/test_view_cache_gpu.py)"}
+    if gstep is not None:
+        res["cuda_graph"] = dict(gstep.stats(), what="one captured graph per camera (fwd + losses + bwd), replayed with one launch; "
+                                                     "tests/test_graphs_gpu.py compares replay with the eager step")
+    return res
 
 
 def named_config_leg(cx, workload, V, fused_feat, K=8, R=3, label=""):
@@ -795,6 +830,8 @@ def run_ours(a):
     torch, world, rank = cx.torch, cx.world, cx.rank
     from opengaussian_b200 import _lib, dist as ogd
     _lib.lib()   # fails loudly if the CUDA library is missing
+    from opengaussian_b200 import rasterizer as _rz
+    _rz.view_cache.enabled = False   # every leg re-derives its views' geometry unless it says otherwise (stage1_step_view_cache)
     ogd.bind_to_gpu_numa_node(cx.local)      # pinned host buffers on the GPU's own NUMA node (8 ranks share the host)
 
     wl, stats, prof, clocks, ms, value, e2e_value, rep, exposed = raster_headline(cx, a)
@@ -814,6 +851,8 @@ def run_ours(a):
     if not a.no_kmeans:
         extras["kmeans"] = kmeans_leg(cx, a)
         extras["stage1_step"] = stage1_leg(cx)
+        extras["stage1_step_view_cache"] = stage1_leg(cx, view_cache=True)
+        extras["stage1_step_view_cache_graph"] = stage1_leg(cx, iters=20, view_cache=True, graph=True)
     if not a.no_configs:
         cfgs = {}
         cfgs["2_blender_300k_800"] = named_config_leg(cx, "blender_300k_800", 4, True, label="config 2: 300 k Gaussians, SH deg 3, 800x800, fwd+bwd RGB+ins_feat")

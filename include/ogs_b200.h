@@ -58,7 +58,7 @@
 extern "C" {
 #endif
 
-#define OGS_ABI_VERSION 5
+#define OGS_ABI_VERSION 6
 #define OGS_TILE 16
 #define OGS_MAX_CHANNELS 16 /* 3 colour channels + n_extra <= OGS_MAX_CHANNELS */
 
@@ -118,6 +118,8 @@ typedef struct ogs_raster_state {
     void* image;     /* final_T float[H*W], n_contrib uint32[H*W] */
     int64_t num_rendered; /* N = number of (Gaussian, tile) duplicates */
     int64_t geom_bytes, binning_bytes, image_bytes;
+    void* feat;      /* NULL, or the activated extra channels [P,n_extra] of THIS call when they do not live in `geom`
+                        (ogs_raster_forward_cached: `geom` is shared by every call that reuses the view) */
 } ogs_raster_state;
 
 typedef struct ogs_raster_grads_in {
@@ -167,6 +169,25 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
 int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* state,
                         const ogs_raster_grads_in* gin, const ogs_raster_grads_out* gout,
                         void* stream);
+
+/* Frozen-geometry view reuse.  From Stage 1 on OpenGaussian detaches xyz / scaling / rotation / opacity / SH
+ * (train.py:431-436) and only `_ins_feat` trains, yet every render() call of the reference re-runs preprocess, the
+ * duplicate emission and the 64-bit sort for a camera whose per-Gaussian records and tile lists cannot have changed.
+ * ogs_raster_forward_cached composites a frame from the `geom` and `binning` buffers an EARLIER ogs_raster_forward
+ * of the same camera and the same geometry inputs left in `cached` (the caller keeps them alive and decides validity:
+ * opengaussian_b200/rasterizer.py::ViewCache keys on the tensors' storage and version counters; ~95 MB per 1 M-Gaussian
+ * view, i.e. hundreds of training views of a scene fit the 180 GB of one B200).  Per call it allocates only the image
+ * state (final_T, n_contrib: tag "image") and, in raw-parameter mode, the activated extra channels (tag "feat"),
+ * recomputes those from in->extra, and runs the forward blend; `state` receives cached's geometry / binning pointers
+ * plus the new buffers and is what ogs_raster_backward takes.  in->extra, in->colors_precomp and in->bg may differ
+ * from the first call; everything else must be identical (not checked beyond the buffer sizes).  out->radii may be
+ * NULL (the caller kept the first call's).  Results are bit-identical to a fresh ogs_raster_forward. */
+int ogs_raster_forward_cached(const ogs_raster_inputs* in, const ogs_raster_outputs* out, ogs_alloc_fn alloc,
+                              void* alloc_user, const ogs_raster_state* cached, ogs_raster_state* state, void* stream);
+/* The leading bytes of a finished forward's `geom` and `binning` buffers that ogs_raster_forward_cached reads (the
+ * forward sizes `binning` for an estimate above N and `geom` may end with the activated extra channels): what a cache
+ * needs to keep. */
+int ogs_raster_cached_bytes(const ogs_raster_inputs* in, int64_t num_rendered, int64_t* geom_bytes, int64_t* binning_bytes);
 
 /* Deferred capacity check.  ogs_raster_forward sizes the (Gaussian, tile) buffers from a running estimate of N and, by
  * default, waits for the frame's real N before it returns -- the one host<->device synchronisation of a frame (the

@@ -34,7 +34,7 @@ class RasterOutputs(C.Structure):
 
 class RasterState(C.Structure):
     _fields_ = [("geom", _fp), ("binning", _fp), ("image", _fp), ("num_rendered", C.c_int64),
-                ("geom_bytes", C.c_int64), ("binning_bytes", C.c_int64), ("image_bytes", C.c_int64)]
+                ("geom_bytes", C.c_int64), ("binning_bytes", C.c_int64), ("image_bytes", C.c_int64), ("feat", _fp)]
 
 
 class RasterGradsIn(C.Structure):
@@ -71,6 +71,9 @@ EXPORTS = {
                                      C.POINTER(RasterState), C.c_void_p]),
     "ogs_raster_backward": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterState), C.POINTER(RasterGradsIn),
                                       C.POINTER(RasterGradsOut), C.c_void_p]),
+    "ogs_raster_forward_cached": (C.c_int, [C.POINTER(RasterInputs), C.POINTER(RasterOutputs), ALLOC_FN, C.c_void_p,
+                                            C.POINTER(RasterState), C.POINTER(RasterState), C.c_void_p]),
+    "ogs_raster_cached_bytes": (C.c_int, [C.POINTER(RasterInputs), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ogs_raster_capacity_check": (C.c_int, []),
     "ogs_raster_capacity_hint": (C.c_int64, [C.c_int64]),
     "ogs_raster_backward_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -130,7 +133,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ogs_abi_version() != 5:
+        if L.ogs_abi_version() != 6:
             raise OgsError("libogs_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

@@ -359,6 +359,74 @@ int ogs_raster_forward(const ogs_raster_inputs* in, const ogs_raster_outputs* ou
     return 0;
 }
 
+int ogs_raster_cached_bytes(const ogs_raster_inputs* in, int64_t num_rendered, int64_t* geom_bytes, int64_t* binning_bytes) {
+    if (!in || num_rendered < 0 || in->P < 0 || in->W <= 0 || in->H <= 0) { set_error("cached_bytes: bad arguments"); return -1; }
+    const int tiles = ((in->W + 15) / 16) * ((in->H + 15) / 16);
+    if (geom_bytes) *geom_bytes = (int64_t)GeomLayout::make(in->P, in->shs != nullptr, 0).total;
+    if (binning_bytes) *binning_bytes = (int64_t)BinLayout::make(num_rendered, tiles).total;
+    return 0;
+}
+
+int ogs_raster_forward_cached(const ogs_raster_inputs* in, const ogs_raster_outputs* out, ogs_alloc_fn alloc,
+                              void* alloc_user, const ogs_raster_state* cached, ogs_raster_state* st, void* stream_) {
+    int rc = validate_inputs(in);
+    if (rc) return rc;
+    if (!out || !out->color || !out->depth || !out->alpha || !alloc || !st || !cached) {
+        set_error("outputs/alloc/state must be set");
+        return -1;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int P = in->P, W = in->W, H = in->H, C = 3 + in->n_extra;
+    const int gx = (W + 15) / 16, gy = (H + 15) / 16, tiles = gx * gy;
+    const bool has_sh = in->shs != nullptr;
+    const int n_feat_act = (in->act_flags & OGS_ACT_EXTRA_UNIT_HALF) ? in->n_extra : 0;
+    // the activated channels sit last in the geometry layout: every other offset is the same with and without them
+    const GeomLayout gl = GeomLayout::make(P, has_sh, 0);
+    const ImgLayout il = ImgLayout::make(W, H);
+    if (!cached->geom || !cached->binning || cached->num_rendered < 0 || cached->geom_bytes < (int64_t)gl.total ||
+        cached->binning_bytes < (int64_t)BinLayout::make(cached->num_rendered, tiles).total) {
+        set_error("cached state does not belong to a finished forward of these sizes (P=%d, %d tiles, N=%lld)", P, tiles,
+                  (long long)cached->num_rendered);
+        return -1;
+    }
+    *st = *cached;
+    st->image = alloc(alloc_user, il.total, "image");
+    st->image_bytes = (int64_t)il.total;
+    st->feat = nullptr;
+    if (!st->image) { set_error("allocation callback returned NULL"); return -6; }
+    const GeomPtrs g = GeomPtrs::from(st->geom, gl);
+    const BinLayout bl = BinLayout::make(st->num_rendered, tiles);
+    if (n_feat_act && P > 0) {
+        st->feat = alloc(alloc_user, (size_t)P * n_feat_act * sizeof(float), "feat");
+        if (!st->feat) { set_error("allocation callback returned NULL"); return -6; }
+        prof_begin(PF_PREPROCESS_FWD, s);
+        rc = launch_feat_refresh(P, n_feat_act, g.rec1, in->extra, (float*)st->feat, s);
+        prof_end(PF_PREPROCESS_FWD, s);
+        if (rc) return rc;
+        OGS_KERNEL_CHECK("feat_refresh", in->debug, s);
+    }
+    if (out->radii && P > 0) {          // radius = rec1.w as int bits; culled Gaussians hold 0 there
+        cudaError_t e = cudaMemcpy2DAsync(out->radii, 4, &g.rec1[0].w, 16, 4, (size_t)P, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return cuda_fail(e, "radii copy");
+    }
+    BlendFwdArgs ba;
+    ba.W = W; ba.H = H; ba.C = C;
+    ba.ranges = (uint2*)((char*)st->binning + bl.ranges);
+    ba.point_list = (uint32_t*)((char*)st->binning + bl.point_list);
+    ba.rec0 = g.rec0; ba.rec1 = g.rec1;
+    ba.base = has_sh ? g.rgb : in->colors_precomp;
+    ba.extra = n_feat_act ? (const float*)st->feat : in->extra; ba.bg = in->bg;
+    ba.out_color = out->color; ba.out_depth = out->depth; ba.out_alpha = out->alpha;
+    ba.final_T = (float*)((char*)st->image + il.final_T);
+    ba.n_contrib = (uint32_t*)((char*)st->image + il.n_contrib);
+    prof_begin(PF_BLEND_FWD, s);
+    rc = launch_blend_forward(ba, s);
+    prof_end(PF_BLEND_FWD, s);
+    if (rc) return rc;
+    OGS_KERNEL_CHECK("blend_forward", in->debug, s);
+    return 0;
+}
+
 int64_t ogs_raster_capacity_hint(int64_t new_hint) {
     ForwardCtx& fc = forward_ctx();
     const int64_t old = (int64_t)fc.cap_hint;
@@ -414,7 +482,7 @@ int ogs_raster_backward(const ogs_raster_inputs* in, const ogs_raster_state* st,
     ba.point_list = (const uint32_t*)((char*)st->binning + bl.point_list);
     ba.rec0 = g.rec0; ba.rec1 = g.rec1;
     ba.base = has_sh ? g.rgb : in->colors_precomp;
-    ba.extra = n_feat_act ? g.feat : in->extra; ba.bg = in->bg;
+    ba.extra = n_feat_act ? (st->feat ? (const float*)st->feat : g.feat) : in->extra; ba.bg = in->bg;
     ba.final_T = (const float*)((char*)st->image + il.final_T);
     ba.n_contrib = (const uint32_t*)((char*)st->image + il.n_contrib);
     ba.dL_dcolor = gin->dL_dcolor; ba.dL_ddepth = gin->dL_ddepth; ba.dL_dalpha = gin->dL_dalpha; ba.dL_dfeat = gin->dL_dfeat;

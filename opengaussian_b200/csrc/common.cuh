@@ -133,6 +133,14 @@ struct ImgLayout {
     }
 };
 
+// Exact e / d for the staging loops (e < 2^16, d < 2^10): one multiply-high instead of the ~20-instruction runtime
+// division.  floor(e * ceil(2^32 / d) / 2^32) == floor(e / d) while e * d < 2^32.
+struct SmallDiv {
+    uint32_t inv;
+    __device__ __forceinline__ explicit SmallDiv(int d) : inv(0xFFFFFFFFu / (uint32_t)d + 1u) {}
+    __device__ __forceinline__ int operator()(int e) const { return (int)__umulhi((uint32_t)e, inv); }
+};
+
 // ---- kernels launchers (defined in the per-family .cu files) ----
 struct PreprocessArgs {
     int P, D, M, W, H;
@@ -147,6 +155,7 @@ struct PreprocessArgs {
     uint32_t* depth_vals;   // [P] identity
 };
 int launch_preprocess_forward(const PreprocessArgs& a, cudaStream_t s);
+int launch_feat_refresh(int P, int n_extra, const float4* rec1, const float* extra, float* feat, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 
 // binning (binning.cu)

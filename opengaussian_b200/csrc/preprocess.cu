@@ -44,6 +44,15 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
 
 #define PF 128   // Gaussians (= threads) per CTA
 
+// (normalize(ins_feat) + 1) / 2 -- scene/gaussian_model.py:161-169 + gaussian_renderer/__init__.py:127.  One function for
+// the preprocess kernel and the cached-view refresh, so that both produce the same bits (this file: --fmad=false).
+__device__ __forceinline__ void unit_half_row(const float* __restrict__ extra, float* __restrict__ feat, int i, int n_extra) {
+    float n2 = 0.f;
+    for (int c = 0; c < n_extra; c++) { const float v = extra[(size_t)i * n_extra + c]; n2 += v * v; }
+    const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+    for (int c = 0; c < n_extra; c++) feat[(size_t)i * n_extra + c] = (extra[(size_t)i * n_extra + c] / nrm + 1.0f) / 2.0f;
+}
+
 template <bool HAS_SH>
 __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
     extern __shared__ float s_sh[];  // [PF][M*3 + 1] when HAS_SH
@@ -168,6 +177,7 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
         __syncthreads();
         const int per = a.M * 3;
         if (a.shs_rest) {
+            const SmallDiv by_pr(per - 3);
             // split SH: row = [_features_dc (3) | _features_rest ((M-1)*3)], two contiguous slabs
             const int pr = per - 3;
             const size_t base_dc = (size_t)blockIdx.x * PF * 3, base_r = (size_t)blockIdx.x * PF * pr;
@@ -181,33 +191,34 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
             const int n4 = (PF * pr) / 4;
             for (int e = threadIdx.x; e < n4; e += PF) {
                 const int f = e * 4;
-                const int g0 = f / pr, g3 = (f + 3) / pr;
+                const int g0 = by_pr(f), g3 = by_pr(f + 3);
                 if ((s_vis[g0] || s_vis[g3 < PF ? g3 : g0]) && base_r + f + 3 < tot_r) {
                     const float4 q = __ldg(src + e);
                     const float v4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
-                        const int gi = (f + t) / pr, k = (f + t) - gi * pr;
+                        const int gi = by_pr(f + t), k = (f + t) - gi * pr;
                         if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = v4[t];
                     }
                 } else if (base_r + f < tot_r) {   // ragged end of the tensor
                     for (int t = 0; t < 4 && base_r + f + t < tot_r; t++) {
-                        const int gi = (f + t) / pr, k = (f + t) - gi * pr;
+                        const int gi = by_pr(f + t), k = (f + t) - gi * pr;
                         if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + f + t);
                     }
                 }
             }
             for (int e = n4 * 4 + threadIdx.x; e < PF * pr; e += PF) {
-                const int gi = e / pr, k = e - gi * pr;
+                const int gi = by_pr(e), k = e - gi * pr;
                 if (s_vis[gi] && base_r + e < tot_r) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + e);
             }
         } else {
         const size_t base = (size_t)blockIdx.x * PF * per;
+        const SmallDiv by_per(per);
         if ((per & 3) == 0) {
             const float4* src = reinterpret_cast<const float4*>(a.shs + base);
             for (int e = threadIdx.x; e < PF / 4 * per; e += PF) {
                 const int f = e * 4;
-                const int gi = f / per, k = f - gi * per;   // per % 4 == 0: the 4 floats share gi
+                const int gi = by_per(f), k = f - gi * per;   // per % 4 == 0: the 4 floats share gi
                 if (s_vis[gi]) {
                     const float4 q = __ldg(src + e);
                     float* d = s_sh + gi * (per + 1) + k;
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
             }
         } else {
             for (int e = threadIdx.x; e < PF * per; e += PF) {
-                const int gi = e / per, k = e - gi * per;
+                const int gi = by_per(e), k = e - gi * per;
                 if (s_vis[gi]) s_sh[gi * (per + 1) + k] = __ldg(a.shs + base + e);
             }
         }
@@ -257,14 +268,7 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
     }
     if (!active) return;
 
-    if (visible && (a.act_flags & OGS_ACT_EXTRA_UNIT_HALF)) {
-        // (normalize(ins_feat) + 1) / 2 -- scene/gaussian_model.py:161-169 + gaussian_renderer/__init__.py:127
-        float n2 = 0.f;
-        for (int c = 0; c < a.n_extra; c++) { const float v = a.extra[(size_t)i * a.n_extra + c]; n2 += v * v; }
-        const float nrm = fmaxf(sqrtf(n2), 1e-12f);
-        for (int c = 0; c < a.n_extra; c++)
-            a.g.feat[(size_t)i * a.n_extra + c] = (a.extra[(size_t)i * a.n_extra + c] / nrm + 1.0f) / 2.0f;
-    }
+    if (visible && (a.act_flags & OGS_ACT_EXTRA_UNIT_HALF)) unit_half_row(a.extra, a.g.feat, i, a.n_extra);
     a.radii[i] = radius_out;
     a.g.rec0[i] = r0;
     a.g.rec1[i] = r1;
@@ -294,6 +298,21 @@ int launch_preprocess_forward(const PreprocessArgs& a, cudaStream_t s) {
     } else {
         preprocess_fwd_kernel<false><<<blocks, PF, 0, s>>>(a);
     }
+    return 0;
+}
+
+// Cached-view forward (ogs_raster_forward_cached): the only per-Gaussian quantity that changes between two calls on a
+// frozen geometry.  Visible Gaussians only, like the preprocess kernel (rec1.w = radius as int bits).
+__global__ void __launch_bounds__(256) feat_refresh_kernel(int P, int n_extra, const float4* __restrict__ rec1,
+                                                           const float* __restrict__ extra, float* __restrict__ feat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (__float_as_int(__ldg(rec1 + i).w) > 0) unit_half_row(extra, feat, i, n_extra);
+}
+
+int launch_feat_refresh(int P, int n_extra, const float4* rec1, const float* extra, float* feat, cudaStream_t s) {
+    if (P <= 0 || n_extra <= 0) return 0;
+    feat_refresh_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, n_extra, rec1, extra, feat);
     return 0;
 }
 

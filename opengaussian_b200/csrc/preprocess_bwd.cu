@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
     bool vis = false;
     if (active) vis = __float_as_int(a.g.rec1[i].w) > 0;
     const int per = a.M * 3;
+    const SmallDiv by_per(per > 0 ? per : 1), by_pr(per > 3 ? per - 3 : 1);
     if (STAGE_SH) {
         s_vis[threadIdx.x] = vis;
         __syncthreads();
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
                 if (s_vis[gi]) s_sh[gi * (per + 1) + k] = __ldg(a.shs + base_dc + e);
             }
             for (int e = threadIdx.x; e < PB * pr; e += PB) {
-                const int gi = e / pr, k = e - gi * pr;
+                const int gi = by_pr(e), k = e - gi * pr;
                 if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + e);
             }
         } else {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
         const float4* src = reinterpret_cast<const float4*>(a.shs + base);
         for (int e = threadIdx.x; e < PB / 4 * per; e += PB) {     // PB * per / 4 float4 (per % 4 == 0)
             const int f = e * 4;
-            const int gi = f / per, k = f - gi * per;
+            const int gi = by_per(f), k = f - gi * per;
             if (s_vis[gi]) {
                 const float4 v = __ldg(src + e);
                 float* d = s_sh + gi * (per + 1) + k;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
             if (a.dL_dshs_rest) {
                 float* dst_r = a.dL_dshs_rest + (size_t)blockIdx.x * PB * pr;
                 for (int e = threadIdx.x; e < rows * pr; e += PB) {
-                    const int gi = e / pr, k = e - gi * pr;
+                    const int gi = by_pr(e), k = e - gi * pr;
                     if (!ac) dst_r[e] = s_sh[gi * (per + 1) + 3 + k];
                     else if (s_vis[gi]) atomicAdd(dst_r + e, s_sh[gi * (per + 1) + 3 + k]);
                 }
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(PB, PB_MINB) preprocess_bwd_kernel(PreprocessB
             float4* dst = reinterpret_cast<float4*>(a.dL_dshs + base);
             for (int e = threadIdx.x; e < rows * per / 4; e += PB) {
                 const int f = e * 4;
-                const int gi = f / per, k = f - gi * per;
+                const int gi = by_per(f), k = f - gi * per;
                 const float* d = s_sh + gi * (per + 1) + k;
                 if (!ac) dst[e] = make_float4(d[0], d[1], d[2], d[3]);
                 else if (s_vis[gi]) atomicAdd(dst + e, make_float4(d[0], d[1], d[2], d[3]));   // red.global.add.v4.f32

@@ -10,8 +10,11 @@ owns device memory and the stream.  Extension over upstream: ``extra_feats=[P,F]
 more per-Gaussian channels (OpenGaussian's ``ins_feat``) in the SAME pass and appends a fifth
 return value ``feats [F,H,W]`` -- this is what lets ``render()`` replace its 4 passes by one.
 """
+import collections
 import ctypes as C
 import itertools
+import os
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -82,6 +85,99 @@ class _Alloc:
 
 
 _ALLOC_THUNK = _lib.ALLOC_FN(_Alloc._cb)
+
+
+def _sig(t):
+    """Identity of a tensor's CONTENTS as far as torch can vouch for them: storage address, shape and the version
+    counter that every in-place operation bumps (detach() / views share it with their base)."""
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+
+
+class _ViewEntry:
+    __slots__ = ("geom_key", "state", "geom", "binning", "radii", "keep", "nbytes")
+
+
+class ViewCache:
+    """Per-camera reuse of everything the rasterizer derives from the GEOMETRY (projected records,
+    SH colours, radii, depth-sorted per-tile lists) while that geometry is frozen.
+
+    From Stage 1 on OpenGaussian detaches xyz / scaling / rotation / opacity / SH and trains `_ins_feat` only
+    (train.py:431-436), but the reference re-runs preprocess, duplication and the 64-bit sort on every render() of a
+    training camera for 40 000 iterations.  Here a forward whose geometry parameters do not require grad leaves its
+    geometry + binning buffers in this cache (exact-size copies: ~95 MB per view at 1 M Gaussians / 10 M duplicates;
+    the default budget is 35 % of the device's memory, i.e. hundreds of views on a 180 GB B200, LRU beyond that), and
+    the next forward of the same camera runs only the feature activation and the blend kernel
+    (C ABI ogs_raster_forward_cached) -- bit-identical images, the usual backward.
+
+    Validity is decided from what torch guarantees: an entry is keyed by the camera tensors and matched against the
+    geometry tensors' storage address, shape and VERSION COUNTER (bumped by every in-place op, shared by detach()
+    and views -- so the per-iteration `.detach()` of train.py:431-436 still hits, an optimizer step or a densification
+    misses).  The entry holds references to those tensors, so an address cannot be recycled while it is alive.
+    NOT seen: writes through `tensor.data` or raw pointers -- call `view_cache.clear()` after such edits, or set
+    `view_cache.enabled = False` (env OGS_VIEW_CACHE=0)."""
+
+    def __init__(self):
+        self.enabled = os.environ.get("OGS_VIEW_CACHE", "1") != "0"
+        gb = os.environ.get("OGS_VIEW_CACHE_GB")
+        self.max_bytes = None if gb is None else int(float(gb) * 2 ** 30)   # None: 35 % of the device, set on first use
+        self._entries = collections.OrderedDict()      # camera key -> _ViewEntry, least recently used first
+        self._lock = threading.Lock()
+        self.bytes = 0
+        self.hits = self.misses = self.evictions = 0
+
+    def clear(self):
+        with self._lock:
+            self._entries.clear()
+            self.bytes = 0
+
+    def __len__(self):
+        return len(self._entries)
+
+    def stats(self):
+        return dict(entries=len(self._entries), bytes=self.bytes, hits=self.hits, misses=self.misses,
+                    evictions=self.evictions, max_bytes=self.max_bytes)
+
+    @staticmethod
+    def keys(rs, means3D, opacities, sh, sh_rest, colors_precomp, scales, rotations, cov3D, act_flags, n_feat_act):
+        dev = means3D.device
+        cam = (dev.type, dev.index, _sig(rs.viewmatrix), _sig(rs.projmatrix), _sig(rs.campos), int(rs.image_height),
+               int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
+               int(rs.sh_degree) if sh is not None else -1)
+        geom = (_sig(means3D), _sig(opacities), _sig(sh), _sig(sh_rest), colors_precomp is not None, _sig(scales),
+                _sig(rotations), _sig(cov3D), int(act_flags) & ~_lib.ACT_EXTRA_UNIT_HALF, bool(n_feat_act))
+        return cam, geom
+
+    def lookup(self, cam_key, geom_key):
+        with self._lock:
+            e = self._entries.get(cam_key)
+            if e is not None and e.geom_key == geom_key:
+                self._entries.move_to_end(cam_key)
+                self.hits += 1
+                return e
+            self.misses += 1
+            return None
+
+    def insert(self, cam_key, entry: _ViewEntry, device=None):
+        with self._lock:
+            if self.max_bytes is None:
+                total = torch.cuda.get_device_properties(device).total_memory if device is not None else 0
+                self.max_bytes = int(0.35 * total)
+            old = self._entries.pop(cam_key, None)          # same camera, other geometry: superseded
+            if old is not None:
+                self.bytes -= old.nbytes
+            if entry.nbytes > self.max_bytes:
+                return False
+            while self._entries and self.bytes + entry.nbytes > self.max_bytes:
+                _, ev = self._entries.popitem(last=False)
+                self.bytes -= ev.nbytes
+                self.evictions += 1
+            self._entries[cam_key] = entry
+            self.bytes += entry.nbytes
+            return True
+
+
+view_cache = ViewCache()
+_CAPTURE_PINS = {}    # device index -> list that receives the cache buffers a CUDA-graph capture reads (graphs.GraphedViewStep)
 
 
 def _fill_inputs(rs: GaussianRasterizationSettings, bg_full, means3D, opacities, shs, colors_precomp, scales,
@@ -253,13 +349,55 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         ri = _fill_inputs(rs, bg_full, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
                           extra, n_extra, sh_rest, act_flags)
-        ro = _lib.RasterOutputs(_lib.ptr(color_all), _lib.ptr(depth), _lib.ptr(alpha), _lib.ptr(radii))
         st = _lib.RasterState()
         alloc = _Alloc(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
-            rc = L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, alloc.user, C.byref(st), C.c_void_p(stream))
-        _lib.check(rc, "ogs_raster_forward")
+        # Frozen geometry (OpenGaussian stages 1-3, train.py:431-436): reuse the camera's records and tile lists
+        frozen = view_cache.enabled and P > 0 and not rs.debug and not any(
+            t is not None and t.requires_grad for t in (means3D, sh, opacities, scales, rotations, cov3Ds_precomp, sh_rest))
+        entry = cam_key = geom_key = None
+        if frozen:
+            n_feat_act = n_extra if (act_flags & _lib.ACT_EXTRA_UNIT_HALF) else 0
+            cam_key, geom_key = ViewCache.keys(rs, means3D, opacities, sh, sh_rest, colors_precomp, scales, rotations,
+                                               cov3Ds_precomp, act_flags, n_feat_act)
+            entry = view_cache.lookup(cam_key, geom_key)
+        if entry is None and torch.cuda.is_current_stream_capturing():
+            raise _lib.OgsError("GaussianRasterizer under CUDA-graph capture needs the view's geometry resident in "
+                                "rasterizer.view_cache (frozen geometry, one eager visit first): a fresh forward reads "
+                                "the frame's duplicate count back to the host")
+        if entry is not None:
+            pins = _CAPTURE_PINS.get(dev.index)
+            if pins is not None:             # an evicted entry must not free memory a captured graph still reads
+                pins.append((entry.geom, entry.binning, entry.radii))
+            radii = entry.radii.detach()     # a fresh tensor object over the first call's radii (this Function's own output)
+            ro = _lib.RasterOutputs(_lib.ptr(color_all), _lib.ptr(depth), _lib.ptr(alpha), None)
+            with torch.cuda.device(dev):
+                rc = L.ogs_raster_forward_cached(C.byref(ri), C.byref(ro), alloc.fn, alloc.user, C.byref(entry.state),
+                                                 C.byref(st), C.c_void_p(stream))
+            _lib.check(rc, "ogs_raster_forward_cached")
+            alloc.bufs["geom"], alloc.bufs["binning"] = entry.geom, entry.binning
+        else:
+            if frozen:
+                ri.defer_capacity_check = 0      # the entry needs this frame's duplicate count now
+            ro = _lib.RasterOutputs(_lib.ptr(color_all), _lib.ptr(depth), _lib.ptr(alpha), _lib.ptr(radii))
+            with torch.cuda.device(dev):
+                rc = L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, alloc.user, C.byref(st), C.c_void_p(stream))
+            _lib.check(rc, "ogs_raster_forward")
+            if frozen and int(st.num_rendered) >= 0:
+                gb, bb = C.c_int64(0), C.c_int64(0)
+                _lib.check(L.ogs_raster_cached_bytes(C.byref(ri), st.num_rendered, C.byref(gb), C.byref(bb)),
+                           "ogs_raster_cached_bytes")
+                e = _ViewEntry()
+                e.geom_key = geom_key
+                e.geom = alloc.bufs["geom"][:gb.value].clone()          # exact-size copies: the forward's own buffers
+                e.binning = alloc.bufs["binning"][:bb.value].clone()    # carry the capacity estimate's head room
+                e.radii = radii
+                e.state = _lib.RasterState(e.geom.data_ptr(), e.binning.data_ptr(), None, st.num_rendered, gb.value,
+                                           bb.value, 0, None)
+                e.keep = (rs.viewmatrix, rs.projmatrix, rs.campos, means3D, opacities, sh, sh_rest, scales, rotations,
+                          cov3Ds_precomp)
+                e.nbytes = gb.value + bb.value + radii.numel() * 4
+                view_cache.insert(cam_key, e, dev)
 
         ctx.rs = rs
         ctx.bg_full = bg_full

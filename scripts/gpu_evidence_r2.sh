@@ -2,6 +2,7 @@
 # Round-2 evidence on ONE GPU (under gpurun), in two parts so that each stays under gpurun's 64 MiB return limit:
 #   part a: parity tests, the bench line, the ncu launch list of the same bench command, comparator, Stage-1 demo
 #   part b: `ncu --set full` captures (one whole frame of the rasterizer; the two k-means Lloyd kernels)
+#   part c: `ncu --set full` over one Stage-1 training step (BASELINE config 3)
 # Everything lands in gpurun_out/; scripts/summarize_profiles.py turns it into profiles/.
 set -u
 TAG=${1:-r2}
@@ -16,6 +17,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
 python scripts/upstream_structure_bench.py > gpurun_out/${TAG}_upstream_structure.json 2> gpurun_out/${TAG}_upstream_structure.err; echo "comparator rc=$?"
 python scripts/stage1_train_demo.py --lr 0.01 --iters 300 > gpurun_out/${TAG}_stage1_demo.json 2> gpurun_out/${TAG}_stage1_demo.err; echo "stage1 demo rc=$?"
 python scripts/kmeans_seg_probe.py > gpurun_out/${TAG}_kmeans_probe.txt 2>&1; echo "kmeans probe rc=$?"
+elif [ "$PART" = "c" ]; then
+python scripts/stage1_steps.py --iters 40 > gpurun_out/${TAG}_stage1_steps.txt; echo "stage1 steps rc=$?"; cat gpurun_out/${TAG}_stage1_steps.txt
+# a step launches 27 kernels of the library: skip 3 steps, capture a window that holds one whole step
+ncu --set full --clock-control none -k regex:"blend|preprocess|rs_|emit_kernel|scan_gather|ranges_kernel|set_scalar|mask_|cohesion|sam_ids|separation" -s 81 -c 30 \
+    -o gpurun_out/${TAG}_stage1 python scripts/stage1_steps.py --iters 6 > gpurun_out/${TAG}_ncu_stage1.log 2>&1; echo "ncu stage1 rc=$?"
+ls -la gpurun_out/
 else
 # quick_bench launches 18 ogs:: kernels per frame; skip 4 frames, capture ONE whole frame
 python scripts/quick_bench.py --iters 3 --prof 0 > /dev/null 2>&1 && \

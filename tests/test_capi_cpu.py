@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_sass_target(lib):
-    assert lib.ogs_abi_version() == 5
+    assert lib.ogs_abi_version() == 6
     import subprocess
     from opengaussian_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
