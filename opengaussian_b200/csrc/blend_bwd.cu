@@ -88,12 +88,20 @@ int blend_bwd_stride(int C, int geom) { return geom ? C + 7 : C; }
 // registers without spills, which lets 12 CTAs of 64 threads share an SM instead of 10.  Measured on B200 (ncu,
 // profiles/r2_kernels_full.csv): warps active 28 -> 33 %, issue active 67 -> 70 %, but 7 % more instructions
 // (rematerialisation), so the net is small: 0.517 ms capped vs 0.531 ms uncapped in the same bench run.
-constexpr int bwd_min_blocks(int C, int pairs) { return (pairs == 2 && C <= 4) ? 12 : 1; }
+constexpr int bwd_min_blocks(int C, int pairs, bool geom = true) { return (pairs == 2 && (C <= 4 || (!geom && C <= 6))) ? 12 : 1; }
 
-template <int C, bool GEOM, int PAIRS>
-__global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_bwd_kernel(BlendBwdArgs a) {
+// C0 > 0 (colour-only backward, GEOM = false): channels [0, C0) carry no incoming gradient -- OpenGaussian's Stage 1
+// back-propagates through the 6 feature channels only (train.py:441-456), the RGB planes of the fused pass have no
+// loss -- so their pixel gradients are not loaded, their weighted sums not formed and not reduced across the lanes
+// (6 of 9 values: a third of the FFMA2s and of the reduction of every evaluated entry).  The accumulator rows keep
+// their C columns (preprocess_bwd reads them by column); columns [0, C0) stay zero.
+template <int C, bool GEOM, int PAIRS, int C0 = 0>
+__global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C - C0, PAIRS, GEOM || C0 == 0)) blend_bwd_kernel(BlendBwdArgs a) {
+    static_assert(C0 == 0 || !GEOM, "the geometry gradients need every channel");
     constexpr int BWD_THREADS = 128 / PAIRS, BWD_WARPS = 4 / PAIRS, NPX = 2 * PAIRS;
     constexpr int V = GEOM ? C + 7 : C;
+    constexpr int CG = C - C0;            // channels with an incoming gradient
+    constexpr int VG = GEOM ? V : CG;     // values reduced per evaluated entry
     constexpr int CH = (C + 1 + 3) & ~3;  // colours + depth, padded to float4
     // everything is double-buffered by batch parity: batch b-1 is staged while batch b is traversed,
     // and batch b is flushed (after the ONE barrier per batch) while the fast warps start on b-1
@@ -116,12 +124,12 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
 
     // per-lane state of the pixel pairs (.x: row y + 8 p, .y: row y + 8 p + 4)
     float2 T2[PAIRS], S2[PAIRS], gd2[PAIRS], ga2[PAIRS], tfbg2[PAIRS], npy[PAIRS];
-    float2 g2[PAIRS][C];
+    float2 g2[PAIRS][CG];
     int last[NPX];
 #pragma unroll
     for (int p = 0; p < PAIRS; p++) {
         float Tf[2], gdv[2] = {0.f, 0.f}, gav[2] = {0.f, 0.f}, bgd[2] = {0.f, 0.f};
-        float gv[2][C];
+        float gv[2][CG];
         const int y0 = byi + (lane >> 3) + 8 * p;
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -131,13 +139,14 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
             last[2 * p + k] = inside ? (int)a.n_contrib[pix] : 0;
             Tf[k] = inside ? a.final_T[pix] : 0.f;
 #pragma unroll
-            for (int c = 0; c < C; c++) {
+            for (int cc = 0; cc < CG; cc++) {
+                const int c = C0 + cc;
                 const float* plane = (a.dL_dfeat && c >= 3) ? a.dL_dfeat + (size_t)(c - 3) * HW
                                                             : (a.dL_dcolor ? a.dL_dcolor + (size_t)c * HW : nullptr);
-                gv[k][c] = (inside && plane) ? __ldg(plane + pix) : 0.f;
-                if (GEOM) bgd[k] = fmaf(__ldg(a.bg + c), gv[k][c], bgd[k]);
+                gv[k][cc] = (inside && plane) ? __ldg(plane + pix) : 0.f;
+                if constexpr (GEOM) bgd[k] = fmaf(__ldg(a.bg + c), gv[k][cc], bgd[k]);
             }
-            if (GEOM) {
+            if constexpr (GEOM) {
                 gdv[k] = (inside && a.dL_ddepth) ? __ldg(a.dL_ddepth + pix) : 0.f;
                 gav[k] = (inside && a.dL_dalpha) ? __ldg(a.dL_dalpha + pix) : 0.f;
             }
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
         T2[p] = make_float2(Tf[0], Tf[1]);
         S2[p] = s2(0.f);
 #pragma unroll
-        for (int c = 0; c < C; c++) g2[p][c] = make_float2(gv[0][c], gv[1][c]);
+        for (int c = 0; c < CG; c++) g2[p][c] = make_float2(gv[0][c], gv[1][c]);
         gd2[p] = make_float2(gdv[0], gdv[1]);
         ga2[p] = make_float2(gav[0], gav[1]);
         tfbg2[p] = make_float2(Tf[0] * bgd[0], Tf[1] * bgd[1]);
@@ -174,12 +183,14 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
             s_id3[b % 3][t] = gid;
             const float4 r1 = __ldg(a.rec1 + gid);
             ogs_stage(__ldg(a.rec0 + gid), r1, s_a2[sb][t], s_b2[sb][t]);
-            s_ch2[sb][t * CH + C] = r1.z;
+            if constexpr (GEOM) s_ch2[sb][t * CH + C] = r1.z;
         }
-        for (int e = threadIdx.x; e < n * C; e += BWD_THREADS) {
-            const int j = e / C, c = e - j * C;
-            const uint32_t gid = a.point_list[range.x + start + j];
-            s_ch2[sb][j * CH + c] = (c < 3) ? __ldg(a.base + 3 * (size_t)gid + c) : __ldg(a.extra + (size_t)(C - 3) * gid + (c - 3));
+        if constexpr (GEOM) {          // the channel values enter dL/dalpha only; the colour-only backward never reads them
+            for (int e = threadIdx.x; e < n * C; e += BWD_THREADS) {
+                const int j = e / C, c = e - j * C;
+                const uint32_t gid = a.point_list[range.x + start + j];
+                s_ch2[sb][j * CH + c] = (c < 3) ? __ldg(a.base + 3 * (size_t)gid + c) : __ldg(a.extra + (size_t)(C - 3) * gid + (c - 3));
+            }
         }
     };
     const int b_first = (max_last - 1) / BB;
@@ -229,15 +240,17 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
                     }
                     if (!__any_sync(0xffffffffu, any)) continue;
                     float chv[CH];
+                    if constexpr (GEOM) {
 #pragma unroll
-                    for (int q = 0; q < CH / 4; q++) {
-                        const float4 t = reinterpret_cast<const float4*>(s_ch + j * CH)[q];
-                        chv[4 * q] = t.x; chv[4 * q + 1] = t.y; chv[4 * q + 2] = t.z; chv[4 * q + 3] = t.w;
+                        for (int q = 0; q < CH / 4; q++) {
+                            const float4 t = reinterpret_cast<const float4*>(s_ch + j * CH)[q];
+                            chv[4 * q] = t.x; chv[4 * q + 1] = t.y; chv[4 * q + 2] = t.z; chv[4 * q + 3] = t.w;
+                        }
                     }
                     // packed sums over the lane's pairs; .x + .y is taken once at the end
-                    float2 vc[C], vd = s2(0.f), su2 = s2(0.f), suy2 = s2(0.f), suyy2 = s2(0.f);
+                    float2 vc[CG], vd = s2(0.f), su2 = s2(0.f), suy2 = s2(0.f), suyy2 = s2(0.f);
 #pragma unroll
-                    for (int c = 0; c < C; c++) vc[c] = s2(0.f);
+                    for (int c = 0; c < CG; c++) vc[c] = s2(0.f);
 #pragma unroll
                     for (int p = 0; p < PAIRS; p++) {
                         const float2 alm = make_float2(ok[2 * p] ? al[p].x : 0.f, ok[2 * p + 1] ? al[p].y : 0.f);
@@ -246,8 +259,8 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
                         T2[p] = __fmul2_rn(T2[p], inv);
                         const float2 w = __fmul2_rn(alm, T2[p]);
 #pragma unroll
-                        for (int c = 0; c < C; c++) vc[c] = __ffma2_rn(w, g2[p][c], vc[c]);
-                        if (GEOM) {
+                        for (int c = 0; c < CG; c++) vc[c] = __ffma2_rn(w, g2[p][c], vc[c]);
+                        if constexpr (GEOM) {
                             float2 dot = __ffma2_rn(s2(chv[0]), g2[p][0], ga2[p]);
 #pragma unroll
                             for (int c = 1; c < C; c++) dot = __ffma2_rn(s2(chv[c]), g2[p][c], dot);
@@ -266,10 +279,10 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
                             vd = __ffma2_rn(w, gd2[p], vd);
                         }
                     }
-                    float v[V];
+                    float v[VG];
 #pragma unroll
-                    for (int c = 0; c < C; c++) v[c] = vc[c].x + vc[c].y;
-                    if (GEOM) {
+                    for (int c = 0; c < CG; c++) v[c] = vc[c].x + vc[c].y;
+                    if constexpr (GEOM) {
                         const float su = su2.x + su2.y, suy = suy2.x + suy2.y;
                         const float sux = su * dx;
                         v[C + 0] = vd.x + vd.y;
@@ -280,28 +293,27 @@ __global__ void __launch_bounds__(128 / PAIRS, bwd_min_blocks(C, PAIRS)) blend_b
                         v[C + 5] = suy * dx;
                         v[C + 6] = suyy2.x + suyy2.y;
                     }
-                    ChunkReduceStore<V, 0>::run(v, lane, my_acc + j * V);
+                    ChunkReduceStore<VG, 0>::run(v, lane, my_acc + j * V + C0);
                 }
             }
         }
         __syncthreads();   // batch b fully traversed by every warp; batch b-1 fully staged
         // ---- flush: sum the warp rows, one red per value per (tile, Gaussian) ----
-        for (int e = threadIdx.x; e < n * V; e += BWD_THREADS) {
+        for (int e0 = threadIdx.x; e0 < n * VG; e0 += BWD_THREADS) {
+            const int j = e0 / VG, k = C0 + (e0 - j * VG);
+            const int e = j * V + k;
             float sum = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < BWD_WARPS; w8++) {
                 sum += acc_b[(size_t)w8 * BB * V + e];
                 acc_b[(size_t)w8 * BB * V + e] = 0.f;
             }
-            if (sum != 0.f) {
-                const int j = e / V, k = e - j * V;
-                atomicAdd(a.acc + (size_t)s_id3[b % 3][j] * a.stride + k, sum);
-            }
+            if (sum != 0.f) atomicAdd(a.acc + (size_t)s_id3[b % 3][j] * a.stride + k, sum);
         }
     }
 }
 
-template <int C, bool GEOM>
+template <int C, bool GEOM, int C0 = 0>
 static int launch_cg(const BlendBwdArgs& a, cudaStream_t s) {
     constexpr int V = GEOM ? C + 7 : C;
     // two pairs per lane pay off while the pixel state fits the register file comfortably (measured: C <= 9)
@@ -311,18 +323,22 @@ static int launch_cg(const BlendBwdArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)2 * (4 / (pairs == 2 ? 2 : 1)) * BB * V * sizeof(float);
     static PerDeviceOnce attr_done[2];
     if (smem > 24 * 1024 && attr_done[pairs == 2].todo()) {   // static + dynamic shared memory may pass the 48 KB default
-        if (pairs == 2) OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        else OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        if (pairs == 2) OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 2, C0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        else OGS_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<C, GEOM, 1, C0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_done[pairs == 2].done();
     }
-    if (pairs == 2) blend_bwd_kernel<C, GEOM, 2><<<grid, 64, smem, s>>>(a);
-    else blend_bwd_kernel<C, GEOM, 1><<<grid, 128, smem, s>>>(a);
+    if (pairs == 2) blend_bwd_kernel<C, GEOM, 2, C0><<<grid, 64, smem, s>>>(a);
+    else blend_bwd_kernel<C, GEOM, 1, C0><<<grid, 128, smem, s>>>(a);
     return 0;
 }
 
 template <int C>
 static int launch_c(const BlendBwdArgs& a, cudaStream_t s) {
-    return a.geom ? launch_cg<C, true>(a, s) : launch_cg<C, false>(a, s);
+    if (a.geom) return launch_cg<C, true>(a, s);
+    if constexpr (C > 3) {
+        if (!a.dL_dcolor && a.dL_dfeat) return launch_cg<C, false, 3>(a, s);   // only the feature channels carry a gradient
+    }
+    return launch_cg<C, false>(a, s);
 }
 
 int launch_blend_backward(const BlendBwdArgs& a, cudaStream_t s) {

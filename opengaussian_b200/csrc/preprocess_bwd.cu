@@ -415,8 +415,93 @@ __device__ __forceinline__ void preprocess_bwd_body(const PreprocessBwdArgs& a, 
     }
 }
 
+// Colour-only backward of the raw-parameter feature channels (OpenGaussian stages 1-2: only `_ins_feat` trains,
+// train.py:431-436): dL/dx of f = (x / n + 1) / 2, n = max(|x|, 1e-12), from the blend sums in columns [3, 3 + F) of the
+// accumulator rows.  The generic kernel above walks its rows with 4-byte strided accesses under a 64-register cap
+// (46 us at 1 M Gaussians); here a CTA moves its 256 rows of `extra` and of the accumulator through shared memory with
+// 16-byte coalesced loads and stores (rows of culled Gaussians hold zeros after the memset, so no visibility lookup).
+// Same expressions, in the same order, as preprocess_bwd_body.
+#define FG_ROWS 256
+template <int F>
+__global__ void __launch_bounds__(FG_ROWS) feat_grad_kernel(int P, int stride, const float* __restrict__ extra,
+                                                            const float* __restrict__ acc, float* __restrict__ dL_dextra,
+                                                            int accumulate) {
+    constexpr int XS = F | 1;                       // odd row strides: conflict-free column walks
+    extern __shared__ float s_fg[];
+    float* s_x = s_fg;                              // [FG_ROWS][XS]
+    float* s_a = s_fg + FG_ROWS * XS;               // [FG_ROWS][stride | 1]
+    const int AS = stride | 1;
+    const int row0 = blockIdx.x * FG_ROWS;
+    const int rows = min(FG_ROWS, P - row0);
+    {
+        const float4* src = reinterpret_cast<const float4*>(extra + (size_t)row0 * F);
+        const int n = rows * F, n4 = n / 4;
+        for (int e = threadIdx.x; e < n4; e += FG_ROWS) {
+            const float4 v = __ldg(src + e);
+            const float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int f = 4 * e + k, r = f / F; s_x[r * XS + (f - r * F)] = t[k]; }
+        }
+        for (int f = 4 * n4 + threadIdx.x; f < n; f += FG_ROWS) { const int r = f / F; s_x[r * XS + (f - r * F)] = __ldg(extra + (size_t)row0 * F + f); }
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(acc + (size_t)row0 * stride);
+        const int n = rows * stride, n4 = n / 4;
+        for (int e = threadIdx.x; e < n4; e += FG_ROWS) {
+            const float4 v = __ldg(src + e);
+            const float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int f = 4 * e + k, r = f / stride; s_a[r * AS + (f - r * stride)] = t[k]; }
+        }
+        for (int f = 4 * n4 + threadIdx.x; f < n; f += FG_ROWS) { const int r = f / stride; s_a[r * AS + (f - r * stride)] = __ldg(acc + (size_t)row0 * stride + f); }
+    }
+    __syncthreads();
+    if (threadIdx.x < rows) {
+        float* x = s_x + threadIdx.x * XS;
+        const float* g = s_a + threadIdx.x * AS + 3;
+        float n2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < F; c++) n2 += x[c] * x[c];
+        const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+        float dotug = 0.f;
+#pragma unroll
+        for (int c = 0; c < F; c++) dotug += (x[c] / nrm) * g[c];
+#pragma unroll
+        for (int c = 0; c < F; c++) x[c] = (g[c] - (x[c] / nrm) * dotug) / (2.0f * nrm);
+    }
+    __syncthreads();
+    {
+        float* dst = dL_dextra + (size_t)row0 * F;
+        const int n = rows * F, n4 = n / 4;
+        for (int e = threadIdx.x; e < n4; e += FG_ROWS) {
+            float t[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int f = 4 * e + k, r = f / F; t[k] = s_x[r * XS + (f - r * F)]; }
+            float4* d4 = reinterpret_cast<float4*>(dst) + e;
+            if (accumulate) { const float4 o = *d4; t[0] += o.x; t[1] += o.y; t[2] += o.z; t[3] += o.w; }
+            *d4 = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        for (int f = 4 * n4 + threadIdx.x; f < n; f += FG_ROWS) {
+            const int r = f / F;
+            const float v = s_x[r * XS + (f - r * F)];
+            dst[f] = accumulate ? dst[f] + v : v;
+        }
+    }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 int launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t s) {
     if (a.P <= 0) return 0;
+    const int F = a.C - 3;
+    if (!a.geom && a.dL_dextra && !a.dL_dcolors_precomp && (a.act_flags & OGS_ACT_EXTRA_UNIT_HALF) && (F == 6 || F == 3) &&
+        aligned16(a.extra) && aligned16(a.acc) && aligned16(a.dL_dextra)) {
+        const size_t smem = (size_t)FG_ROWS * ((F | 1) + (a.stride | 1)) * sizeof(float);
+        const int grid = (a.P + FG_ROWS - 1) / FG_ROWS;
+        if (F == 6) feat_grad_kernel<6><<<grid, FG_ROWS, smem, s>>>(a.P, a.stride, a.extra, a.acc, a.dL_dextra, a.accumulate & 1);
+        else feat_grad_kernel<3><<<grid, FG_ROWS, smem, s>>>(a.P, a.stride, a.extra, a.acc, a.dL_dextra, a.accumulate & 1);
+        return 0;
+    }
     const int per = a.M * 3;
     const size_t smem = (size_t)PB * (per + 1) * sizeof(float);
     if (a.shs_rest && !(a.geom && smem <= 100 * 1024)) {

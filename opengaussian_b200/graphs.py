@@ -21,6 +21,7 @@ Anything that cannot be captured -- a view whose geometry is not resident (cache
 geometry (the forward then has to read the frame's duplicate count back) -- runs eagerly, every time, with the same
 results."""
 import collections
+import warnings
 from typing import Callable, Hashable, Iterable, Optional
 
 import torch
@@ -89,10 +90,12 @@ class GraphedViewStep:
         prev = _rz._CAPTURE_PINS.get(dev.index)
         _rz._CAPTURE_PINS[dev.index] = g.pins             # the rasterizer records the cache buffers the capture reads
         try:
-            with torch.cuda.graph(g.graph, pool=self._pool):
-                loss = self.view_loss(view)
-                loss.backward()
-                g.loss = loss.detach()
+            with warnings.catch_warnings():
+                warnings.filterwarnings("ignore", message="The CUDA Graph is empty")   # a refused capture ends empty
+                with torch.cuda.graph(g.graph, pool=self._pool):
+                    loss = self.view_loss(view)
+                    loss.backward()
+                    g.loss = loss.detach()
         finally:
             if prev is None:
                 _rz._CAPTURE_PINS.pop(dev.index, None)

@@ -93,6 +93,14 @@ def _sig(t):
     return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
 
 
+def pin_for_capture(device, *tensors):
+    """While graphs.GraphedViewStep captures on `device`, remembers `tensors` (library-internal cached buffers the
+    captured kernels read) for as long as the graph lives; a no-op otherwise."""
+    pins = _CAPTURE_PINS.get(device.index)
+    if pins is not None:
+        pins.append(tensors)
+
+
 class _ViewEntry:
     __slots__ = ("geom_key", "state", "geom", "binning", "radii", "keep", "nbytes")
 
@@ -177,6 +185,7 @@ class ViewCache:
 
 
 view_cache = ViewCache()
+_BG_FULL = {}         # device index -> (signature, [bg | extra_bg | 0] tensor, bg, extra_bg) of the last forward with extra channels
 _CAPTURE_PINS = {}    # device index -> list that receives the cache buffers a CUDA-graph capture reads (graphs.GraphedViewStep)
 
 
@@ -335,11 +344,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         bg = _f32c(rs.bg).reshape(-1)
         if n_extra == 0:
             bg_full = bg
-        elif extra_bg is None:
-            bg_full = torch.cat([bg, bg.new_zeros(n_extra)])
         else:
-            eb = _f32c(extra_bg).reshape(-1).to(dev)
-            bg_full = torch.cat([bg, eb, bg.new_zeros(n_extra - eb.numel())])
+            # [bg | extra_bg | 0...]: rebuilt only when one of the two tensors changes (storage, version counter)
+            sig = (_sig(bg), _sig(extra_bg), n_extra)
+            hit = _BG_FULL.get(dev.index)
+            if hit is None or hit[0] != sig:
+                if extra_bg is None:
+                    full = torch.cat([bg, bg.new_zeros(n_extra)])
+                else:
+                    eb = _f32c(extra_bg).reshape(-1).to(dev)
+                    full = torch.cat([bg, eb, bg.new_zeros(n_extra - eb.numel())])
+                hit = (sig, full, bg, extra_bg)            # the sources stay alive, so their addresses stay theirs
+                _BG_FULL[dev.index] = hit
+            bg_full = hit[1]
+            pin_for_capture(dev, bg_full)
         rs = rs._replace(viewmatrix=_f32c(rs.viewmatrix), projmatrix=_f32c(rs.projmatrix), campos=_f32c(rs.campos))
 
         color_all = torch.empty(3 + n_extra, H, W, dtype=torch.float32, device=dev)
@@ -366,9 +384,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                                 "rasterizer.view_cache (frozen geometry, one eager visit first): a fresh forward reads "
                                 "the frame's duplicate count back to the host")
         if entry is not None:
-            pins = _CAPTURE_PINS.get(dev.index)
-            if pins is not None:             # an evicted entry must not free memory a captured graph still reads
-                pins.append((entry.geom, entry.binning, entry.radii))
+            pin_for_capture(dev, entry.geom, entry.binning, entry.radii)   # an evicted entry must not free what a graph reads
             radii = entry.radii.detach()     # a fresh tensor object over the first call's radii (this Function's own output)
             ro = _lib.RasterOutputs(_lib.ptr(color_all), _lib.ptr(depth), _lib.ptr(alpha), None)
             with torch.cuda.device(dev):
@@ -399,6 +415,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 e.nbytes = gb.value + bb.value + radii.numel() * 4
                 view_cache.insert(cam_key, e, dev)
 
+        # outputs a loss does not touch hand the backward None instead of a zero-filled image (Stage 1 has no colour
+        # or depth loss: the kernel then runs its feature-channel-only form, C ABI dL_dcolor = NULL)
+        ctx.set_materialize_grads(False)
         ctx.rs = rs
         ctx.bg_full = bg_full
         ctx.state = st

@@ -22,7 +22,7 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, pin_for_capture
 
 
 def _knn_mean_dists(x: torch.Tensor, K: int, chunk: int = 4096) -> torch.Tensor:
@@ -33,6 +33,37 @@ def _knn_mean_dists(x: torch.Tensor, K: int, chunk: int = 4096) -> torch.Tensor:
         d = torch.cdist(x[i:i + chunk], x) ** 2
         out.append(torch.topk(d, K, dim=1, largest=False).values)
     return torch.cat(out, 0)
+
+
+_ZERO_SINKS = {}     # (P, device) -> (zeros [P,3], zeros [P,3]): the frozen-geometry stand-in for the screen-space gradient sink
+_TILED_BG = {}       # device -> (signature of bg3, nb, tiled background, bg3)
+
+
+def _zero_sink(xyz):
+    """A zero `viewspace_points` tensor whose .grad is zeros, shared by every frozen-geometry render() of this model size
+    (two 12 MB fills per call at 1 M Gaussians otherwise).  Nothing writes to it: the densification statistics that read
+    it (train.py:598) only run while the positions train, and then render() builds a real gradient sink."""
+    key = (xyz.shape[0], xyz.device, xyz.dtype)
+    hit = _ZERO_SINKS.get(key)
+    if hit is None:
+        _ZERO_SINKS.clear()                      # one model size at a time
+        hit = (torch.zeros_like(xyz), torch.zeros_like(xyz))
+        hit[0].grad = hit[1]
+        _ZERO_SINKS[key] = hit
+    pin_for_capture(xyz.device, *hit)
+    return hit[0]
+
+
+def _tiled_bg(bg3, nb):
+    """bg_color repeated over the feature channels (the reference reuses one rasterizer, hence one background, for all
+    its 3-channel passes); cached per device on the background tensor's storage and version counter."""
+    sig = (bg3.data_ptr(), bg3._version, nb)
+    hit = _TILED_BG.get(bg3.device)
+    if hit is None or hit[0] != sig:
+        hit = (sig, torch.cat([bg3] * ((nb + 2) // 3))[:nb].contiguous(), bg3)     # keeps bg3 alive: the address stays its own
+        _TILED_BG[bg3.device] = hit
+    pin_for_capture(bg3.device, hit[1])
+    return hit[1]
 
 
 def _feat_pass(rasterizer, bg3, means3D, means2D, opacity, scales, rotations, cov3D_precomp, feat, shs=None,
@@ -98,8 +129,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
         except Exception:
             pass
     else:
-        screenspace_points = torch.zeros_like(xyz)
-        screenspace_points.grad = torch.zeros_like(xyz)
+        screenspace_points = _zero_sink(xyz)
 
     tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
     tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
@@ -166,7 +196,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
         q = getattr(pc, "_ins_feat_q", None)
         raw_feat = pc._ins_feat if (origin_feat or q is None or len(q) == 0) else q
         nb = raw_feat.shape[-1]
-        ebg = torch.cat([bg3] * ((nb + 2) // 3))[:nb]
+        ebg = _tiled_bg(bg3, nb)
         rendered_image, radii, rendered_depth, rendered_alpha, rendered_ins_feat = rasterizer.forward_raw(
             means3D, means2D, pc._opacity, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation,
             raw_ins_feat=raw_feat, extra_bg=ebg)
@@ -175,7 +205,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
         # ONE launch: RGB + feature channels + depth + alpha; silhouette == alpha (same geometry)
         ins_feat = (pc.get_ins_feat(origin=origin_feat) + 1) / 2
         nb = ins_feat.shape[-1]
-        ebg = torch.cat([bg3] * ((nb + 2) // 3))[:nb]
+        ebg = _tiled_bg(bg3, nb)
         rendered_image, radii, rendered_depth, rendered_alpha, rendered_ins_feat = rasterizer(
             means3D=means3D, means2D=means2D, shs=shs, colors_precomp=colors_precomp, opacities=opacity,
             scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp, extra_feats=ins_feat, extra_bg=ebg)
@@ -312,5 +342,5 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
             "occured_leaf_id": occured_leaf_id,
             "cluster_occur": cluster_occur,
             "viewspace_points": screenspace_points,
-            "visibility_filter": radii > 0,
+            "visibility_filter": viewed_pts,
             "radii": radii}
