@@ -41,6 +41,20 @@ namespace ogs {
 #define KM_PPT 4                              // points per thread (packed pairs)
 #endif
 #define KM_CTA_POINTS (KM_THREADS * KM_PPT)   // 1024
+// Tile buffers in shared memory.  A thread copies its four points into registers before it scores them, so the tile
+// buffer is free again as soon as every thread has done that: ONE buffer, refilled by the next tile's bulk copy while
+// the current tile is scored, hides the copy just as well as two -- and at k = 64, D = 9 it takes the CTA from 95 KB to
+// 59 KB of shared memory, i.e. from two to three CTAs (24 warps) per SM.  The kernel is bound by fixed-latency
+// dependencies (ncu: `wait` 1.8 and `short_scoreboard` 1.2 stall cycles per issue at 4 warps per scheduler), so the
+// extra warps are what it needs.
+#ifndef KM_NBUF
+#define KM_NBUF 1
+#endif
+#define KM_MAX_PER_SM 3                       // 80 registers x 256 threads: three CTAs fill the register file
+static inline int km_ctas_per_sm(size_t smem) {
+    int n = (int)((size_t)226 * 1024 / (smem + 1024));
+    return n < 1 ? 1 : (n > KM_MAX_PER_SM ? KM_MAX_PER_SM : n);
+}
 #define KM_GROUP 16                           // CTAs per first-level group of the fused reduction
 
 // ---- TMA bulk copy (global -> shared, completion on an mbarrier) ----
@@ -97,8 +111,8 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
     const int tile_floats = KM_CTA_POINTS * D;            // a rows then b rows of one tile
-    float* s_pts = smem;                                  // [2][tile_floats]
-    float* s_c = smem + 2 * (size_t)tile_floats;          // [k][DP]
+    float* s_pts = smem;                                  // [KM_NBUF][tile_floats]
+    float* s_c = smem + KM_NBUF * (size_t)tile_floats;    // [k][DP]
     float* s_acc = s_c + (size_t)k * DP;                  // [KM_WARPS][k][D+1] (only when partials)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -142,9 +156,9 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
     int buf = 0;
     if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(blockIdx.x)) issue(blockIdx.x, 0);
 
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= (KM_NBUF - 1)) {
         const int64_t tn = t + gridDim.x;
-        if (threadIdx.x == 0 && tn < n_tiles && tile_is_bulk(tn)) {
+        if (KM_NBUF == 2 && threadIdx.x == 0 && tn < n_tiles && tile_is_bulk(tn)) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // buffer was last read through the generic proxy
             issue(tn, buf ^ 1);
         }
@@ -180,6 +194,13 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
                     else v = (d < Da) ? __ldg(a + i * Da + d) : __fmul_rn(__ldg(b + i * Db + (d - Da)), scale_b);
                 }
                 if (q & 1) X[q >> 1][d].y = v; else X[q >> 1][d].x = v;
+            }
+        }
+        if (KM_NBUF == 1 && staged) {
+            __syncthreads();             // every thread holds its points in registers: the buffer can take the next tile
+            if (threadIdx.x == 0 && tn < n_tiles && tile_is_bulk(tn)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(tn, 0);
             }
         }
         float2 best[KM_PPT / 2];
@@ -249,7 +270,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
                 __syncwarp();
             }
         }
-        if (staged) __syncthreads();   // everyone is done with s_pts[buf] before it is refilled two tiles from now
+        if (KM_NBUF == 2 && staged) __syncthreads();   // everyone is done with s_pts[buf] before it is refilled two tiles from now
     }
     if (partials) {
         __syncthreads();
@@ -343,14 +364,14 @@ static int launch_assign_d(int64_t N, const float* a, int Da, const float* b, in
                            const float* centers, int k, const int64_t* select_ids, int64_t selected,
                            int64_t id_offset, int64_t* ids_out, float* sums, float* counts, cudaStream_t s) {
     const bool fuse = (sums != nullptr) || (counts != nullptr);
-    size_t smem = (size_t)2 * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
+    size_t smem = (size_t)KM_NBUF * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
     if (fuse) smem += (size_t)KM_WARPS * k * (D + 1) * sizeof(float);
     if (smem > 220 * 1024) { set_error("kmeans_assign: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
     { const int rc_attr = ensure_assign_smem<D>(smem); if (rc_attr) return rc_attr; }
     // bulk copies need 16-byte aligned sources and sizes: tile strides are multiples of 4096 bytes
     const int bulk_ok = (((uintptr_t)a & 15) == 0 && (Db == 0 || ((uintptr_t)b & 15) == 0)) ? 1 : 0;
     int64_t want = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
-    const int per_sm = smem > 110 * 1024 ? 1 : 2;
+    const int per_sm = km_ctas_per_sm(smem);
     int grid = (int)(want < (int64_t)OGS_NUM_SMS * per_sm ? want : (int64_t)OGS_NUM_SMS * per_sm);
     if (grid < 1) grid = 1;
     float* partials = nullptr;
@@ -388,7 +409,7 @@ int launch_kmeans_assign(int64_t N, const float* a, int Da, const float* b, int 
 // ---- one Lloyd iteration in one launch (assign + centroid sums + [peer all-reduce] + centre update) ----
 // workspace (caller-owned, zero-initialised once): [tickets: 256 B][partials: grid_max * k * (D+1) floats][group tables]
 size_t kmeans_lloyd_workspace_bytes(int k, int D) {
-    const size_t grid_max = (size_t)OGS_NUM_SMS * 2;
+    const size_t grid_max = (size_t)OGS_NUM_SMS * KM_MAX_PER_SM;
     return 256 + (grid_max + (grid_max + KM_GROUP - 1) / KM_GROUP) * k * (D + 1) * sizeof(float);
 }
 
@@ -396,7 +417,7 @@ template <int D>
 static int launch_lloyd_d(int64_t N, const float* a, int Da, const float* b, int Db, float scale_b, float* centers, int k,
                           int k_out, const int64_t* select_ids, int64_t selected, int64_t id_offset, int64_t* ids_out,
                           float* counts_state, float eps_add, const ogs_peer_comm* comm, void* workspace, cudaStream_t s) {
-    size_t smem = (size_t)2 * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
+    size_t smem = (size_t)KM_NBUF * KM_CTA_POINTS * D * sizeof(float) + (size_t)k * ((D + 1 + 3) & ~3) * sizeof(float);
     smem += (size_t)KM_WARPS * k * (D + 1) * sizeof(float);
     if (smem > 220 * 1024) { set_error("kmeans_lloyd_pass: k=%d D=%d needs %zu B shared memory", k, D, smem); return -5; }
     if (comm && (size_t)k * (D + 1) * sizeof(float) > peer_comm_slot_bytes(comm)) {
@@ -406,7 +427,7 @@ static int launch_lloyd_d(int64_t N, const float* a, int Da, const float* b, int
     { const int rc_attr = ensure_assign_smem<D>(smem); if (rc_attr) return rc_attr; }
     const int bulk_ok = (((uintptr_t)a & 15) == 0 && (Db == 0 || ((uintptr_t)b & 15) == 0)) ? 1 : 0;
     int64_t want = (N + KM_CTA_POINTS - 1) / KM_CTA_POINTS;
-    const int per_sm = smem > 110 * 1024 ? 1 : 2;
+    const int per_sm = km_ctas_per_sm(smem);
     int grid = (int)(want < (int64_t)OGS_NUM_SMS * per_sm ? want : (int64_t)OGS_NUM_SMS * per_sm);
     if (grid < 1) grid = 1;                          // an empty shard still takes part in the collective
     KmTail tail;

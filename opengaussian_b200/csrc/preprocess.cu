@@ -53,8 +53,12 @@ __device__ __forceinline__ void unit_half_row(const float* __restrict__ extra, f
     for (int c = 0; c < n_extra; c++) feat[(size_t)i * n_extra + c] = (extra[(size_t)i * n_extra + c] / nrm + 1.0f) / 2.0f;
 }
 
+#ifndef SH_UB
+#define SH_UB 6     // 16-byte SH loads in flight per thread while the block's slab is staged (12 per thread at degree 3)
+#endif
+
 template <bool HAS_SH>
-__global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
+__global__ void __launch_bounds__(PF, HAS_SH ? 8 : 1) preprocess_fwd_kernel(PreprocessArgs a) {
     extern __shared__ float s_sh[];  // [PF][M*3 + 1] when HAS_SH
     __shared__ uint8_t s_vis[PF];
     const int i = blockIdx.x * PF + threadIdx.x;
@@ -189,21 +193,37 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
             // the slab base is 16-byte aligned (PF * pr * 4 bytes per CTA); a float4 may straddle two rows
             const float4* src = reinterpret_cast<const float4*>(a.shs_rest + base_r);
             const int n4 = (PF * pr) / 4;
-            for (int e = threadIdx.x; e < n4; e += PF) {
-                const int f = e * 4;
-                const int g0 = by_pr(f), g3 = by_pr(f + 3);
-                if ((s_vis[g0] || s_vis[g3 < PF ? g3 : g0]) && base_r + f + 3 < tot_r) {
-                    const float4 q = __ldg(src + e);
-                    const float v4[4] = {q.x, q.y, q.z, q.w};
+            // SH_UB loads are issued before the first shared-memory store that depends on one of them: the loop used to
+            // alternate LDG.128 -> STS (in-order issue stalls on the store's operand), i.e. one DRAM round trip per
+            // 16 bytes and thread -- ncu: 8.8 long-scoreboard stall cycles per issued instruction
+            for (int e0 = threadIdx.x; e0 < n4; e0 += PF * SH_UB) {
+                float4 q[SH_UB];
+                int mode[SH_UB];                   // 0: nothing, 1: one 16-byte load, 2: ragged end of the tensor
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const int gi = by_pr(f + t), k = (f + t) - gi * pr;
-                        if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = v4[t];
+                for (int u = 0; u < SH_UB; u++) {
+                    const int e = e0 + u * PF, f = e * 4;
+                    mode[u] = 0;
+                    if (e < n4) {
+                        const int g0 = by_pr(f), g3 = by_pr(f + 3);
+                        if ((s_vis[g0] || s_vis[g3 < PF ? g3 : g0]) && base_r + f + 3 < tot_r) { mode[u] = 1; q[u] = __ldg(src + e); }
+                        else if (base_r + f < tot_r) mode[u] = 2;
                     }
-                } else if (base_r + f < tot_r) {   // ragged end of the tensor
-                    for (int t = 0; t < 4 && base_r + f + t < tot_r; t++) {
-                        const int gi = by_pr(f + t), k = (f + t) - gi * pr;
-                        if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + f + t);
+                }
+#pragma unroll
+                for (int u = 0; u < SH_UB; u++) {
+                    const int f = (e0 + u * PF) * 4;
+                    if (mode[u] == 1) {
+                        const float v4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const int gi = by_pr(f + t), k = (f + t) - gi * pr;
+                            if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = v4[t];
+                        }
+                    } else if (mode[u] == 2) {
+                        for (int t = 0; t < 4 && base_r + f + t < tot_r; t++) {
+                            const int gi = by_pr(f + t), k = (f + t) - gi * pr;
+                            if (s_vis[gi]) s_sh[gi * (per + 1) + 3 + k] = __ldg(a.shs_rest + base_r + f + t);
+                        }
                     }
                 }
             }
@@ -216,13 +236,25 @@ __global__ void __launch_bounds__(PF) preprocess_fwd_kernel(PreprocessArgs a) {
         const SmallDiv by_per(per);
         if ((per & 3) == 0) {
             const float4* src = reinterpret_cast<const float4*>(a.shs + base);
-            for (int e = threadIdx.x; e < PF / 4 * per; e += PF) {
-                const int f = e * 4;
-                const int gi = by_per(f), k = f - gi * per;   // per % 4 == 0: the 4 floats share gi
-                if (s_vis[gi]) {
-                    const float4 q = __ldg(src + e);
-                    float* d = s_sh + gi * (per + 1) + k;
-                    d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+            const int total = PF / 4 * per;
+            for (int e0 = threadIdx.x; e0 < total; e0 += PF * SH_UB) {       // loads first, stores after (see above)
+                float4 q[SH_UB];
+                int dsti[SH_UB];
+#pragma unroll
+                for (int u = 0; u < SH_UB; u++) {
+                    const int e = e0 + u * PF, f = e * 4;
+                    dsti[u] = -1;
+                    if (e < total) {
+                        const int gi = by_per(f);                             // per % 4 == 0: the 4 floats share gi
+                        if (s_vis[gi]) { dsti[u] = gi * (per + 1) + (f - gi * per); q[u] = __ldg(src + e); }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SH_UB; u++) {
+                    if (dsti[u] >= 0) {
+                        float* d = s_sh + dsti[u];
+                        d[0] = q[u].x; d[1] = q[u].y; d[2] = q[u].z; d[3] = q[u].w;
+                    }
                 }
             }
         } else {
