@@ -97,13 +97,14 @@ def main():
         for d in table:
             w.writerow([d["kernel"][:80]] + [("%.4g" % d[c]) if c in d else "" for c in cols[1:]])
     # one Stage-1 training step (scripts/gpu_evidence_r2.sh part c): its own table, not part of traffic.json
-    rep = os.path.join(SRC, f"{tag}_stage1.ncu-rep")
-    if os.path.exists(rep):
-        with open(os.path.join(OUT, f"{tag}_stage1_kernels_full.csv"), "w", newline="") as f:
-            w = csv.writer(f)
-            w.writerow(cols)
-            for d in raw_rows(rep):
-                w.writerow([d["kernel"][:80]] + [("%.4g" % d[c]) if c in d else "" for c in cols[1:]])
+    for suffix in ("stage1", "stage1_cached"):
+        rep = os.path.join(SRC, f"{tag}_{suffix}.ncu-rep")
+        if os.path.exists(rep):
+            with open(os.path.join(OUT, f"{tag}_{suffix}_kernels_full.csv"), "w", newline="") as f:
+                w = csv.writer(f)
+                w.writerow(cols)
+                for d in raw_rows(rep):
+                    w.writerow([d["kernel"][:80]] + [("%.4g" % d[c]) if c in d else "" for c in cols[1:]])
     # per-family DRAM traffic per launch group: kernels of one family inside ONE frame are summed
     fam_acc = {}
     for d in table:

@@ -207,3 +207,35 @@ def test_reference_call_convention_on_a_cached_view():
     assert torch.equal(img_sh, img_sh_ref) and torch.equal(img_sh2, img_sh_ref)
     assert torch.equal(run(f0, True)[0], ref0[0])                       # the precomputed-colour entry is still intact
     rz.view_cache.clear()
+
+
+@pytest.mark.parametrize("cached", [False, True])
+def test_multi_view_step_accumulates_feature_gradients(cached):
+    """A Stage-1 step over several views (dist.render_views_backward): the 2nd..Vth view add their `_ins_feat` gradient
+    into the existing .grad inside the backward's own kernel (feat_grad_kernel, accumulate form) -- with resident views
+    and without.  Must equal the sum of the views' separate gradients."""
+    from opengaussian_b200 import dist as ogd, rasterizer as rz
+    from opengaussian_b200.renderer import render
+    dev = torch.device("cuda")
+    gs, cams = synth.make_scene("plumbing_10k_256", n_views=3)
+    cam = [_cam(c, dev) for c in cams]
+    pc = synth.SynthModel(gs, dev, stage0=False)
+    bg = torch.zeros(3, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(9)
+    G = [torch.randn(6, cam[0].image_height, cam[0].image_width, device=dev, generator=gen) for _ in cam]
+    rz.view_cache.clear()
+    want = torch.zeros_like(pc._ins_feat)
+    for i in range(3):
+        want += _render(cam[i], pc, bg, G[i], cached=False)[2]
+    prev, rz.view_cache.enabled = rz.view_cache.enabled, cached
+    try:
+        for rep in range(2):                 # second repetition: every view is resident when cached
+            pc._ins_feat.grad = None
+            ogd.render_views_backward(lambda i: (render(cam[i], pc, PIPE, bg, 40_000, rescale=False)["ins_feat"] * G[i]).sum(),
+                                      [0, 1, 2], [pc._ins_feat], already_split=True)
+            got = pc._ins_feat.grad
+            assert float((got - want).abs().max()) <= 3e-5 * float(want.abs().max())
+        assert len(rz.view_cache) == (3 if cached else 0)
+    finally:
+        rz.view_cache.enabled = prev
+        rz.view_cache.clear()
