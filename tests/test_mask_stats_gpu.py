@@ -248,3 +248,22 @@ def test_calculate_iou_edge_cases():
     assert torch.allclose(calculate_iou(v, v), torch.ones(2, 2, device="cuda"))
     with pytest.raises(_lib.OgsError):
         calculate_iou(o.cpu(), o.cpu())
+
+
+@pytest.mark.parametrize("M,H,W", [(1, 16, 16), (7, 48, 64), (120, 968, 1296), (254, 64, 80), (255, 64, 80), (300, 32, 48),
+                                   (12, 33, 35)])
+def test_sam_mask_expansion_equals_one_hot(M, H, W):
+    """get_SAM_mask_and_feat's [num_mask,H,W] bool masks (reference utils/opengs_utlis.py:146-148: one_hot of the id map,
+    mask 0 dropped) from the byte-parallel expansion kernel (M <= 254, H*W % 16 == 0) and from the per-mask kernel."""
+    from opengaussian_b200 import mask_stats as ms
+    g = torch.Generator().manual_seed(M * 131 + H)
+    level_ids = torch.randint(-1, M, (H, W), generator=g)             # the SAM file's ids: -1 = no mask, 0..M-1 = masks
+    level_ids[0, :4] = torch.tensor([0, min(1, M - 1), -1, M - 1])    # a 0x01 byte above a 0x00 byte, "no mask", the last id
+    sam = torch.stack([level_ids, level_ids, level_ids, level_ids]).cuda()
+    mask_id, mask_bool, invalid = ms.get_SAM_mask_and_feat(sam, level=0, num_mask=M)
+    want_id = level_ids.cuda() + 1                                    # reference :142: 0 = invalid, 1..M
+    want = torch.nn.functional.one_hot(want_id, M + 1).permute(2, 0, 1)[1:].bool()
+    assert mask_bool.shape == (M, H, W) and mask_bool.dtype == torch.bool
+    assert torch.equal(mask_bool, want)
+    assert torch.equal(mask_bool.view(torch.uint8), want.view(torch.uint8))      # bytes are exactly 0 / 1
+    assert torch.equal(invalid, want_id == 0) and torch.equal(mask_id, want_id)
