@@ -113,7 +113,7 @@ class ViewCache:
     (train.py:431-436), but the reference re-runs preprocess, duplication and the 64-bit sort on every render() of a
     training camera for 40 000 iterations.  Here a forward whose geometry parameters do not require grad leaves its
     geometry + binning buffers in this cache (exact-size copies: ~95 MB per view at 1 M Gaussians / 10 M duplicates;
-    the default budget is 35 % of the device's memory, i.e. hundreds of views on a 180 GB B200, LRU beyond that), and
+    the default budget is 25 % of the device's memory, i.e. hundreds of views on a 180 GB B200, LRU beyond that), and
     the next forward of the same camera runs only the feature activation and the blend kernel
     (C ABI ogs_raster_forward_cached) -- bit-identical images, the usual backward.
 
@@ -127,7 +127,7 @@ class ViewCache:
     def __init__(self):
         self.enabled = os.environ.get("OGS_VIEW_CACHE", "1") != "0"
         gb = os.environ.get("OGS_VIEW_CACHE_GB")
-        self.max_bytes = None if gb is None else int(float(gb) * 2 ** 30)   # None: 35 % of the device, set on first use
+        self.max_bytes = None if gb is None else int(float(gb) * 2 ** 30)   # None: 25 % of the device, set on first use
         self._entries = collections.OrderedDict()      # camera key -> _ViewEntry, least recently used first
         self._lock = threading.Lock()
         self.bytes = 0
@@ -169,7 +169,7 @@ class ViewCache:
         with self._lock:
             if self.max_bytes is None:
                 total = torch.cuda.get_device_properties(device).total_memory if device is not None else 0
-                self.max_bytes = int(0.35 * total)
+                self.max_bytes = int(0.25 * total)
             old = self._entries.pop(cam_key, None)          # same camera, other geometry: superseded
             if old is not None:
                 self.bytes -= old.nbytes
