@@ -16,7 +16,8 @@ parameters' CURRENT VALUES and tensors that stay alive at the same address (came
 its Python side effects happen only on the eager and the capturing visit.  Parameters are read in place, so optimizer
 steps are seen; a parameter that is REPLACED by a new tensor (or any change the ``guard`` reports, e.g. the geometry's
 version counters) drops the graphs and starts over.  Gradients are written, not accumulated: after the call
-``p.grad`` is this view's gradient (the graph's own buffer, valid until the same view is replayed again).
+``p.grad`` is this view's gradient (the graph's own buffer, valid until the same view is replayed again);
+``step(view, accumulate=True)`` adds it to an existing ``.grad`` instead (the 2nd..Vth view of a multi-view step).
 Anything that cannot be captured -- a view whose geometry is not resident (cache disabled or over budget), trainable
 geometry (the forward then has to read the frame's duplicate count back) -- runs eagerly, every time, with the same
 results."""
@@ -69,9 +70,13 @@ class GraphedViewStep:
     def stats(self):
         return dict(graphs=len(self._graphs), replays=self.replays, captures=self.captures, eager=self.eager)
 
-    def _eager(self, view):
-        for p in self.params:
-            p.grad = None
+    def _graphable(self):
+        return bool(self.params) and self.params[0].is_cuda
+
+    def _eager(self, view, accumulate=False):
+        if not accumulate:
+            for p in self.params:
+                p.grad = None
         loss = self.view_loss(view)
         loss.backward()
         self.eager += 1
@@ -105,9 +110,9 @@ class GraphedViewStep:
         self.captures += 1
         return g
 
-    def __call__(self, view) -> torch.Tensor:
-        if not self.params or not self.params[0].is_cuda:
-            return self._eager(view)
+    def __call__(self, view, accumulate: bool = False) -> torch.Tensor:
+        if not self._graphable():
+            return self._eager(view, accumulate)
         sig = self._signature()
         if sig != self._sig:                # parameters replaced or geometry changed: every graph reads stale addresses
             self.reset()
@@ -117,13 +122,21 @@ class GraphedViewStep:
         if g is None:
             if k in self._eager_only or k not in self._seen:
                 self._seen.add(k)
-                return self._eager(view)
+                return self._eager(view, accumulate)
+            held = [p.grad for p in self.params] if accumulate else None     # the capture starts from .grad = None
             try:
                 g = self._capture(view, sig)
             except (_rz._lib.OgsError, RuntimeError):
                 self._eager_only.add(k)
-                torch.cuda.synchronize(self.params[0].device)
-                return self._eager(view)
+                if self.params[0].is_cuda:
+                    torch.cuda.synchronize(self.params[0].device)
+                if held is not None:
+                    for p, h in zip(self.params, held):
+                        p.grad = h
+                return self._eager(view, accumulate)
+            if held is not None:
+                for p, h in zip(self.params, held):
+                    p.grad = h
             self._graphs[k] = g
             if self.max_graphs is not None:
                 while len(self._graphs) > self.max_graphs:
@@ -133,5 +146,8 @@ class GraphedViewStep:
         g.graph.replay()
         self.replays += 1
         for p, gr in zip(self.params, g.grads):
-            p.grad = gr
+            if accumulate and p.grad is not None and gr is not None and p.grad is not gr:
+                p.grad.add_(gr)
+            else:
+                p.grad = gr
         return g.loss

@@ -122,7 +122,8 @@ class ViewCache:
     and views -- so the per-iteration `.detach()` of train.py:431-436 still hits, an optimizer step or a densification
     misses).  The entry holds references to those tensors, so an address cannot be recycled while it is alive.
     NOT seen: writes through `tensor.data` or raw pointers -- call `view_cache.clear()` after such edits, or set
-    `view_cache.enabled = False` (env OGS_VIEW_CACHE=0)."""
+    `view_cache.enabled = False` (env OGS_VIEW_CACHE=0; per call: `pipe.view_cache = False` in render()).  The `radii`
+    a cache hit returns alias the entry's copy: read-only, as every caller in the reference treats them."""
 
     def __init__(self):
         self.enabled = os.environ.get("OGS_VIEW_CACHE", "1") != "0"
@@ -137,6 +138,11 @@ class ViewCache:
         with self._lock:
             self._entries.clear()
             self.bytes = 0
+
+    def disabled(self):
+        """Context manager: forwards issued inside neither read nor fill the cache (render() uses it for
+        ``pipe.view_cache = False``)."""
+        return _CacheSwitch(self, False)
 
     def __len__(self):
         return len(self._entries)
@@ -182,6 +188,19 @@ class ViewCache:
             self._entries[cam_key] = entry
             self.bytes += entry.nbytes
             return True
+
+
+class _CacheSwitch:
+    def __init__(self, cache, on):
+        self.cache, self.on = cache, on
+
+    def __enter__(self):
+        self.prev, self.cache.enabled = self.cache.enabled, self.on
+        return self.cache
+
+    def __exit__(self, *exc):
+        self.cache.enabled = self.prev
+        return False
 
 
 view_cache = ViewCache()
@@ -407,7 +426,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 e.geom_key = geom_key
                 e.geom = alloc.bufs["geom"][:gb.value].clone()          # exact-size copies: the forward's own buffers
                 e.binning = alloc.bufs["binning"][:bb.value].clone()    # carry the capacity estimate's head room
-                e.radii = radii
+                e.radii = radii.clone()      # the caller owns the tensor this call returns; later hits alias the entry's copy
                 e.state = _lib.RasterState(e.geom.data_ptr(), e.binning.data_ptr(), None, st.num_rendered, gb.value,
                                            bb.value, 0, None)
                 e.keep = (rs.viewmatrix, rs.projmatrix, rs.campos, means3D, opacities, sh, sh_rest, scales, rotations,

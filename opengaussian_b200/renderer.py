@@ -23,6 +23,7 @@ import math
 import torch
 
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, pin_for_capture
+from .rasterizer import view_cache as _view_cache
 
 
 def _knn_mean_dists(x: torch.Tensor, K: int, chunk: int = 4096) -> torch.Tensor:
@@ -113,7 +114,14 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, iteration,
            post_process=False,     # post
            root_num=64, leaf_num=10,
            fused=True):
-    """Render the scene.  Background tensor (bg_color) must be on GPU!"""
+    """Render the scene.  Background tensor (bg_color) must be on GPU!
+    ``pipe.view_cache = False`` keeps this call out of the frozen-geometry view cache (rasterizer.ViewCache)."""
+    if getattr(pipe, "view_cache", True) is False and _view_cache.enabled:
+        with _view_cache.disabled():
+            return render(viewpoint_camera, pc, pipe, bg_color, iteration, scaling_modifier, override_color, visible_mask,
+                          mask_num, cluster_idx, leaf_cluster_idx, rescale, origin_feat, render_feat_map, render_color,
+                          render_cluster, better_vis, selected_root_id, selected_leaf_id, pre_mask, seg_rgb, post_process,
+                          root_num, leaf_num, fused)
     xyz = pc.get_xyz
     # Screen-space gradient sink (reference :45): its .grad feeds the densification statistics (train.py:598,
     # scene/gaussian_model.py:512-514), which only exist while the geometry trains.  From stage 1 on OpenGaussian

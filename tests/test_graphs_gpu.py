@@ -119,3 +119,20 @@ def test_uncapturable_views_run_eagerly():
         _check(step2(0), pc._ins_feat.grad, want)
     assert step2.stats()["graphs"] == 1
     rz.view_cache.clear()
+
+
+def test_multi_view_step_with_accumulate():
+    """step(view, accumulate=True) adds the view's gradient to the existing .grad -- eager, capturing and replaying visits."""
+    from opengaussian_b200 import rasterizer as rz
+    from opengaussian_b200.graphs import GraphedViewStep, geometry_guard
+    dev, pc, view_loss = _setup("plumbing_10k_256", 2)
+    rz.view_cache.clear()
+    rz.view_cache.enabled = True
+    w0, w1 = _eager(view_loss, pc, 0), _eager(view_loss, pc, 1)
+    step = GraphedViewStep(view_loss, [pc._ins_feat], guard=geometry_guard(pc))
+    for visit in range(4):
+        step(0)
+        step(1, accumulate=True)
+        _check(w0[0] + w1[0], pc._ins_feat.grad, (w0[0] + w1[0], w0[1] + w1[1]))
+    assert step.stats()["graphs"] == 2 and step.stats()["replays"] == 6
+    rz.view_cache.clear()

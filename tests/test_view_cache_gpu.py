@@ -239,3 +239,26 @@ def test_multi_view_step_accumulates_feature_gradients(cached):
     finally:
         rz.view_cache.enabled = prev
         rz.view_cache.clear()
+
+
+def test_pipe_flag_keeps_a_call_out_of_the_cache():
+    from opengaussian_b200 import rasterizer as rz
+    from opengaussian_b200.renderer import render
+    dev = torch.device("cuda")
+    gs, cams = synth.make_scene("plumbing_10k_256", n_views=1)
+    cam = _cam(cams[0], dev)
+    pc = synth.SynthModel(gs, dev, stage0=False)
+    bg = torch.zeros(3, device=dev)
+    rz.view_cache.clear()
+    off = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False, view_cache=False)
+    a = render(cam, pc, off, bg, 40_000, rescale=False)
+    assert len(rz.view_cache) == 0 and rz.view_cache.enabled
+    b = render(cam, pc, PIPE, bg, 40_000, rescale=False)
+    c = render(cam, pc, PIPE, bg, 40_000, rescale=False)
+    assert len(rz.view_cache) == 1
+    for k in IMG_KEYS:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k])
+    b["radii"].add_(1)                                  # the first call's radii belong to the caller ...
+    d = render(cam, pc, PIPE, bg, 40_000, rescale=False)
+    assert torch.equal(d["radii"], a["radii"])          # ... the entry keeps its own copy
+    rz.view_cache.clear()
