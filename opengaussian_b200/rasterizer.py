@@ -117,6 +117,10 @@ class ViewCache:
     the next forward of the same camera runs only the feature activation and the blend kernel
     (C ABI ogs_raster_forward_cached) -- bit-identical images, the usual backward.
 
+    Admission: forwards on the model's own parameter tensors (raw-parameter mode, what render() uses for its fused pass)
+    fill an entry at once; forwards on activated tensors only when the same tensors arrive twice in a row
+    (`second_sighting`) -- the getters, the Stage-2 rescale draw and the cluster filters build new tensors per call.
+
     Validity is decided from what torch guarantees: an entry is keyed by the camera tensors and matched against the
     geometry tensors' storage address, shape and VERSION COUNTER (bumped by every in-place op, shared by detach()
     and views -- so the per-iteration `.detach()` of train.py:431-436 still hits, an optimizer step or a densification
@@ -130,6 +134,7 @@ class ViewCache:
         gb = os.environ.get("OGS_VIEW_CACHE_GB")
         self.max_bytes = None if gb is None else int(float(gb) * 2 ** 30)   # None: 25 % of the device, set on first use
         self._entries = collections.OrderedDict()      # camera key -> _ViewEntry, least recently used first
+        self._sight = {}                               # device index -> (key, tensors) of the last unadmitted forward
         self._lock = threading.Lock()
         self.bytes = 0
         self.hits = self.misses = self.evictions = 0
@@ -137,7 +142,23 @@ class ViewCache:
     def clear(self):
         with self._lock:
             self._entries.clear()
+            self._sight.clear()
             self.bytes = 0
+
+    def second_sighting(self, device_index, key, keep) -> bool:
+        """Admission rule for forwards that receive ACTIVATED tensors (the reference's own call convention): the getters
+        of scene/gaussian_model.py:122-169 build new tensors on every call, so do the Stage-2 rescale draw and the
+        cluster filters of render() -- geometry that will never be seen again must not cost an entry (two buffer copies,
+        a host wait for the frame's duplicate count, the eviction of a useful view).  Such a forward is admitted only
+        when the forward before it on this device had exactly the same key; the record holds that forward's tensors, so
+        a recycled address cannot fake the match.  Raw-parameter forwards (the model's own parameter tensors) are
+        admitted at once."""
+        with self._lock:
+            last = self._sight.get(device_index)
+            if last is not None and last[0] == key:
+                return True
+            self._sight[device_index] = (key, keep)
+            return False
 
     def disabled(self):
         """Context manager: forwards issued inside neither read nor fill the cache (render() uses it for
@@ -156,7 +177,7 @@ class ViewCache:
         dev = means3D.device
         cam = (dev.type, dev.index, _sig(rs.viewmatrix), _sig(rs.projmatrix), _sig(rs.campos), int(rs.image_height),
                int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
-               int(rs.sh_degree) if sh is not None else -1)
+               int(rs.sh_degree) if sh is not None else -1, bool(int(act_flags) & ~_lib.ACT_EXTRA_UNIT_HALF))
         geom = (_sig(means3D), _sig(opacities), _sig(sh), _sig(sh_rest), colors_precomp is not None, _sig(scales),
                 _sig(rotations), _sig(cov3D), int(act_flags) & ~_lib.ACT_EXTRA_UNIT_HALF, bool(n_feat_act))
         return cam, geom
@@ -393,11 +414,17 @@ class _RasterizeGaussians(torch.autograd.Function):
         frozen = view_cache.enabled and P > 0 and not rs.debug and not any(
             t is not None and t.requires_grad for t in (means3D, sh, opacities, scales, rotations, cov3Ds_precomp, sh_rest))
         entry = cam_key = geom_key = None
+        admit = False
         if frozen:
             n_feat_act = n_extra if (act_flags & _lib.ACT_EXTRA_UNIT_HALF) else 0
             cam_key, geom_key = ViewCache.keys(rs, means3D, opacities, sh, sh_rest, colors_precomp, scales, rotations,
                                                cov3Ds_precomp, act_flags, n_feat_act)
             entry = view_cache.lookup(cam_key, geom_key)
+            if entry is None:
+                keep = (rs.viewmatrix, rs.projmatrix, rs.campos, means3D, opacities, sh, sh_rest, scales, rotations,
+                        cov3Ds_precomp)
+                admit = bool(act_flags & ~_lib.ACT_EXTRA_UNIT_HALF) or \
+                    view_cache.second_sighting(dev.index, (cam_key, geom_key), keep)
         if entry is None and torch.cuda.is_current_stream_capturing():
             raise _lib.OgsError("GaussianRasterizer under CUDA-graph capture needs the view's geometry resident in "
                                 "rasterizer.view_cache (frozen geometry, one eager visit first): a fresh forward reads "
@@ -412,13 +439,13 @@ class _RasterizeGaussians(torch.autograd.Function):
             _lib.check(rc, "ogs_raster_forward_cached")
             alloc.bufs["geom"], alloc.bufs["binning"] = entry.geom, entry.binning
         else:
-            if frozen:
+            if admit:
                 ri.defer_capacity_check = 0      # the entry needs this frame's duplicate count now
             ro = _lib.RasterOutputs(_lib.ptr(color_all), _lib.ptr(depth), _lib.ptr(alpha), _lib.ptr(radii))
             with torch.cuda.device(dev):
                 rc = L.ogs_raster_forward(C.byref(ri), C.byref(ro), alloc.fn, alloc.user, C.byref(st), C.c_void_p(stream))
             _lib.check(rc, "ogs_raster_forward")
-            if frozen and int(st.num_rendered) >= 0:
+            if admit and int(st.num_rendered) >= 0:
                 gb, bb = C.c_int64(0), C.c_int64(0)
                 _lib.check(L.ogs_raster_cached_bytes(C.byref(ri), st.num_rendered, C.byref(gb), C.byref(bb)),
                            "ogs_raster_cached_bytes")
@@ -429,8 +456,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 e.radii = radii.clone()      # the caller owns the tensor this call returns; later hits alias the entry's copy
                 e.state = _lib.RasterState(e.geom.data_ptr(), e.binning.data_ptr(), None, st.num_rendered, gb.value,
                                            bb.value, 0, None)
-                e.keep = (rs.viewmatrix, rs.projmatrix, rs.campos, means3D, opacities, sh, sh_rest, scales, rotations,
-                          cov3Ds_precomp)
+                e.keep = keep
                 e.nbytes = gb.value + bb.value + radii.numel() * 4
                 view_cache.insert(cam_key, e, dev)
 

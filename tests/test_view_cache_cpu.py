@@ -76,3 +76,20 @@ def test_lookup_insert_supersede_and_lru():
     vc.clear()
     assert len(vc) == 0 and vc.bytes == 0
     assert set(vc.stats()) >= {"entries", "bytes", "hits", "misses", "evictions", "max_bytes"}
+
+
+def test_activated_tensors_are_admitted_on_their_second_sighting_only():
+    vc = ViewCache()
+    t1, t2 = torch.zeros(3), torch.zeros(3)
+    assert not vc.second_sighting(0, ("cam", _sig(t1)), (t1,))          # first time: remembered, not admitted
+    assert vc.second_sighting(0, ("cam", _sig(t1)), (t1,))              # the same tensors again: admitted
+    assert not vc.second_sighting(0, ("cam", _sig(t2)), (t2,))          # other tensors (a getter's new result): not admitted
+    assert not vc.second_sighting(0, ("cam", _sig(t1)), (t1,))          # ... and the alternation never is
+    assert not vc.second_sighting(1, ("cam", _sig(t1)), (t1,))          # records are per device
+    vc.clear()
+    assert not vc.second_sighting(0, ("cam", _sig(t1)), (t1,))
+    # raw-parameter and activated forwards of one camera are different entries (the flag is part of the camera key)
+    view, proj, pos = torch.eye(4), torch.eye(4), torch.zeros(3)
+    g = _geo()
+    assert _keys(_rs(view, proj, pos), g, act=7)[0] != _keys(_rs(view, proj, pos), g, act=0)[0]
+    assert _keys(_rs(view, proj, pos), g, act=7)[0] == _keys(_rs(view, proj, pos), g, act=7 | 8)[0]

@@ -189,9 +189,12 @@ def test_reference_call_convention_on_a_cached_view():
     f0 = gs["ins_feat"][:, :3].to(dev)
     f1 = gs["ins_feat"][:, 3:].to(dev)
     ref0, ref1 = run(f0, False), run(f1, False)
-    a, b, cc = run(f0, True), run(f0, True), run(f1, True)              # miss, hit, hit with other colours
-    assert len(rz.view_cache) == 1 and rz.view_cache.hits >= 2
-    for got, want in ((a, ref0), (b, ref0), (cc, ref1)):
+    h0 = rz.view_cache.hits
+    z = run(f0, True)                                                   # activated tensors: the first sighting is not kept
+    assert len(rz.view_cache) == 0
+    a, b, cc = run(f0, True), run(f0, True), run(f1, True)              # admitted (same tensors again), hit, hit with other colours
+    assert len(rz.view_cache) == 1 and rz.view_cache.hits == h0 + 2
+    for got, want in ((z, ref0), (a, ref0), (b, ref0), (cc, ref1)):
         for x, y in zip(got[:4], want[:4]):
             assert torch.equal(x, y)
         for x, y in zip(got[4:], want[4:]):
@@ -199,6 +202,13 @@ def test_reference_call_convention_on_a_cached_view():
     # an SH pass of the same camera and geometry is its own entry (SH colours live in the cached records)
     img_sh = GaussianRasterizer(rs)(means2D=torch.zeros_like(geo["means3D"]), shs=shs, **geo)[0]
     img_sh2 = GaussianRasterizer(rs)(means2D=torch.zeros_like(geo["means3D"]), shs=shs, **geo)[0]
+    img_sh3 = GaussianRasterizer(rs)(means2D=torch.zeros_like(geo["means3D"]), shs=shs, **geo)[0]
+    assert len(rz.view_cache) == 2 and torch.equal(img_sh3, img_sh)
+    # per-call temporaries (what the reference's getters produce) never become entries
+    for _ in range(3):
+        tmp = {k: v.clone() for k, v in geo.items()}
+        GaussianRasterizer(rs)(means2D=torch.zeros_like(geo["means3D"]), shs=shs, **tmp)
+    assert len(rz.view_cache) == 2
     rz.view_cache.enabled = False
     try:
         img_sh_ref = GaussianRasterizer(rs)(means2D=torch.zeros_like(geo["means3D"]), shs=shs, **geo)[0]
