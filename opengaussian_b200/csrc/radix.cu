@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_pass_kernel(const KeyT
     __shared__ uint32_t s_wh[RS_WARPS * RS_RADIX];   // per-warp digit counters -> exclusive warp offsets
     __shared__ uint32_t s_dstart[RS_RADIX];          // local exclusive start of each digit in the tile
     __shared__ uint32_t s_gbase[RS_RADIX];           // global position of local sorted slot 0 of the digit
-    __shared__ KeyT s_keys[TILE];
-    __shared__ uint32_t s_vals[TILE];
+    __shared__ __align__(16) KeyT s_keys[TILE];
+    __shared__ __align__(16) uint32_t s_vals[TILE];
     __shared__ uint32_t s_tile, s_tile_valid;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,16 +131,49 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_pass_kernel(const KeyT
     uint32_t rank[ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* wh = s_wh + warp * RS_RADIX;
-    uint32_t val[ITEMS];   // values are fetched with the keys: their latency hides behind the ranking
+    uint32_t val[ITEMS];
+    // Whole tiles come in through the reorder buffers: every thread issues its share of the tile's keys AND values as
+    // 16-byte loads back to back (one DRAM round trip for the CTA), stores them to shared memory and picks up its
+    // warp-striped items from there.  The per-item form below compiled to 32 narrow loads per thread of which ptxas
+    // (128-register budget) issued eleven key loads together, the other five each directly in front of its first use,
+    // and the value loads only after the ranking -- seven exposed round trips per tile with two CTAs per SM to hide them
+    // (ncu source page: the first use of each late key is the kernel's top stall site after the scatter).
+    constexpr int NK = (int)(ITEMS * sizeof(KeyT) / 16), NV = ITEMS / 4;
+    // (Not for the look-back variant: the depth sort's 245 tiles are one wave whose passes are bound by the chain
+    // rank -> publish -> look back; the staging barrier in front of the ranking made it 8 us slower, measured.)
+    const bool whole = !LOOKBACK && NK > 0 && NK * 16 == (int)(ITEMS * sizeof(KeyT)) && (ITEMS % 4) == 0 && tile_n == (uint32_t)TILE &&
+                       (((uintptr_t)(kin + tile_start) | (uintptr_t)(vin + tile_start)) & 15) == 0;
+    if (whole) {
+        const uint4* ksrc = reinterpret_cast<const uint4*>(kin + tile_start);
+        const uint4* vsrc = reinterpret_cast<const uint4*>(vin + tile_start);
+        uint4 qk[NK > 0 ? NK : 1], qv[NV > 0 ? NV : 1];
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const uint32_t idx = wbase + i * 32 + lane;
-        key[i] = idx < n ? (uint32_t)kin[idx] : 0xFFFFFFFFu;
-    }
+        for (int u = 0; u < NK; u++) qk[u] = __ldg(ksrc + tid + u * RS_THREADS);
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const uint32_t idx = wbase + i * 32 + lane;
-        val[i] = idx < n ? vin[idx] : 0u;
+        for (int u = 0; u < NV; u++) qv[u] = __ldg(vsrc + tid + u * RS_THREADS);
+#pragma unroll
+        for (int u = 0; u < NK; u++) reinterpret_cast<uint4*>(s_keys)[tid + u * RS_THREADS] = qk[u];
+#pragma unroll
+        for (int u = 0; u < NV; u++) reinterpret_cast<uint4*>(s_vals)[tid + u * RS_THREADS] = qv[u];
+        __syncthreads();
+        const int lbase = warp * (32 * ITEMS) + lane;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            key[i] = (uint32_t)s_keys[lbase + i * 32];
+            val[i] = s_vals[lbase + i * 32];
+        }
+        // the buffers are next written by the reorder phase, behind the barriers of the ranking
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t idx = wbase + i * 32 + lane;
+            key[i] = idx < n ? (uint32_t)kin[idx] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t idx = wbase + i * 32 + lane;
+            val[i] = idx < n ? vin[idx] : 0u;
+        }
     }
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
